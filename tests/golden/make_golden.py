@@ -1,0 +1,265 @@
+"""Generate the golden fixtures by running the REFERENCE code itself on CPU fp32.
+
+Run in the build container only (needs the read-only checkout at /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference holds no tests or golden vectors for this path, so
+these fixtures are the parity pin: inputs, deterministic weights and the
+reference's outputs/gradients, produced with fixed seeds.  Shims (none touches
+arithmetic): ``torch.tensor`` module alias for models/utils.py:2, and
+``Tensor.cuda`` made a no-op for the hard-coded ``.cuda()`` calls
+(generator.py:59-60, utils.py:117-140).
+"""
+import os
+import sys
+import types
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+REF = os.environ.get('AG2V_REFERENCE', '/root/reference')
+
+shim = types.ModuleType('torch.tensor')
+shim.Tensor = torch.Tensor
+sys.modules['torch.tensor'] = shim
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+torch.Tensor.cuda = lambda self, *a, **k: self
+torch.Tensor.get_device = lambda self: 0
+
+from _util import det_state, det_tensor  # noqa: E402
+from ag2video_b200.config import cater_vocab, synthetic_batch  # noqa: E402
+
+from models.graph_models.graph import GraphTripleConv  # noqa: E402
+from models.layout import boxes_to_layout, masks_to_layout  # noqa: E402
+from models.bilinear import crop_bbox_batch  # noqa: E402
+from models.spade_models.networks.normalization import SPADE  # noqa: E402
+from models.spade_models.networks.architecture import SPADEResnetBlock  # noqa: E402
+from models.graph_models.model import Acts2LayoutModel  # noqa: E402
+from models.meta_models import AG2VideoModel  # noqa: E402
+from data.args import parser, init_args  # noqa: E402
+
+torch.manual_seed(0)
+torch.set_num_threads(8)
+
+
+def save(name, obj):
+    path = os.path.join(HERE, name)
+    torch.save(obj, path)
+    print('%-22s %8.1f KB' % (name, os.path.getsize(path) / 1024))
+
+
+def load_det(module, seed):
+    module.load_state_dict(det_state(module.state_dict(), seed), strict=True)
+
+
+def grads_of(module):
+    return {k.replace('.module.', '.'): p.grad.clone() for k, p in module.named_parameters()
+            if p.grad is not None}
+
+
+def ref_opt(argv):
+    opt = parser.parse_args(argv + ['--gpu_ids', '-1', '--use_cuda', '0', '--no_vgg_loss'])
+    opt.vocab = cater_vocab()
+    init_args(opt)
+    return opt
+
+
+# ---------------------------------------------------------------- K1 ------
+def gconv_case():
+    dims = dict(obj_input_dim=24, object_output_dim=16, predicate_input_dim=16,
+                predicate_output_dim=16, hidden_dim=32, num_attributes=4)
+    layer = GraphTripleConv(**dims)
+    load_det(layer, 11)
+    B, O, E = 2, 5, 7
+    obj = det_tensor('gconv.obj', (B, O, 24), 1).requires_grad_()
+    pred = det_tensor('gconv.pred', (B, E, 16), 1).requires_grad_()
+    # self loop, repeated nodes, node 4 isolated in clip 0, masked edges
+    edges = torch.tensor([[[0, 1], [1, 1], [2, 0], [3, 2], [0, 3], [2, 2], [1, 0]],
+                          [[4, 0], [0, 4], [1, 2], [2, 1], [3, 3], [4, 4], [0, 0]]])
+    ind = torch.tensor([[1, 1, 0, 1, 1, 0, 1], [1, 0, 1, 1, 1, 1, 0]], dtype=torch.bool)
+    new_obj, new_p = layer(obj, pred, edges, ind)
+    c1, c2 = det_tensor('gconv.c1', new_obj.shape, 1), det_tensor('gconv.c2', new_p.shape, 1)
+    ((new_obj * c1).sum() + (new_p * c2).sum()).backward()
+    save('gconv.pt', dict(dims=dims, state=layer.state_dict(), obj=obj.detach(), pred=pred.detach(),
+                          edges=edges, ind=ind, new_obj=new_obj.detach(), new_p=new_p.detach(),
+                          c1=c1, c2=c2, dobj=obj.grad, dpred=pred.grad, dparams=grads_of(layer)))
+
+
+def gconv_net_case():
+    first = dict(obj_input_dim=64, object_output_dim=16, predicate_input_dim=16,
+                 predicate_output_dim=16, hidden_dim=32, num_attributes=4)
+    rest = dict(first, obj_input_dim=16)
+    layers = torch.nn.ModuleList([GraphTripleConv(**first), GraphTripleConv(**rest), GraphTripleConv(**rest)])
+    holder = torch.nn.Module()
+    holder.gconvs = layers
+    load_det(holder, 12)
+    B, O, E = 2, 6, 9
+    g = torch.Generator().manual_seed(5)
+    obj = det_tensor('net.obj', (B, O, 64), 1).requires_grad_()
+    pred = det_tensor('net.pred', (B, E, 16), 1).requires_grad_()
+    edges = torch.randint(0, O, (B, E, 2), generator=g)
+    ind = torch.rand(B, E, generator=g) > 0.25
+    o, p = obj, pred
+    for l in layers:
+        o, p = l(o, p, edges, ind)
+    c1, c2 = det_tensor('net.c1', o.shape, 1), det_tensor('net.c2', p.shape, 1)
+    ((o * c1).sum() + (p * c2).sum()).backward()
+    save('gconv_net.pt', dict(layers=[first, rest, rest], state=holder.state_dict(), obj=obj.detach(),
+                              pred=pred.detach(), edges=edges, ind=ind, new_obj=o.detach(),
+                              new_p=p.detach(), c1=c1, c2=c2, dobj=obj.grad, dpred=pred.grad,
+                              dparams=grads_of(holder)))
+
+
+# ---------------------------------------------------------------- K2 ------
+def layout_case():
+    cases = {}
+    boxes_a = torch.tensor([[0.10, 0.20, 0.30, 0.25], [0.00, 0.00, 0.00, 0.00], [0.55, 0.40, 0.219, 0.292],
+                            [0.85, 0.80, 0.30, 0.30], [0.50, 0.50, 0.02, 0.02], [-0.10, 0.30, 0.40, 0.20]])
+    # literal boxes of the reference's stale demo (models/layout.py:246-252), used as xywh
+    boxes_demo = torch.tensor([[0.25, 0.125, 0.5, 0.875], [0, 0, 1, 0.25], [0.6125, 0, 0.875, 1],
+                               [0, 0.8, 1, 1.0], [0.25, 0.125, 0.5, 0.875], [0.6125, 0, 0.875, 1]])
+    boxes_pad = torch.tensor([[0.2, 0.2, 0.156, 0.208], [-1., -1., -1., -1.], [0.0, 0.0, 1.0, 1.0]])
+    specs = [('mixed32', boxes_a, 8, 32, None, 'sum'), ('demo64', boxes_demo, 4, 64, None, 'sum'),
+             ('rect', boxes_a, 5, 24, 40, 'sum'), ('avg', boxes_a, 3, 16, None, 'avg'),
+             ('padbox', boxes_pad, 4, 32, None, 'sum'), ('cater128', None, 16, 128, None, 'sum')]
+    for name, boxes, D, H, W, pooling in specs:
+        if boxes is None:
+            batch = synthetic_batch(B=1, F=1, image_size=8, seed=3, with_images=False)
+            boxes = batch['boxes'][0, 0, :-1].clone()
+        vecs = det_tensor('layout.%s' % name, (boxes.shape[0], D), 2).requires_grad_()
+        out = boxes_to_layout(vecs, boxes, H, W, pooling=pooling)
+        cot = det_tensor('layout.cot.%s' % name, out.shape, 2)
+        (out * cot).sum().backward()
+        cases[name] = dict(vecs=vecs.detach(), boxes=boxes, H=H, W=W, pooling=pooling,
+                           out=out.detach(), cot=cot, dvecs=vecs.grad.clone())
+    save('layout.pt', cases)
+
+
+def masks_case():
+    cases = {}
+    g = torch.Generator().manual_seed(9)
+    boxes = torch.tensor([[0.10, 0.20, 0.30, 0.25], [0.25, 0.30, 0.40, 0.40], [0.55, 0.10, 0.219, 0.292],
+                          [0.05, 0.60, 0.50, 0.30]])
+    for name, M, H, test_mode in [('m5_train', 5, 32, False), ('m5_test', 5, 32, True),
+                                  ('m16_train', 16, 48, False), ('m16_test', 16, 48, True)]:
+        masks = (torch.rand(4, M, M, generator=g) > 0.35).float()
+        if M == 16:
+            masks = masks * torch.rand(4, M, M, generator=g)
+        vecs = det_tensor('masks.%s' % name, (4, 6), 3).requires_grad_()
+        out = masks_to_layout(vecs, boxes, masks, H, test_mode=test_mode)
+        cot = det_tensor('masks.cot.%s' % name, out.shape, 3)
+        (out * cot).sum().backward()
+        cases[name] = dict(vecs=vecs.detach(), boxes=boxes, masks=masks, H=H, test_mode=test_mode,
+                           out=out.detach(), cot=cot, dvecs=vecs.grad.clone())
+    save('masks_layout.pt', cases)
+
+
+def crop_case():
+    vocab = cater_vocab()
+    batch = synthetic_batch(B=2, F=2, image_size=24, seed=21, n_objects=None)
+    imgs = batch['imgs'].clone().requires_grad_()
+    boxes = batch['boxes'].clone()
+    boxes[0, 1, 1] = 0.0                      # an all-zero box is dropped (bilinear.py:81-83)
+    crops, objs_flat = crop_bbox_batch(imgs, batch['objs'], boxes, 8, vocab=vocab)
+    cots = [det_tensor('crop.cot.%d' % i, c.shape, 4) for i, c in enumerate(crops)]
+    sum((c * k).sum() for c, k in zip(crops, cots)).backward()
+    save('crop.pt', dict(imgs=imgs.detach(), objs=batch['objs'], boxes=boxes, HH=8,
+                         crops=[c.detach() for c in crops], objs_flat=objs_flat, cots=cots,
+                         dimgs=imgs.grad.clone()))
+
+
+# ---------------------------------------------------------------- K3 ------
+def spade_case():
+    cases = {}
+    for name, C, L, r, Hs, B in [('c16_r8', 16, 8, 8, 32, 2), ('c8_r16', 8, 16, 16, 16, 3)]:
+        m = SPADE('spadesyncbatch3x3', C, L)
+        load_det(m, 31)
+        m.train()
+        x = det_tensor('spade.x.%s' % name, (B, C, r, r), 5).mul(1.5).add(0.3).requires_grad_()
+        seg = det_tensor('spade.seg.%s' % name, (B, L, Hs, Hs), 5).requires_grad_()
+        state0 = {k: v.clone() for k, v in m.state_dict().items()}
+        out = m(x, seg)
+        cot = det_tensor('spade.cot.%s' % name, out.shape, 5)
+        (out * cot).sum().backward()
+        state1 = {k: v.clone() for k, v in m.state_dict().items()}
+        m.eval()
+        with torch.no_grad():
+            out_eval = m(x, seg)
+        cases[name] = dict(C=C, L=L, state=state0, state_after=state1, x=x.detach(), seg=seg.detach(),
+                           out=out.detach(), cot=cot, dx=x.grad.clone(), dseg=seg.grad.clone(),
+                           dparams=grads_of(m), out_eval=out_eval)
+    save('spade.pt', cases)
+
+
+def block_case():
+    cases = {}
+    opt = types.SimpleNamespace(norm_G='spectralspadesyncbatch3x3', semantic_nc=8)
+    for name, fin, fout in [('b16_8', 16, 8), ('b8_8', 8, 8)]:
+        m = SPADEResnetBlock(fin, fout, opt)
+        load_det(m, 41)
+        m.train()
+        x = det_tensor('block.x.%s' % name, (2, fin, 8, 8), 6).requires_grad_()
+        seg = det_tensor('block.seg.%s' % name, (2, 8, 16, 16), 6).requires_grad_()
+        state0 = {k: v.clone() for k, v in m.state_dict().items()}
+        out = m(x, seg)
+        cot = det_tensor('block.cot.%s' % name, out.shape, 6)
+        (out * cot).sum().backward()
+        cases[name] = dict(fin=fin, fout=fout, state=state0, x=x.detach(), seg=seg.detach(),
+                           out=out.detach(), cot=cot, dx=x.grad.clone(), dseg=seg.grad.clone(),
+                           dparams=grads_of(m),
+                           state_after={k: v.clone() for k, v in m.state_dict().items()})
+    save('spade_block.pt', cases)
+
+
+# ------------------------------------------------------------ callers -----
+def acts2layout_case():
+    opt = ref_opt(['--embedding_dim', '16', '--gconv_dim', '16', '--gconv_hidden_dim', '32',
+                   '--image_size', '32,32'])
+    m = Acts2LayoutModel(opt)
+    load_det(m, 51)
+    batch = synthetic_batch(B=2, F=4, image_size=32, seed=77, with_images=False)
+    obj_vecs, boxes_pred, extra = m(batch['objs'], batch['triplets'], batch['actions'], batch['boxes'])
+    c1, c2 = det_tensor('a2l.c1', obj_vecs.shape, 7), det_tensor('a2l.c2', boxes_pred.shape, 7)
+    ((obj_vecs * c1).sum() + (boxes_pred * c2).sum()).backward()
+    save('acts2layout.pt', dict(over=dict(embedding_dim=16, gconv_dim=16, gconv_hidden_dim=32),
+                                seed=51, batch_seed=77, batch={k: v for k, v in batch.items() if v is not None},
+                                obj_vecs=obj_vecs.detach(), boxes_pred=boxes_pred.detach(),
+                                temporal_triplets=extra[1], rel_t=extra[2], c1=c1, c2=c2,
+                                dparams=grads_of(m)))
+
+
+def generator_case():
+    """BASELINE config 1: generator fwd+bwd, 64x64, batch 2, frames_per_action 4."""
+    opt = ref_opt(['--image_size', '64,64', '--batch_size', '2'])
+    m = AG2VideoModel(opt, torch.device('cpu'))
+    load_det(m, 61)
+    m.train()
+    batch = synthetic_batch(B=2, F=4, image_size=64, seed=99)
+    out = m(batch['imgs'], batch['objs'], batch['triplets'], batch['actions'],
+            boxes_gt=batch['boxes'], test_mode=False, use_gt=True)
+    imgs_pred, boxes_pred, flows, conf, _ = out
+    loss = (imgs_pred - batch['imgs']).abs().mean() + (boxes_pred - batch['boxes'])[:, 1:].abs().mean()
+    loss.backward()
+    grads = grads_of(m)
+    picks = ['layout_to_video.netG.up_3.norm_1.mlp_gamma.weight',
+             'layout_to_video.netG.head_0.norm_0.mlp_shared.0.weight',
+             'layout_to_video.netG.fc.bias',
+             'acts_to_objs.gconvs.0.net1.0.weight', 'acts_to_objs.gconvs.2.net2.2.weight',
+             'acts_to_boxes.box_net.2.weight', 'layout_to_video.attribute_embedding.att_emb_1.weight']
+    save('generator64.pt', dict(seed=61, batch_seed=99, imgs_pred=imgs_pred.detach(),
+                                boxes_pred=boxes_pred.detach(), flows=flows.detach(), conf=conf.detach(),
+                                loss=loss.detach(),
+                                grad_norms={k: float(v.norm()) for k, v in grads.items()},
+                                grad_picks={k: grads[k].flatten()[:4096].clone() for k in picks}))
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['gconv', 'gconv_net', 'layout', 'masks', 'crop', 'spade', 'block',
+                             'acts2layout', 'generator']
+    for w in which:
+        globals()['%s_case' % w]()

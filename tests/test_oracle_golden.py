@@ -1,0 +1,160 @@
+"""Pin the oracle: every restated function against fixtures produced by the
+reference code itself (tests/golden/make_golden.py).  CPU only."""
+import types
+
+import pytest
+import torch
+
+from _util import det_state, golden, max_rel
+from ag2video_b200.config import make_opt, synthetic_batch
+from oracle import networks as onet
+from oracle import ops as oops
+
+TOL = 2e-6      # same torch build, same primitives: differences are summation-order noise
+
+
+def _grads(module):
+    return {k: p.grad for k, p in module.named_parameters() if p.grad is not None}
+
+
+def _check_grads(got, want, tol=TOL):
+    assert set(got) == set(want)
+    for k in want:
+        assert max_rel(got[k], want[k]) <= tol, k
+
+
+def test_gconv_matches_reference():
+    g = golden('gconv.pt')
+    layer = oops.GraphTripleConv(**g['dims'])
+    layer.load_state_dict(g['state'], strict=True)
+    obj, pred = g['obj'].clone().requires_grad_(), g['pred'].clone().requires_grad_()
+    new_obj, new_p = layer(obj, pred, g['edges'], g['ind'])
+    assert torch.equal(new_obj, g['new_obj']) or max_rel(new_obj, g['new_obj']) <= TOL
+    assert max_rel(new_p, g['new_p']) <= TOL
+    ((new_obj * g['c1']).sum() + (new_p * g['c2']).sum()).backward()
+    assert max_rel(obj.grad, g['dobj']) <= TOL
+    assert max_rel(pred.grad, g['dpred']) <= TOL
+    _check_grads(_grads(layer), g['dparams'])
+
+
+def test_gconv_net_matches_reference():
+    g = golden('gconv_net.pt')
+    net = oops.GraphTripleConvNet(g['layers'])
+    net.load_state_dict(g['state'], strict=True)
+    obj, pred = g['obj'].clone().requires_grad_(), g['pred'].clone().requires_grad_()
+    o, p = net(obj, pred, g['edges'], g['ind'])
+    assert max_rel(o, g['new_obj']) <= TOL and max_rel(p, g['new_p']) <= TOL
+    ((o * g['c1']).sum() + (p * g['c2']).sum()).backward()
+    assert max_rel(obj.grad, g['dobj']) <= TOL and max_rel(pred.grad, g['dpred']) <= TOL
+    _check_grads(_grads(net), g['dparams'])
+
+
+@pytest.mark.parametrize('name', ['mixed32', 'demo64', 'rect', 'avg', 'padbox', 'cater128'])
+def test_boxes_to_layout_matches_reference(name):
+    c = golden('layout.pt')[name]
+    vecs = c['vecs'].clone().requires_grad_()
+    out = oops.boxes_to_layout(vecs, c['boxes'], c['H'], c['W'], pooling=c['pooling'])
+    assert torch.equal(out != 0, c['out'] != 0), 'pixel support must be bit-exact'
+    assert max_rel(out, c['out']) <= TOL
+    (out * c['cot']).sum().backward()
+    assert max_rel(vecs.grad, c['dvecs']) <= TOL
+
+
+@pytest.mark.parametrize('name', ['m5_train', 'm5_test', 'm16_train', 'm16_test'])
+def test_masks_to_layout_matches_reference(name):
+    c = golden('masks_layout.pt')[name]
+    vecs = c['vecs'].clone().requires_grad_()
+    out = oops.masks_to_layout(vecs, c['boxes'], c['masks'], c['H'], test_mode=c['test_mode'])
+    assert torch.equal(out != 0, c['out'] != 0)
+    assert max_rel(out, c['out']) <= TOL
+    (out * c['cot']).sum().backward()
+    assert max_rel(vecs.grad, c['dvecs']) <= TOL
+
+
+def test_crop_bbox_batch_matches_reference():
+    from ag2video_b200.config import cater_vocab
+    c = golden('crop.pt')
+    imgs = c['imgs'].clone().requires_grad_()
+    crops, flat = oops.crop_bbox_batch(imgs, c['objs'], c['boxes'], c['HH'], vocab=cater_vocab())
+    assert len(crops) == len(c['crops'])
+    for got, want, gf, wf in zip(crops, c['crops'], flat, c['objs_flat']):
+        assert got.shape == want.shape and max_rel(got, want) <= TOL
+        assert torch.equal(gf, wf)
+    sum((a * k).sum() for a, k in zip(crops, c['cots'])).backward()
+    assert max_rel(imgs.grad, c['dimgs']) <= TOL
+
+
+@pytest.mark.parametrize('name', ['c16_r8', 'c8_r16'])
+def test_spade_matches_reference(name):
+    c = golden('spade.pt')[name]
+    m = oops.SPADE('spadesyncbatch3x3', c['C'], c['L'])
+    m.load_state_dict(c['state'], strict=True)
+    m.train()
+    x, seg = c['x'].clone().requires_grad_(), c['seg'].clone().requires_grad_()
+    out = m(x, seg)
+    assert max_rel(out, c['out']) <= TOL
+    (out * c['cot']).sum().backward()
+    assert max_rel(x.grad, c['dx']) <= 5e-6 and max_rel(seg.grad, c['dseg']) <= 5e-6
+    _check_grads(_grads(m), c['dparams'], 5e-6)
+    for k, v in c['state_after'].items():
+        assert max_rel(m.state_dict()[k].float(), v.float()) <= TOL, k
+    m.eval()
+    with torch.no_grad():
+        assert max_rel(m(x, seg), c['out_eval']) <= TOL
+
+
+@pytest.mark.parametrize('name', ['b16_8', 'b8_8'])
+def test_spade_resnet_block_matches_reference(name):
+    c = golden('spade_block.pt')[name]
+    opt = types.SimpleNamespace(norm_G='spectralspadesyncbatch3x3', semantic_nc=8)
+    m = oops.SPADEResnetBlock(c['fin'], c['fout'], opt)
+    m.load_state_dict(c['state'], strict=True)
+    m.train()
+    x, seg = c['x'].clone().requires_grad_(), c['seg'].clone().requires_grad_()
+    out = m(x, seg)
+    assert max_rel(out, c['out']) <= TOL
+    (out * c['cot']).sum().backward()
+    assert max_rel(x.grad, c['dx']) <= 5e-6 and max_rel(seg.grad, c['dseg']) <= 5e-6
+    _check_grads(_grads(m), c['dparams'], 5e-6)
+    for k, v in c['state_after'].items():
+        assert max_rel(m.state_dict()[k].float(), v.float()) <= TOL, k
+
+
+def test_acts2layout_matches_reference():
+    c = golden('acts2layout.pt')
+    opt = make_opt(32, **c['over'])
+    m = onet.Acts2LayoutModel(opt)
+    m.load_state_dict(det_state(m.state_dict(), c['seed']), strict=True)
+    b = c['batch']
+    obj_vecs, boxes_pred, extra = m(b['objs'], b['triplets'], b['actions'], b['boxes'])
+    assert torch.equal(extra[1], c['temporal_triplets'])
+    assert max_rel(extra[2], c['rel_t']) <= TOL
+    assert max_rel(obj_vecs, c['obj_vecs']) <= TOL and max_rel(boxes_pred, c['boxes_pred']) <= TOL
+    ((obj_vecs * c['c1']).sum() + (boxes_pred * c['c2']).sum()).backward()
+    _check_grads(_grads(m), c['dparams'], 5e-6)
+
+
+def test_generator64_matches_reference():
+    """BASELINE config 1 end to end: the whole oracle generator against the
+    reference's AG2VideoModel at 64x64, batch 2, 4 frames."""
+    c = golden('generator64.pt')
+    torch.manual_seed(0)
+    opt = make_opt(64, batch_size=2)
+    m = onet.AG2VideoModel(opt)
+    m.load_state_dict(det_state(m.state_dict(), c['seed']), strict=True)
+    m.train()
+    b = synthetic_batch(B=2, F=4, image_size=64, seed=c['batch_seed'])
+    imgs_pred, boxes_pred, flows, conf, _ = m(b['imgs'], b['objs'], b['triplets'], b['actions'],
+                                              boxes_gt=b['boxes'], use_gt=True)
+    assert max_rel(imgs_pred, c['imgs_pred']) <= 2e-5
+    assert max_rel(boxes_pred, c['boxes_pred']) <= 2e-5
+    assert max_rel(flows, c['flows']) <= 2e-4
+    loss = (imgs_pred - b['imgs']).abs().mean() + (boxes_pred - b['boxes'])[:, 1:].abs().mean()
+    assert abs(float(loss) - float(c['loss'])) <= 1e-5 * abs(float(c['loss']))
+    loss.backward()
+    grads = _grads(m)
+    for k, v in c['grad_picks'].items():
+        assert max_rel(grads[k].flatten()[:4096], v) <= 5e-4, k
+    bad = [k for k, n in c['grad_norms'].items()
+           if abs(float(grads[k].norm()) - n) > 2e-3 * max(n, 1e-6)]
+    assert not bad, bad[:5]
