@@ -1,0 +1,42 @@
+// Shared definitions for the SPADE kernels (reference:
+// models/spade_models/networks/normalization.py:66-110, architecture.py:50-68).
+//
+// Internal layout: every activation the K3 kernels touch is NHWC fp32 (logical
+// NCHW tensors in torch.channels_last memory format), so the implicit-GEMM
+// reduction index (ky, kx, c) is contiguous in c.
+//
+// gamma/beta packing ("gb8"): the two modulation convolutions run as ONE GEMM
+// whose output columns interleave gamma and beta in groups of eight channels:
+//     n = 16*(c/8) + 8*is_beta + (c%8)
+// so that the thread that owns gamma[p,c] in the accumulator also owns beta[p,c]
+// and the epilogue can apply  out = xhat*(1+gamma)+beta  without a round trip.
+#pragma once
+#include "common.cuh"
+
+namespace ag2v {
+
+enum ConvEpilogue : int {
+  EPI_BIAS = 0,        // out = acc + bias
+  EPI_BIAS_RELU = 1,   // out = relu(acc + bias)                    (mlp_shared, normalization.py:103)
+  EPI_SPADE = 2,       // out = act((x-mean)*rstd*(1+g)+b), g/b = acc + bias (normalization.py:104-108)
+  EPI_GATE = 3,        // out = gate > 0 ? acc : 0                  (backward through the ReLU)
+  EPI_ACCUM = 4,       // out += acc   (gradient w.r.t. the shared full-resolution segmap)
+};
+
+struct ConvParams {
+  // input view [B, R, R(w), Cin]: element strides for b / y / x, channels contiguous
+  const float* in; long long in_sb, in_sy, in_sx;
+  int B, Hh, Ww, Cin;
+  const float* wpk;          // packed weights [9][Nout][Cin]
+  const float* bias;         // [Nout] in packed column order, may be null
+  int Nout;
+  float* out; long long out_sb, out_sy, out_sx;   // output view [B, Hh, Ww, Nout]
+  // EPI_SPADE: Nout == 2*C in gb8 order; out is [.., C]
+  const float* x; const float* mean; const float* rstd; float* gamma_out; float slope; int C;
+  // EPI_GATE
+  const float* gate;
+};
+
+__host__ __device__ inline int gb8_col(int c, int is_beta) { return 16 * (c >> 3) + 8 * is_beta + (c & 7); }
+
+}  // namespace ag2v

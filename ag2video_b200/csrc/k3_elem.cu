@@ -1,0 +1,343 @@
+// K3 — HBM-bound pieces of SPADE: batch-norm statistics, the backward
+// element-wise passes, weight (un)packing.  All activations are NHWC fp32.
+// Per-channel reductions are two-level and fixed-order (deterministic): per-CTA
+// partials in fp32, combined in double.
+#include "k3_common.cuh"
+
+namespace ag2v {
+
+constexpr int kElemThreads = 256;
+constexpr int kMaxSplit = 592;       // 4 CTAs per SM
+
+struct ChanGeom { int cx, py, chunks, nsplit; };
+
+static ChanGeom chan_geom(long long P, int C) {
+  ChanGeom g;
+  int c4 = C / 4, cx = 1;
+  while (cx < c4 && cx < kElemThreads) cx <<= 1;
+  g.cx = cx; g.py = kElemThreads / cx; g.chunks = ceil_div(c4, cx);
+  long long ns = ceil_div_ll(P, (long long)g.py * 8);
+  g.nsplit = (int)(ns < 1 ? 1 : (ns > kMaxSplit ? kMaxSplit : ns));
+  return g;
+}
+
+// MODE 0: s0 = sum x, s1 = sum x^2                      (F.batch_norm statistics)
+// MODE 1: SPADE backward, pass 1 (see spade_bwd_pre below)
+struct ChanArgs {
+  const float* x; long long P; int C;
+  float* part;                      // [nsplit][NS][C]
+  // MODE 1
+  const float* dout; const float* out; const float* gamma; const float* mean; const float* rstd;
+  float* dgb; float* dxhat; float slope; int act;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, ChanGeom gm) {
+  constexpr int NS = MODE == 0 ? 2 : 4;
+  __shared__ float4 red[kElemThreads];
+  const int tx = threadIdx.x % gm.cx, ty = threadIdx.x / gm.cx;
+  const int C = a.C, c4n = C >> 2;
+  for (int chunk = 0; chunk < gm.chunks; ++chunk) {
+    const int c4 = chunk * gm.cx + tx;
+    const bool live = c4 < c4n;
+    const int c = c4 << 2;
+    float4 s[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu;
+    if (MODE == 1 && live) { mu = *reinterpret_cast<const float4*>(a.mean + c); rs = *reinterpret_cast<const float4*>(a.rstd + c); }
+    if (live) {
+      for (long long p = (long long)blockIdx.x * gm.py + ty; p < a.P; p += (long long)gm.nsplit * gm.py) {
+        const size_t off = (size_t)p * C + c;
+        const float4 xv = *reinterpret_cast<const float4*>(a.x + off);
+        if (MODE == 0) {
+          s[0].x += xv.x; s[0].y += xv.y; s[0].z += xv.z; s[0].w += xv.w;
+          s[1].x = fmaf(xv.x, xv.x, s[1].x); s[1].y = fmaf(xv.y, xv.y, s[1].y);
+          s[1].z = fmaf(xv.z, xv.z, s[1].z); s[1].w = fmaf(xv.w, xv.w, s[1].w);
+        } else {
+          const float4 dv = *reinterpret_cast<const float4*>(a.dout + off);
+          const float4 ov = *reinterpret_cast<const float4*>(a.out + off);
+          const float4 gv = *reinterpret_cast<const float4*>(a.gamma + off);
+          float4 g, xh, dxh;
+          const float sl = a.slope;
+          g.x = (a.act && !(ov.x > 0.f)) ? dv.x * sl : dv.x;
+          g.y = (a.act && !(ov.y > 0.f)) ? dv.y * sl : dv.y;
+          g.z = (a.act && !(ov.z > 0.f)) ? dv.z * sl : dv.z;
+          g.w = (a.act && !(ov.w > 0.f)) ? dv.w * sl : dv.w;
+          xh.x = (xv.x - mu.x) * rs.x; xh.y = (xv.y - mu.y) * rs.y;
+          xh.z = (xv.z - mu.z) * rs.z; xh.w = (xv.w - mu.w) * rs.w;
+          const float4 dgam = make_float4(g.x * xh.x, g.y * xh.y, g.z * xh.z, g.w * xh.w);
+          dxh.x = g.x * (1.f + gv.x); dxh.y = g.y * (1.f + gv.y);
+          dxh.z = g.z * (1.f + gv.z); dxh.w = g.w * (1.f + gv.w);
+          float* row = a.dgb + (size_t)p * 2 * C;
+          *reinterpret_cast<float4*>(row + gb8_col(c, 0)) = dgam;
+          *reinterpret_cast<float4*>(row + gb8_col(c, 1)) = g;
+          *reinterpret_cast<float4*>(a.dxhat + off) = dxh;
+          s[0].x += g.x; s[0].y += g.y; s[0].z += g.z; s[0].w += g.w;
+          s[1].x += dgam.x; s[1].y += dgam.y; s[1].z += dgam.z; s[1].w += dgam.w;
+          s[2].x += dxh.x; s[2].y += dxh.y; s[2].z += dxh.z; s[2].w += dxh.w;
+          s[3].x = fmaf(dxh.x, xh.x, s[3].x); s[3].y = fmaf(dxh.y, xh.y, s[3].y);
+          s[3].z = fmaf(dxh.z, xh.z, s[3].z); s[3].w = fmaf(dxh.w, xh.w, s[3].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      __syncthreads();
+      red[threadIdx.x] = s[i];
+      __syncthreads();
+      if (ty == 0 && live) {
+        float4 t = red[tx];
+        for (int r = 1; r < gm.py; ++r) {
+          float4 u = red[r * gm.cx + tx];
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        *reinterpret_cast<float4*>(a.part + ((size_t)blockIdx.x * NS + i) * C + c) = t;
+      }
+    }
+  }
+}
+
+// sums[i][c] (double) = sum over splits of part[split][i][c], in split order
+__global__ void chan_reduce_kernel(const float* __restrict__ part, int nsplit, int NS, int C, double* __restrict__ sums) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NS * C) return;
+  const int i = idx / C, c = idx - i * C;
+  double acc = 0.0;
+  for (int s = 0; s < nsplit; ++s) acc += (double)part[((size_t)s * NS + i) * C + c];
+  sums[idx] = acc;
+}
+
+// F.batch_norm(training=True, momentum, eps): biased variance for normalisation,
+// unbiased for the running estimate (sync_batchnorm/batchnorm.py:63-68,128-145).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] / count;
+  double var = sums[C + c] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+  }
+}
+
+// eval mode: statistics are the running estimates
+__global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                     int C, float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = running_mean[c];
+  rstd[c] = 1.f / sqrtf(running_var[c] + eps);
+}
+
+// pass 2 of the SPADE backward: batch-norm input gradient, in place on dxhat.
+//   training: dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat));  eval: dx = rstd * dxhat
+__global__ void __launch_bounds__(kElemThreads)
+spade_bwd_dx_kernel(const float* __restrict__ x, float* __restrict__ dxhat, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const double* __restrict__ sums, double count, int training,
+                    long long P, int C) {
+  const long long n4 = P * (C >> 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (C >> 2)) << 2;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    float4 d = reinterpret_cast<float4*>(dxhat)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    if (training) {
+      const float m1x = (float)(sums[2 * C + c] / count), m2x = (float)(sums[3 * C + c] / count);
+      const float m1y = (float)(sums[2 * C + c + 1] / count), m2y = (float)(sums[3 * C + c + 1] / count);
+      const float m1z = (float)(sums[2 * C + c + 2] / count), m2z = (float)(sums[3 * C + c + 2] / count);
+      const float m1w = (float)(sums[2 * C + c + 3] / count), m2w = (float)(sums[3 * C + c + 3] / count);
+      d.x = rs.x * (d.x - m1x - (xv.x - mu.x) * rs.x * m2x);
+      d.y = rs.y * (d.y - m1y - (xv.y - mu.y) * rs.y * m2y);
+      d.z = rs.z * (d.z - m1z - (xv.z - mu.z) * rs.z * m2z);
+      d.w = rs.w * (d.w - m1w - (xv.w - mu.w) * rs.w * m2w);
+    } else {
+      d.x *= rs.x; d.y *= rs.y; d.z *= rs.z; d.w *= rs.w;
+    }
+    reinterpret_cast<float4*>(dxhat)[i] = d;
+  }
+}
+
+// Pack OIHW 3x3 weights for the implicit GEMMs.
+//   forward : dst[tap][n][ci]  = W(n)[co(n)][ci][tap]          rows = output columns
+//   dgrad   : dst[tap][ci][k]  = W(k)[co(k)][ci][8 - tap]      (transposed + flipped)
+// With two sources (gamma, beta) the combined channel index follows gb8_col.
+__global__ void pack_w3x3_kernel(const float* __restrict__ wa, const float* __restrict__ wb,
+                                 const float* __restrict__ ba, const float* __restrict__ bb, int Co, int Ci,
+                                 int dgrad, float* __restrict__ dst, float* __restrict__ bias_dst) {
+  const int Ntot = wb ? 2 * Co : Co;
+  const long long total = 9LL * Ntot * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int tap, n, ci;
+    if (!dgrad) { ci = (int)(i % Ci); n = (int)((i / Ci) % Ntot); tap = (int)(i / ((long long)Ci * Ntot)); }
+    else { n = (int)(i % Ntot); ci = (int)((i / Ntot) % Ci); tap = (int)(i / ((long long)Ci * Ntot)); }
+    int co = n, is_b = 0;
+    if (wb) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
+    const float* src = is_b ? wb : wa;
+    const int t = dgrad ? 8 - tap : tap;
+    dst[i] = src[((size_t)co * Ci + ci) * 9 + t];
+  }
+  if (bias_dst != nullptr && blockIdx.x == 0) {
+    for (int n = threadIdx.x; n < Ntot; n += blockDim.x) {
+      int co = n, is_b = 0;
+      if (wb) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
+      const float* b = is_b ? bb : ba;
+      bias_dst[n] = b ? b[co] : 0.f;
+    }
+  }
+}
+
+// Sum the split-K partials of a weight gradient and scatter them back to OIHW.
+//   part[split][tap][n][ci]  ->  dW(n)[co(n)][ci][tap]
+__global__ void unpack_dw_kernel(const float* __restrict__ part, int nsplit, int Co, int Ci, int two,
+                                 float* __restrict__ dwa, float* __restrict__ dwb) {
+  const int Ntot = two ? 2 * Co : Co;
+  const long long per = 9LL * Ntot * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Ci); const int n = (int)((i / Ci) % Ntot); const int tap = (int)(i / ((long long)Ci * Ntot));
+    float acc = 0.f;
+    for (int s = 0; s < nsplit; ++s) acc += part[(size_t)s * per + i];
+    int co = n, is_b = 0;
+    if (two) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
+    float* dst = is_b ? dwb : dwa;
+    dst[((size_t)co * Ci + ci) * 9 + tap] = acc;
+  }
+}
+
+// gb8-ordered per-column sums (double) -> the two bias gradients
+__global__ void unpack_db_kernel(const double* __restrict__ s_beta, const double* __restrict__ s_gamma, int C,
+                                 float* __restrict__ db_gamma, float* __restrict__ db_beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  db_gamma[c] = (float)s_gamma[c];
+  db_beta[c] = (float)s_beta[c];
+}
+
+__global__ void double_to_float_kernel(const double* __restrict__ src, int n, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+
+}  // namespace ag2v
+
+using namespace ag2v;
+
+static int chan_check(long long P, int C) {
+  AG2V_REQUIRE(P > 0 && C > 0 && C % 4 == 0, "per-channel reduction: need P > 0 and C %% 4 == 0 (P=%lld C=%d)", P, C);
+  return AG2V_OK;
+}
+
+// Floats needed for the partial buffer of a per-channel reduction with NS sums.
+extern "C" size_t ag2v_chan_partial_floats(long long P, int C, int NS) {
+  if (P <= 0 || C <= 0) return 0;
+  ChanGeom g = chan_geom(P, C);
+  return (size_t)g.nsplit * NS * C;
+}
+
+// sums[0..C) = sum x, sums[C..2C) = sum x^2 over the P rows of x [P, C] (doubles).
+extern "C" int ag2v_bn_stats(const float* x, long long P, int C, float* partial, double* sums, cudaStream_t stream) {
+  int rc = chan_check(P, C);
+  if (rc) return rc;
+  AG2V_REQUIRE(x && partial && sums, "bn_stats: null pointer");
+  ChanGeom g = chan_geom(P, C);
+  ChanArgs a{};
+  a.x = x; a.P = P; a.C = C; a.part = partial;
+  chan_partial_kernel<0><<<g.nsplit, kElemThreads, 0, stream>>>(a, g);
+  AG2V_LAUNCH_CHECK();
+  chan_reduce_kernel<<<ceil_div(2 * C, 256), 256, 0, stream>>>(partial, g.nsplit, 2, C, sums);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// mean/rstd from (possibly all-reduced) sums; updates running stats when given.
+extern "C" int ag2v_bn_finalize(const double* sums, double count, int C, float eps, float momentum,
+                                float* running_mean, float* running_var, float* mean, float* rstd,
+                                cudaStream_t stream) {
+  AG2V_REQUIRE(sums && mean && rstd && C > 0 && count > 0, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(sums, count, C, eps, momentum, running_mean, running_var, mean, rstd);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+extern "C" int ag2v_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
+                                  float* mean, float* rstd, cudaStream_t stream) {
+  AG2V_REQUIRE(running_mean && running_var && mean && rstd && C > 0, "bn_eval_stats: bad arguments");
+  bn_eval_stats_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(running_mean, running_var, C, eps, mean, rstd);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// SPADE backward, element-wise pass 1.  Inputs [P, C] NHWC: dout, out (post
+// activation), x, gamma (saved by the forward), mean/rstd [C].  Writes dgb [P, 2C]
+// (gb8 columns: d gamma = g*xhat, d beta = g), dxhat [P, C] and the four
+// per-channel sums (doubles, [4][C]): sum g, sum g*xhat, sum dxhat, sum dxhat*xhat.
+extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma,
+                                  const float* mean, const float* rstd, long long P, int C, int act,
+                                  float slope, float* dgb, float* dxhat, float* partial, double* sums,
+                                  cudaStream_t stream) {
+  int rc = chan_check(P, C);
+  if (rc) return rc;
+  AG2V_REQUIRE(C % 8 == 0, "spade_bwd_pre: C %% 8 == 0 required (C=%d)", C);
+  AG2V_REQUIRE(dout && out && x && gamma && mean && rstd && dgb && dxhat && partial && sums, "spade_bwd_pre: null pointer");
+  ChanGeom g = chan_geom(P, C);
+  ChanArgs a{};
+  a.x = x; a.P = P; a.C = C; a.part = partial; a.dout = dout; a.out = out; a.gamma = gamma;
+  a.mean = mean; a.rstd = rstd; a.dgb = dgb; a.dxhat = dxhat; a.slope = slope; a.act = act;
+  chan_partial_kernel<1><<<g.nsplit, kElemThreads, 0, stream>>>(a, g);
+  AG2V_LAUNCH_CHECK();
+  chan_reduce_kernel<<<ceil_div(4 * C, 256), 256, 0, stream>>>(partial, g.nsplit, 4, C, sums);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// SPADE backward pass 2: dxhat -> dx in place (sums as produced by spade_bwd_pre,
+// all-reduced across ranks by the caller under SyncBN; count = global element count).
+extern "C" int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean, const float* rstd,
+                                 const double* sums, double count, int training, long long P, int C,
+                                 cudaStream_t stream) {
+  int rc = chan_check(P, C);
+  if (rc) return rc;
+  AG2V_REQUIRE(x && dxhat && mean && rstd && sums, "spade_bwd_dx: null pointer");
+  long long n4 = P * (C / 4);
+  int blocks = (int)(ceil_div_ll(n4, kElemThreads * 4) > 4 * 148 * 8 ? 4 * 148 * 8 : ceil_div_ll(n4, kElemThreads * 4));
+  if (blocks < 1) blocks = 1;
+  spade_bwd_dx_kernel<<<blocks, kElemThreads, 0, stream>>>(x, dxhat, mean, rstd, sums, count, training, P, C);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// wa/wb: OIHW [Co, Ci, 3, 3] (wb null for a single conv); see pack_w3x3_kernel.
+extern "C" int ag2v_pack_w3x3(const float* wa, const float* wb, const float* ba, const float* bb, int Co, int Ci,
+                              int dgrad, float* dst, float* bias_dst, cudaStream_t stream) {
+  AG2V_REQUIRE(wa && dst && Co > 0 && Ci > 0, "pack_w3x3: bad arguments");
+  AG2V_REQUIRE(!wb || Co % 8 == 0, "pack_w3x3: gamma/beta packing needs Co %% 8 == 0");
+  long long total = 9LL * (wb ? 2 * Co : Co) * Ci;
+  int blocks = (int)(ceil_div_ll(total, 256) > 2368 ? 2368 : ceil_div_ll(total, 256));
+  pack_w3x3_kernel<<<blocks, 256, 0, stream>>>(wa, wb, ba, bb, Co, Ci, dgrad, dst, bias_dst);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+extern "C" int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
+                                 cudaStream_t stream) {
+  AG2V_REQUIRE(part && dwa && nsplit > 0 && Co > 0 && Ci > 0 && (!two || dwb), "unpack_dw3x3: bad arguments");
+  long long total = 9LL * (two ? 2 * Co : Co) * Ci;
+  int blocks = (int)(ceil_div_ll(total, 256) > 2368 ? 2368 : ceil_div_ll(total, 256));
+  unpack_dw_kernel<<<blocks, 256, 0, stream>>>(part, nsplit, Co, Ci, two, dwa, dwb);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+extern "C" int ag2v_double_to_float(const double* src, int n, float* dst, cudaStream_t stream) {
+  AG2V_REQUIRE(src && dst && n > 0, "double_to_float: bad arguments");
+  double_to_float_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(src, n, dst);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
