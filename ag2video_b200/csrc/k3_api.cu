@@ -1,0 +1,46 @@
+// C-ABI entry for the 3x3 implicit-GEMM convolution used by SPADE (forward convs
+// and input gradients).  Dispatch: the tcgen05/TMEM/TMA kernel (k3_conv_tc.cu)
+// for the shapes it supports, otherwise the generic mma.sync kernel
+// (k3_conv_mma.cu).  Both are GPU kernels of this library; there is no CPU or
+// vendor-library fallback.
+#include "k3_common.cuh"
+
+namespace ag2v {
+int conv3x3_check(const ConvParams& p, int epi);
+int conv3x3_mma(const ConvParams& p, int epi, int round_out, cudaStream_t stream);
+int conv3x3_tc(const ConvParams& p, int epi, int round_out, cudaStream_t stream);   // may return AG2V_ERR_UNSUPPORTED
+bool conv3x3_tc_supported(const ConvParams& p, int epi);
+}  // namespace ag2v
+
+using namespace ag2v;
+
+// impl: 0 = auto (tcgen05 when supported), 1 = force mma.sync, 2 = force tcgen05 (error if unsupported)
+extern "C" int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in_sx, int B, int Hh,
+                            int Ww, int Cin, const float* wpk, const float* bias, int Nout, float* out,
+                            long long out_sb, long long out_sy, long long out_sx, int epilogue, int round_out,
+                            const float* x, const float* mean, const float* rstd, float* gamma_out,
+                            float slope, int C, const float* gate, int impl, cudaStream_t stream) {
+  ConvParams p{};
+  p.in = in; p.in_sb = in_sb; p.in_sy = in_sy; p.in_sx = in_sx;
+  p.B = B; p.Hh = Hh; p.Ww = Ww; p.Cin = Cin;
+  p.wpk = wpk; p.bias = bias; p.Nout = Nout;
+  p.out = out; p.out_sb = out_sb; p.out_sy = out_sy; p.out_sx = out_sx;
+  p.x = x; p.mean = mean; p.rstd = rstd; p.gamma_out = gamma_out; p.slope = slope; p.C = C;
+  p.gate = gate;
+  int rc = conv3x3_check(p, epilogue);
+  if (rc) return rc;
+  if (impl == 1) return conv3x3_mma(p, epilogue, round_out, stream);
+  if (impl == 2) {
+    if (!conv3x3_tc_supported(p, epilogue))
+      return fail(AG2V_ERR_UNSUPPORTED, "conv3x3: shape not supported by the tcgen05 kernel (Cin=%d Nout=%d %dx%d)", Cin, Nout, Hh, Ww);
+    return conv3x3_tc(p, epilogue, round_out, stream);
+  }
+  if (conv3x3_tc_supported(p, epilogue)) return conv3x3_tc(p, epilogue, round_out, stream);
+  return conv3x3_mma(p, epilogue, round_out, stream);
+}
+
+extern "C" int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue) {
+  ConvParams p{};
+  p.B = B; p.Hh = Hh; p.Ww = Ww; p.Cin = Cin; p.Nout = Nout; p.C = Nout / 2;
+  return conv3x3_tc_supported(p, epilogue) ? 1 : 0;
+}

@@ -77,3 +77,51 @@ def boxes_to_layout(vecs, boxes, H, W=None, pooling='sum'):
     avg = _pooling_flag(pooling)
     W = H if W is None else W
     return _BoxesToLayoutFn.apply(vecs.unsqueeze(0), boxes.unsqueeze(0), None, int(H), int(W), avg)
+
+
+L.register('ag2v_masks_to_layout_fwd', L.c_i, [L.c_p] * 5 + [L.c_i] * 6 + [L.c_p] * 3 + [L.c_p])
+L.register('ag2v_masks_to_layout_bwd', L.c_i, [L.c_p] * 2 + [L.c_i] * 4 + [L.c_p] + [L.c_p])
+
+
+class _MasksToLayoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vecs, boxes, masks, H, W, test_mode):
+        L.need_cuda(vecs, boxes, masks)
+        vecs, boxes, masks = L.f32c(vecs), L.f32c(boxes), L.f32c(masks)
+        O, D = vecs.shape
+        M = masks.shape[1]
+        dev = vecs.device
+        S = torch.empty(max(O, 1), H, W, device=dev, dtype=torch.float32)
+        order = torch.empty(max(O, 1), device=dev, dtype=torch.int32)
+        out = torch.empty(1, D, H, W, device=dev, dtype=torch.float32)
+        L.check(L.lib().ag2v_masks_to_layout_fwd(L.ptr(vecs), L.ptr(boxes), L.ptr(masks), L.ptr(_linspace(W, dev)),
+                                                 L.ptr(_linspace(H, dev)), O, D, M, H, W, int(test_mode), L.ptr(S),
+                                                 L.ptr(order), L.ptr(out), L.stream()))
+        ctx.save_for_backward(S)
+        ctx.dims = (O, D, H, W, bool(test_mode))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (S,) = ctx.saved_tensors
+        O, D, H, W, test_mode = ctx.dims
+        if test_mode:
+            raise RuntimeError('masks_to_layout(test_mode=True) is an inference-only compositing path')
+        dvecs = torch.zeros(O, D, device=dout.device, dtype=torch.float32)
+        L.check(L.lib().ag2v_masks_to_layout_bwd(L.ptr(L.f32c(dout)), L.ptr(S), O, D, H, W, L.ptr(dvecs), L.stream()))
+        # masks come from data or from a frozen mask head on this path: no gradient for them or the boxes
+        return dvecs, None, None, None, None, None
+
+
+def masks_to_layout(vecs, boxes, masks, H, W=None, pooling='sum', test_mode=False):
+    """vecs [O,D], boxes [O,4] xywh, masks [O,M,M] -> [1,D,H,W]  (layout.py:66-95).
+    ``test_mode`` composites objects in ascending order of sampled mass, first writer
+    wins where the clean mask exceeds 0.5 (layout.py:185-197)."""
+    O, D = vecs.size()
+    M = masks.size(1)
+    assert masks.size() == (O, M, M)
+    W = H if W is None else W
+    out = _MasksToLayoutFn.apply(vecs, boxes, masks.float(), int(H), int(W), bool(test_mode))
+    if pooling != 'sum':
+        raise ValueError('Invalid pooling "%s"' % pooling)
+    return out

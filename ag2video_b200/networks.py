@@ -1,0 +1,278 @@
+"""The callers that drive the hot path, rebuilt around the sm_100a operators.
+
+These modules mirror the reference's module tree (same attribute names and
+state-dict keys, so reference checkpoints load after stripping DataParallel's
+``module.`` infix) but are laid out for the kernels instead of translated:
+
+* ``Acts2LayoutModel``  (models/graph_models/model.py:23-174): the per-timestep
+  recurrence; each graph layer is one fused kernel.
+* ``Layout2VidGenerator`` (models/spade_models/networks/generator.py:11-93): all
+  B*F layouts of a batch come from ONE launch with a device-side object mask
+  (no boolean-index compaction, no ``.item()`` sync); activations run in
+  ``torch.channels_last`` so the SPADE kernels read them in place.
+* ``SPADEGenerator`` (spade_generator.py:8-81): one ``SharedSeg`` per call.
+* ``FlowsGenerator`` (flows_generator.py:13-109) and ``conv_dim_in`` are plain
+  convolutions and stay on cuDNN (out of scope).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.utils import spectral_norm
+
+from .graph import GraphTripleConv
+from .layout import boxes_to_layout_batched
+from .spade import SPADEResnetBlock, SharedSeg
+
+CL = torch.channels_last
+
+
+class AttributeEmbeddings(nn.Module):
+    """models/attribute_embed.py:16-46."""
+
+    def __init__(self, attributes, embedding_dim):
+        super().__init__()
+        self.n_attr = len(attributes)
+        if self.n_attr > 1:
+            self.attribute_fc_gen = nn.Linear(self.n_attr * embedding_dim, self.n_attr * embedding_dim)
+        for i, name in enumerate(list(attributes)):
+            self.add_module('att_emb_%d' % i, nn.Embedding(max(attributes[name].values()) + 1, embedding_dim))
+
+    def forward(self, objs):
+        v = torch.cat([getattr(self, 'att_emb_%d' % k)(objs[..., k]) for k in range(objs.shape[-1])], dim=-1)
+        return self.attribute_fc_gen(v) if self.n_attr > 1 else v
+
+
+def real_object_mask(objs, vocab):
+    """models/utils.py:95-102 for a whole batch: [B, O] bool, True for real objects."""
+    first = objs[..., 0]
+    return (first != 0) & (first != vocab['object_name_to_idx']['__image__'])
+
+
+class Acts2LayoutModel(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        v = opt.vocab
+        emb, gdim, hid = opt.embedding_dim, opt.gconv_dim, opt.gconv_hidden_dim
+        n_attr = len(v['attributes'])
+        obj_in = n_attr * emb
+        self.vocab, self.embedding_dim = v, emb
+        self.only_temporal = bool(getattr(opt, 'only_temporal', 0))
+        self.pad_act = v['action_name_to_idx']['__padding__']
+        self.pad_pred = v['pred_name_to_idx']['__padding__']
+        self.attribute_embedding = AttributeEmbeddings(v['attributes'], emb)
+        self.pred_embeddings = nn.Embedding(len(v['pred_idx_to_name']), emb)
+        self.acts_embeddings = nn.Embedding(len(v['action_idx_to_name']), emb)
+        first = dict(obj_input_dim=obj_in, object_output_dim=gdim, predicate_input_dim=emb, predicate_output_dim=gdim,
+                     hidden_dim=hid, num_attributes=n_attr, mlp_normalization=opt.mlp_normalization,
+                     pooling=opt.gconv_pooling, loc_dim=4)
+        rest = dict(first, obj_input_dim=gdim, predicate_input_dim=gdim)
+        self.gconvs = nn.ModuleList([GraphTripleConv(**(first if i == 0 else rest)) for i in range(opt.gconv_num_layers)])
+        self.box_net = nn.Sequential(nn.Linear(gdim, hid), nn.ReLU(), nn.Linear(hid, 4))
+        self.obj_vecs_net = nn.Sequential(nn.Linear(obj_in + 4, obj_in, bias=False), nn.ReLU(),
+                                          nn.Linear(obj_in, obj_in, bias=False), nn.ReLU())
+
+    def forward(self, objs, triplets, actions, boxes_gt=None, test_mode=False):
+        B, T = triplets.shape[:2]
+        A = actions.shape[1]
+        dev = actions.device
+        act = actions.unsqueeze(1).expand(B, T, A, 7)
+        f1, f2 = act[..., 3].float(), act[..., 4].float()
+        steps = torch.arange(T, device=dev, dtype=torch.float32).view(1, T, 1)
+        rel_t = (steps / T) * (f2 - f1 + 1e-6) + f1                                   # model.py:118
+        a_id = torch.where((rel_t >= 0) & (rel_t <= 1), act[..., 1], act[..., 1].new_full((), float(self.pad_act)))
+        temporal_triplets = torch.stack([act[..., 0], a_id, act[..., 2]], dim=-1).long()
+        x_end, y_end = act[..., 5], act[..., 6]
+        # everything that does not depend on the recurrence is prepared for all timesteps at once
+        act_vecs = self.acts_embeddings(temporal_triplets[..., 1])
+        act_vecs = torch.cat([act_vecs[..., :-3], x_end.unsqueeze(-1), y_end.unsqueeze(-1), rel_t.unsqueeze(-1)], dim=-1)
+        edges = temporal_triplets[..., [0, 2]]
+        ind = temporal_triplets[..., 1] != self.pad_act
+        pred_vecs = act_vecs
+        if not self.only_temporal:
+            edges = torch.cat([triplets[..., [0, 2]], edges], dim=2)
+            ind = torch.cat([triplets[..., 1] != self.pad_pred, ind], dim=2)
+            pred_vecs = torch.cat([self.pred_embeddings(triplets[..., 1]), act_vecs], dim=2)
+        edges, ind = edges.contiguous(), ind.contiguous()
+        emb = self.attribute_embedding(objs)
+        boxes = [boxes_gt[:, 0]]
+        per_t = [emb.new_zeros(objs.shape[0], objs.shape[1], self.embedding_dim)]
+        for t in range(1, T):
+            obj_vecs = self.obj_vecs_net(torch.cat([emb, boxes[-1]], dim=-1))
+            p_vecs = pred_vecs[:, t]
+            for layer in self.gconvs:
+                obj_vecs, p_vecs = layer(obj_vecs, p_vecs, edges[:, t], ind[:, t])
+            per_t.append(obj_vecs)
+            boxes.append(boxes[-1] + self.box_net(obj_vecs))                           # model.py:168
+        locs = torch.stack([x_end, y_end], dim=-1)
+        return torch.stack(per_t, dim=1), torch.stack(boxes, dim=1), [triplets, temporal_triplets, rel_t, locs]
+
+
+class _BN2d(nn.Module):
+    """SynchronizedBatchNorm2d(affine=True) on one device = F.batch_norm
+    (sync_batchnorm/batchnorm.py:63-68); cuDNN, outside the hot-path scope."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer('running_mean', torch.zeros(c))
+        self.register_buffer('running_var', torch.ones(c))
+        self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+
+    def forward(self, x):
+        return F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training, 0.1, 1e-5)
+
+
+def _sn_conv_bn(cin, cout, stride=1):
+    return nn.Sequential(spectral_norm(nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)), _BN2d(cout))
+
+
+class _FlowResBlock(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv_0 = spectral_norm(nn.Conv2d(c, c, 3, padding=1))
+        self.conv_1 = spectral_norm(nn.Conv2d(c, c, 3, padding=1))
+        self.bn_0, self.bn_1 = _BN2d(c), _BN2d(c)
+
+    def forward(self, x):
+        dx = self.conv_0(F.leaky_relu(self.bn_0(x), 0.2))
+        return x + self.conv_1(F.leaky_relu(self.bn_1(dx), 0.2))
+
+
+class FlowsGenerator(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        cin = opt.gconv_dim * 4 * opt.n_frames_G + (opt.n_frames_G - 1) * 3
+        nf, nd = opt.nff, opt.n_downsample_F
+        ch = [min(1024, nf * 2 ** i) for i in range(nd + 1)]
+        down = [_sn_conv_bn(cin, nf), nn.LeakyReLU(0.2)]
+        for i in range(nd):
+            down += [_sn_conv_bn(ch[i], ch[i + 1], stride=2), nn.LeakyReLU(0.2)]
+        up = []
+        for i in reversed(range(nd)):
+            up += [nn.Upsample(scale_factor=2), _sn_conv_bn(ch[i + 1], ch[i]), nn.LeakyReLU(0.2)]
+        self.flow_multiplier = opt.flow_multiplier
+        self.down_flow = nn.Sequential(*down)
+        self.res_flow = nn.Sequential(*[_FlowResBlock(ch[-1]) for _ in range(opt.n_blocks_F)])
+        self.up_flow = nn.Sequential(*up)
+        self.conv_flow = nn.Sequential(nn.Conv2d(nf, 2, 3, padding=1))
+        self.conv_w = nn.Sequential(nn.Conv2d(nf, 1, 3, padding=1), nn.Sigmoid())
+
+    def forward(self, label):
+        feat = self.up_flow(self.res_flow(self.down_flow(label)))
+        return self.conv_w(feat), self.conv_flow(feat) * self.flow_multiplier
+
+
+class SPADEGenerator(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        if opt.num_upsampling_layers != 'normal':
+            raise NotImplementedError('num_upsampling_layers=%s' % opt.num_upsampling_layers)
+        nf = opt.ngf
+        self.sw = opt.image_size[0] // 32
+        self.sh = round(self.sw / opt.aspect_ratio)
+        self.fc = nn.Conv2d(opt.semantic_nc, 16 * nf, 3, padding=1)
+        self.head_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.G_middle_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.G_middle_1 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.up_0 = SPADEResnetBlock(16 * nf, 8 * nf, opt)
+        self.up_1 = SPADEResnetBlock(8 * nf, 4 * nf, opt)
+        self.up_2 = SPADEResnetBlock(4 * nf, 2 * nf, opt)
+        self.up_3 = SPADEResnetBlock(2 * nf, nf, opt)
+        self.conv_img = nn.Conv2d(nf, 3, 3, padding=1)
+
+    def forward(self, layout):
+        seg = SharedSeg.wrap(layout)                       # one NHWC copy + one gradient buffer for all 18 SPADEs
+        up = lambda z: F.interpolate(z, scale_factor=2, mode='nearest')
+        x = self.fc(F.interpolate(layout, size=(self.sh, self.sw)))
+        x = self.head_0(x, seg)
+        x = self.G_middle_0(up(x), seg)
+        x = self.G_middle_1(x, seg)
+        for name in ('up_0', 'up_1', 'up_2', 'up_3'):
+            x = getattr(self, name)(up(x), seg)
+        return torch.tanh(self.conv_img(F.leaky_relu(x, 0.2)))
+
+
+def flow_warp(image, flow):
+    """models/utils.py:113-140 (border padding, align_corners=False)."""
+    b, _, h, w = image.shape
+    hor = torch.linspace(-1.0, 1.0, w).to(image.device).view(1, 1, 1, w).expand(b, 1, h, w)
+    ver = torch.linspace(-1.0, 1.0, h).to(image.device).view(1, 1, h, 1).expand(b, 1, h, w)
+    grid = torch.cat([hor, ver], 1)
+    flow = torch.cat([flow[:, 0:1] / ((w - 1.0) / 2.0), flow[:, 1:2] / ((h - 1.0) / 2.0)], dim=1)
+    return F.grid_sample(image, (grid + flow).permute(0, 2, 3, 1), mode='bilinear', padding_mode='border',
+                         align_corners=False)
+
+
+class Layout2VidGenerator(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.attribute_embedding = AttributeEmbeddings(opt.vocab['attributes'], 384 // len(opt.vocab['attributes']))
+        self.netG = SPADEGenerator(opt)
+        self.flows_network = FlowsGenerator(opt)
+        cin = opt.gconv_dim * 4 * opt.n_frames_G + 3
+        self.conv_dim_in = nn.Sequential(_sn_conv_bn(cin, opt.semantic_nc), nn.LeakyReLU(0.2))
+
+    def build_layouts(self, objs, obj_vecs, boxes):
+        """[B, F+1, D, H, H]: one launch for all (clip, frame) layouts (generator.py:36-54)."""
+        B, T, O = boxes.shape[:3]
+        H = self.opt.image_size[0]
+        att = self.attribute_embedding(objs)
+        vecs = torch.cat([att.unsqueeze(1).expand(B, T, O, att.shape[-1]), obj_vecs], dim=-1)
+        valid = real_object_mask(objs, self.opt.vocab).unsqueeze(1).expand(B, T, O)
+        seg = boxes_to_layout_batched(vecs.reshape(B * T, O, -1), boxes.reshape(B * T, O, 4),
+                                      valid.reshape(B * T, O), H, H)
+        seg = seg.view(B, T, -1, H, H)
+        return torch.cat([seg, seg[:, -1:]], dim=1)
+
+    def forward(self, imgs_gt, objs, obj_vecs, layout, imgs_prev=None, test_mode=False):
+        seg = self.build_layouts(objs, obj_vecs, layout)
+        n_prev = self.opt.n_frames_G - 1
+        B, T = imgs_gt.shape[0], layout.shape[1]
+        H = self.opt.image_size[0]
+        imgs_prev = imgs_gt[:, :n_prev]
+        conf = torch.zeros(B, T, 1, H, H, device=imgs_gt.device)
+        flows = torch.zeros(B, T, 2, H, H, device=imgs_gt.device)
+        for t in range(n_prev, T):
+            seg_t = seg[:, t - n_prev:t + 1].reshape(B, -1, H, H)
+            prev = imgs_prev[:, -n_prev:] if (test_mode or self.opt.bp_prev) else imgs_gt[:, t - n_prev:t]
+            prev = prev.reshape(B, -1, H, H)
+            weight, flow = self.flows_network(torch.cat([seg_t, prev], dim=1).contiguous(memory_format=CL))
+            warped = flow_warp(prev[:, -3:], flow)
+            diff = prev[:, -3:] - warped
+            conf[:, t - 1] = ((diff * diff).sum(dim=1, keepdim=True) < 0.02).float()
+            flows[:, t - 1] = flow
+            x = self.conv_dim_in(torch.cat([seg_t, warped], dim=1).contiguous(memory_format=CL))
+            img = self.netG(x) + warped
+            imgs_prev = torch.cat([imgs_prev, img.unsqueeze(1)], dim=1)
+        return imgs_prev, flows, conf
+
+
+class AG2VideoModel(nn.Module):
+    """models/meta_models.py:9-57; data parallelism is one process per GPU
+    (ag2video_b200.dist) instead of the reference's in-process DataParallel."""
+
+    def __init__(self, opt, device=None):
+        super().__init__()
+        self.acts_to_boxes = Acts2LayoutModel(opt)
+        self.acts_to_objs = Acts2LayoutModel(opt)
+        self.layout_to_video = Layout2VidGenerator(opt)
+        if device is not None:
+            self.to(device)
+        self.to(memory_format=CL)
+
+    def forward(self, imgs, objs, triplets, actions, boxes_gt=None, test_mode=False, use_gt=False, graph_only=False):
+        _, boxes_pred, actions_data = self.acts_to_boxes(objs, triplets, actions, boxes_gt, test_mode)
+        if graph_only:
+            return boxes_pred
+        obj_vecs, _, actions_data = self.acts_to_objs(objs, triplets, actions, boxes_gt, test_mode)
+        boxes_in = boxes_gt if use_gt else boxes_pred.detach()
+        imgs_pred, flows, conf = self.layout_to_video(imgs, objs, obj_vecs, boxes_in, test_mode=test_mode)
+        return imgs_pred, boxes_pred, flows, conf, actions_data
+
+
+def load_reference_state(model, state):
+    """Load a reference checkpoint's ``model_state`` (scripts/train.py:528-543): drop
+    the ``.module.`` infix of its DataParallel wrappers (meta_models.py:16-27)."""
+    return model.load_state_dict({k.replace('.module.', '.'): v for k, v in state.items()}, strict=True)

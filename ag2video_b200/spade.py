@@ -1,0 +1,343 @@
+"""SPADE and SPADEResnetBlock on sm_100a (drop-in for
+models/spade_models/networks/normalization.py:66-110 and architecture.py:21-68).
+
+Same constructors, ``forward`` signatures and state-dict keys as the reference
+(``param_free_norm.{running_mean,running_var,num_batches_tracked}``,
+``mlp_shared.0.*``, ``mlp_gamma.*``, ``mlp_beta.*``; ``conv_0/1/s`` keep torch's
+spectral-norm hooks).  The modulation path runs on this library's kernels:
+
+  stats kernel -> [SyncBN all-reduce] -> implicit-GEMM conv (seg -> actv, ReLU)
+  -> implicit-GEMM conv (actv -> gamma|beta) whose epilogue applies
+  ``(x-mean)*rstd*(1+gamma)+beta`` (+ LeakyReLU inside SPADEResnetBlock).
+
+Activations are handled as NHWC (``torch.channels_last``); the nearest
+down-sample of the segmap is a strided view, never materialised.
+"""
+import re
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.utils import spectral_norm
+
+from . import _lib as L
+from ._lib import c_f, c_i, c_p, c_sz
+
+c_ll = L.ctypes.c_longlong
+c_d = L.ctypes.c_double
+
+L.register('ag2v_chan_partial_floats', c_sz, [c_ll, c_i, c_i])
+L.register('ag2v_bn_stats', c_i, [c_p, c_ll, c_i, c_p, c_p, c_p])
+L.register('ag2v_bn_finalize', c_i, [c_p, c_d, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p])
+L.register('ag2v_bn_eval_stats', c_i, [c_p, c_p, c_i, c_f, c_p, c_p, c_p])
+L.register('ag2v_spade_bwd_pre', c_i, [c_p] * 6 + [c_ll, c_i, c_i, c_f] + [c_p] * 4 + [c_p])
+L.register('ag2v_spade_bwd_dx', c_i, [c_p] * 5 + [c_d, c_i, c_ll, c_i, c_p])
+L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_p, c_p, c_p])
+L.register('ag2v_unpack_dw3x3', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
+L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_p, c_p])
+L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 5)
+L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p])
+L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_ll, c_ll, c_ll,
+                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_i, c_p])
+L.register('ag2v_conv3x3_tc_supported', c_i, [c_i] * 6)
+
+EPI_BIAS, EPI_BIAS_RELU, EPI_SPADE, EPI_GATE, EPI_ACCUM = 0, 1, 2, 3, 4
+NHIDDEN = 128                      # "Yes, hardcoded" (normalization.py:84)
+CONV_IMPL = 0                      # 0 auto, 1 mma.sync, 2 tcgen05 (tests flip this)
+
+_sync_group = {'group': None, 'enabled': False}
+
+
+def set_sync_bn(enabled, group=None):
+    """SyncBN semantics across data-parallel ranks (reference:
+    sync_batchnorm/batchnorm.py:74-83): all-reduce the per-channel sums."""
+    _sync_group['enabled'] = bool(enabled)
+    _sync_group['group'] = group
+
+
+def _world():
+    import torch.distributed as dist
+    if _sync_group['enabled'] and dist.is_available() and dist.is_initialized():
+        return dist, dist.get_world_size(_sync_group['group'])
+    return None, 1
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, epi, round_out=0,
+          x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None):
+    L.check(L.lib().ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
+                                 L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
+                                 out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
+                                 L.ptr(gamma_out), float(slope), C, L.ptr(gate), CONV_IMPL, L.stream()))
+
+
+def _pack(wa, wb, ba, bb, dgrad):
+    Co, Ci = wa.shape[0], wa.shape[1]
+    Ntot = 2 * Co if wb is not None else Co
+    dst = torch.empty(9 * Ntot * Ci, device=wa.device, dtype=torch.float32)
+    bias = torch.empty(Ntot, device=wa.device, dtype=torch.float32) if not dgrad else None
+    L.check(L.lib().ag2v_pack_w3x3(L.ptr(wa), L.ptr(wb), L.ptr(ba), L.ptr(bb), Co, Ci, int(dgrad), L.ptr(dst),
+                                   L.ptr(bias), L.stream()))
+    return dst, bias
+
+
+def _wgrad(dy, Nout, x, x_strides, Cin, B, Hh, Ww, two, like_a, like_b):
+    lib = L.lib()
+    nsplit = lib.ag2v_wgrad3x3_nsplit(B, Hh, Ww, Nout, Cin)
+    part = torch.empty(nsplit * 9 * Nout * Cin, device=dy.device, dtype=torch.float32)
+    L.check(lib.ag2v_wgrad3x3(L.ptr(dy), Nout, L.ptr(x), x_strides[0], x_strides[1], x_strides[2], Cin, B, Hh, Ww,
+                              L.ptr(part), L.stream()))
+    dwa = torch.empty_like(like_a, memory_format=torch.contiguous_format)
+    dwb = torch.empty_like(like_b, memory_format=torch.contiguous_format) if two else None
+    Co = Nout // 2 if two else Nout
+    L.check(lib.ag2v_unpack_dw3x3(L.ptr(part), nsplit, Co, Cin, int(two), L.ptr(dwa), L.ptr(dwb), L.stream()))
+    return dwa, dwb
+
+
+class SharedSeg:
+    """One segmap shared by many SPADE layers of a generator call (18 in the
+    reference's SPADEGenerator): converted to NHWC once, and all layers add their
+    input gradient into ONE buffer instead of materialising 18 full-resolution
+    gradients.  Create with ``SharedSeg.wrap(seg)`` and pass it as ``segmap``."""
+
+    def __init__(self):
+        self.seg = None        # NHWC data, detached
+        self.token = None      # autograd handle tying the consumers to the producer
+        self.grad = None
+
+    @staticmethod
+    def wrap(seg):
+        L.need_cuda(seg)
+        h = SharedSeg()
+        seg_cl, token = _SharedSegFn.apply(seg, h)
+        h.seg = seg_cl.detach()
+        h.token = token
+        return h
+
+    def grad_buffer(self):
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.seg, memory_format=torch.channels_last)
+        return self.grad
+
+
+class _SharedSegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, seg, handle):
+        ctx.handle = handle
+        seg_cl = _cl(seg.detach().float())
+        token = torch.zeros(1, device=seg.device)
+        ctx.mark_non_differentiable(seg_cl)
+        return seg_cl, token
+
+    @staticmethod
+    def backward(ctx, _dseg, _dtoken):
+        g = ctx.handle.grad
+        ctx.handle.grad = None
+        return g, None
+
+
+class _SpadeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, seg, token, w_sh, b_sh, w_g, b_g, w_b, b_b, mod, shared, slope):
+        L.need_cuda(x, seg, w_sh)
+        lib = L.lib()
+        dev = x.device
+        x = _cl(x.float())
+        seg = seg if shared is not None else _cl(seg.float())
+        B, C, r, rw = x.shape
+        _, Lc, Hs, Ws = seg.shape
+        if Hs % r or Ws % rw:
+            raise NotImplementedError('SPADE: segmap %dx%d is not an integer multiple of the activation %dx%d' % (Hs, Ws, r, rw))
+        if C % 8 or Lc % 4:
+            raise NotImplementedError('SPADE kernels need norm_nc %% 8 == 0 and label_nc %% 4 == 0 (got %d, %d)' % (C, Lc))
+        sy, sx = Hs // r, Ws // rw
+        seg_strides = (Hs * Ws * Lc, sy * Ws * Lc, sx * Lc)
+        P = B * r * rw
+        training = mod.training
+        bn = mod.param_free_norm
+        mean = torch.empty(C, device=dev, dtype=torch.float32)
+        rstd = torch.empty(C, device=dev, dtype=torch.float32)
+        count = float(P)
+        if training:
+            part = torch.empty(lib.ag2v_chan_partial_floats(P, C, 2), device=dev, dtype=torch.float32)
+            sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+            L.check(lib.ag2v_bn_stats(L.ptr(x), P, C, L.ptr(part), L.ptr(sums), L.stream()))
+            dist, world = _world()
+            if world > 1:
+                dist.all_reduce(sums, group=_sync_group['group'])
+                count = float(P * world)
+            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, bn.eps, bn.momentum, L.ptr(bn.running_mean),
+                                         L.ptr(bn.running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
+        else:
+            L.check(lib.ag2v_bn_eval_stats(L.ptr(bn.running_mean), L.ptr(bn.running_var), C, bn.eps, L.ptr(mean),
+                                           L.ptr(rstd), L.stream()))
+        pk = mod._packed(w_sh, b_sh, w_g, b_g, w_b, b_b)
+        actv = torch.empty(B, r, rw, NHIDDEN, device=dev, dtype=torch.float32)
+        _conv(seg, seg_strides, B, r, rw, Lc, pk['w1'], pk['b1'], NHIDDEN, actv, (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN),
+              EPI_BIAS_RELU, round_out=1)
+        out = torch.empty(B, C, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
+        need_grad = any(ctx.needs_input_grad)
+        gamma = torch.empty(B, r, rw, C, device=dev, dtype=torch.float32) if need_grad else None
+        _conv(actv, (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN), B, r, rw, NHIDDEN, pk['w2'], pk['b2'], 2 * C, out,
+              (r * rw * C, rw * C, C), EPI_SPADE, x=x, mean=mean, rstd=rstd, gamma_out=gamma, slope=slope, C=C)
+        if need_grad:
+            ctx.save_for_backward(x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b)
+        ctx.meta = (B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope)
+        ctx.mod, ctx.shared = mod, shared
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b = ctx.saved_tensors
+        B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope = ctx.meta
+        mod, shared = ctx.mod, ctx.shared
+        lib = L.lib()
+        dev = x.device
+        dout = _cl(dout.float())
+        act = 0 if slope == 1.0 else 1
+        dgb = torch.empty(P, 2 * C, device=dev, dtype=torch.float32)
+        dx = torch.empty(B, C, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
+        part = torch.empty(lib.ag2v_chan_partial_floats(P, C, 4), device=dev, dtype=torch.float32)
+        sums = torch.empty(4 * C, device=dev, dtype=torch.float64)
+        L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), P, C,
+                                       act, float(slope), L.ptr(dgb), L.ptr(dx), L.ptr(part), L.ptr(sums), L.stream()))
+        db = torch.empty(2 * C, device=dev, dtype=torch.float32)     # [sum g | sum g*xhat] = [d bias_beta | d bias_gamma]
+        L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, L.ptr(db), L.stream()))
+        if training:
+            dist, world = _world()
+            if world > 1:
+                tail = sums[2 * C:]
+                dist.all_reduce(tail, group=_sync_group['group'])
+        L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
+                                      int(training), P, C, L.stream()))
+        a_strides = (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN)
+        # gamma / beta convolutions: weight gradient, then input gradient gated by the ReLU of actv
+        dw_g, dw_b = _wgrad(dgb, 2 * C, actv, a_strides, NHIDDEN, B, r, rw, True, w_g, w_b)
+        pkt = mod._packed_t(w_sh, w_g, w_b)
+        dactv = torch.empty(B, r, rw, NHIDDEN, device=dev, dtype=torch.float32)
+        _conv(dgb, (r * rw * 2 * C, rw * 2 * C, 2 * C), B, r, rw, 2 * C, pkt['w2t'], None, NHIDDEN, dactv, a_strides,
+              EPI_GATE, round_out=1, gate=actv)
+        # shared convolution: bias / weight gradients, then the gradient w.r.t. the (strided) segmap
+        part1 = torch.empty(lib.ag2v_chan_partial_floats(P, NHIDDEN, 2), device=dev, dtype=torch.float32)
+        sums1 = torch.empty(2 * NHIDDEN, device=dev, dtype=torch.float64)
+        L.check(lib.ag2v_bn_stats(L.ptr(dactv), P, NHIDDEN, L.ptr(part1), L.ptr(sums1), L.stream()))
+        db_sh = torch.empty(NHIDDEN, device=dev, dtype=torch.float32)
+        L.check(lib.ag2v_double_to_float(L.ptr(sums1), NHIDDEN, L.ptr(db_sh), L.stream()))
+        dw_sh, _ = _wgrad(dactv, NHIDDEN, seg, seg_strides, Lc, B, r, rw, False, w_sh, None)
+        dseg = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            if shared is not None:
+                buf = shared.grad_buffer()
+            else:
+                buf = torch.zeros(B, Lc, Hs, Ws, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
+                dseg = buf
+            _conv(dactv, a_strides, B, r, rw, NHIDDEN, pkt['w1t'], None, Lc, buf, seg_strides, EPI_ACCUM)
+        dtoken = torch.zeros(1, device=dev) if (shared is not None and ctx.needs_input_grad[2]) else None
+        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None
+
+
+class _ParamFreeNorm(nn.Module):
+    """Buffers of SynchronizedBatchNorm2d(affine=False) (normalization.py:76-77) —
+    storage only; the statistics are computed by the SPADE kernels."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.register_buffer('running_mean', torch.zeros(num_features))
+        self.register_buffer('running_var', torch.ones(num_features))
+        self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+
+
+class SPADE(nn.Module):
+    """SPADE(config_text, norm_nc, label_nc).forward(x, segmap)  (normalization.py:66-110).
+    ``segmap`` may also be a ``SharedSeg`` handle.  ``fused_slope`` (used by
+    SPADEResnetBlock) folds ``leaky_relu(., slope)`` into the epilogue."""
+
+    def __init__(self, config_text, norm_nc, label_nc):
+        super().__init__()
+        assert config_text.startswith('spade')
+        parsed = re.search(r'spade(\D+)(\d)x\d', config_text)
+        kind, ks = str(parsed.group(1)), int(parsed.group(2))
+        if kind not in ('syncbatch', 'batch'):
+            if kind == 'instance':
+                raise NotImplementedError('spadeinstance is not on the accelerated path')
+            raise ValueError('%s is not a recognized param-free norm type in SPADE' % kind)
+        if ks != 3:
+            raise NotImplementedError('the implicit-GEMM kernels are 3x3 (the reference default)')
+        self.param_free_norm = _ParamFreeNorm(norm_nc)
+        self.mlp_shared = nn.Sequential(nn.Conv2d(label_nc, NHIDDEN, kernel_size=3, padding=1), nn.ReLU())
+        self.mlp_gamma = nn.Conv2d(NHIDDEN, norm_nc, kernel_size=3, padding=1)
+        self.mlp_beta = nn.Conv2d(NHIDDEN, norm_nc, kernel_size=3, padding=1)
+        self.fused_slope = 1.0
+        self._pk = None
+        self._pkt = None
+
+    @staticmethod
+    def _key(*ts):
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _packed(self, w_sh, b_sh, w_g, b_g, w_b, b_b):
+        key = self._key(w_sh, b_sh, w_g, b_g, w_b, b_b)
+        if self._pk is None or self._pk['key'] != key:
+            w1, b1 = _pack(w_sh.contiguous(), None, b_sh, None, False)
+            w2, b2 = _pack(w_g.contiguous(), w_b.contiguous(), b_g, b_b, False)
+            self._pk = dict(key=key, w1=w1, b1=b1, w2=w2, b2=b2)
+        return self._pk
+
+    def _packed_t(self, w_sh, w_g, w_b):
+        key = self._key(w_sh, w_g, w_b)
+        if self._pkt is None or self._pkt['key'] != key:
+            w1t, _ = _pack(w_sh.contiguous(), None, None, None, True)
+            w2t, _ = _pack(w_g.contiguous(), w_b.contiguous(), None, None, True)
+            self._pkt = dict(key=key, w1t=w1t, w2t=w2t)
+        return self._pkt
+
+    def forward(self, x, segmap):
+        shared = segmap if isinstance(segmap, SharedSeg) else None
+        seg = shared.seg if shared is not None else segmap
+        token = shared.token if shared is not None else None
+        return _SpadeFn.apply(x, seg, token, self.mlp_shared[0].weight, self.mlp_shared[0].bias,
+                              self.mlp_gamma.weight, self.mlp_gamma.bias, self.mlp_beta.weight, self.mlp_beta.bias,
+                              self, shared, float(self.fused_slope))
+
+
+class SPADEResnetBlock(nn.Module):
+    """SPADEResnetBlock(fin, fout, opt).forward(x, seg)  (architecture.py:21-68).
+    The LeakyReLU(0.2) after norm_0 / norm_1 is fused into the SPADE epilogue;
+    conv_0 / conv_1 / conv_s stay torch modules with their spectral-norm hooks."""
+
+    def __init__(self, fin, fout, opt):
+        super().__init__()
+        self.learned_shortcut = (fin != fout)
+        fmiddle = min(fin, fout)
+        self.conv_0 = nn.Conv2d(fin, fmiddle, kernel_size=3, padding=1)
+        self.conv_1 = nn.Conv2d(fmiddle, fout, kernel_size=3, padding=1)
+        if self.learned_shortcut:
+            self.conv_s = nn.Conv2d(fin, fout, kernel_size=1, bias=False)
+        if 'spectral' in opt.norm_G:
+            self.conv_0 = spectral_norm(self.conv_0)
+            self.conv_1 = spectral_norm(self.conv_1)
+            if self.learned_shortcut:
+                self.conv_s = spectral_norm(self.conv_s)
+        cfg = opt.norm_G.replace('spectral', '')
+        self.norm_0 = SPADE(cfg, fin, opt.semantic_nc)
+        self.norm_1 = SPADE(cfg, fmiddle, opt.semantic_nc)
+        self.norm_0.fused_slope = 0.2
+        self.norm_1.fused_slope = 0.2
+        if self.learned_shortcut:
+            self.norm_s = SPADE(cfg, fin, opt.semantic_nc)
+
+    def forward(self, x, seg):
+        own = None
+        if not isinstance(seg, SharedSeg):
+            seg = own = SharedSeg.wrap(seg)
+        x_s = self.conv_s(self.norm_s(x, seg)) if self.learned_shortcut else x
+        dx = self.conv_0(self.norm_0(x, seg))
+        dx = self.conv_1(self.norm_1(dx, seg))
+        return x_s + dx
+
+    def actvn(self, x):
+        return F.leaky_relu(x, 2e-1)

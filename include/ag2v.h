@@ -1,0 +1,147 @@
+/* libag2v_sm100a — C ABI of the B200-native AG2Vid hot path.
+ *
+ * The reference (roeiherz/AG2Video) has no FFI layer: its boundary is a set of
+ * Python names bound at import time.  These entry points
+ * are what a binding of that boundary calls; each one cites the reference code it
+ * replaces.  Conventions:
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the
+ *     caller (PyTorch's caching allocator in the shipped host code); the library
+ *     never allocates or frees device memory and keeps no state between calls;
+ *   - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises;
+ *   - return value 0 = ok, negative = error (ag2v_last_error_string() has the text;
+ *     -1 bad argument, -2 CUDA error, -3 wrong architecture, -4 unsupported shape);
+ *   - tensors are fp32; "NHWC" means channels-last storage of a logical NCHW tensor.
+ */
+#ifndef AG2V_H_
+#define AG2V_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* ag2v_stream_t; /* == cudaStream_t */
+
+/* ---- library --------------------------------------------------------------- */
+const char* ag2v_last_error_string(void);
+int ag2v_version(void);
+int ag2v_check_device(void);                 /* 0 iff the current device is sm_100 */
+int ag2v_sm_count(void);
+unsigned long long ag2v_launch_count(void);  /* kernels enqueued by this library so far */
+
+/* ---- K1: action-graph convolution ---------------------------------------------
+ * Replaces GraphTripleConv.forward (models/graph_models/graph.py:41-107) and its
+ * autograd backward.  obj [B,O,Din], pred [B,E,Dp], edges [B,E,2] int64,
+ * ind [B,E] uint8 (pred_indicators), net1 = (W1a [H,2Din+Dp], b1a, W1b [2H+Dpo,H], b1b),
+ * net2 = (W2a [H,H], b2a, W2b [Dout,H], b2b); outputs new_obj [B,O,Dout], new_p [B,E,Dpo].
+ * `saved` (ag2v_gcn_layer_saved_floats floats) carries activations to the backward.
+ * All feature sizes must be multiples of 8. */
+size_t ag2v_gcn_layer_saved_floats(int B, int O, int E, int H, int Dpo);
+size_t ag2v_gcn_layer_bwd_workspace_floats(int B, int O, int E, int Din, int Dp, int H, int Dpo);
+int ag2v_gcn_layer_fwd(const float* obj, const float* pred, const long long* edges, const uint8_t* ind,
+                       const float* W1a, const float* b1a, const float* W1b, const float* b1b,
+                       const float* W2a, const float* b2a, const float* W2b, const float* b2b,
+                       int B, int O, int E, int Din, int Dp, int H, int Dout, int Dpo,
+                       float* new_obj, float* new_p, float* saved, ag2v_stream_t stream);
+int ag2v_gcn_layer_bwd(const float* obj, const float* pred, const long long* edges, const uint8_t* ind,
+                       const float* W1a, const float* W1b, const float* W2a, const float* W2b,
+                       const float* new_obj, const float* saved, const float* d_new_obj,
+                       const float* d_new_p /* may be NULL */,
+                       int B, int O, int E, int Din, int Dp, int H, int Dout, int Dpo,
+                       float* workspace, float* dobj, float* dpred, float* dW1a, float* db1a, float* dW1b,
+                       float* db1b, float* dW2a, float* db2a, float* dW2b, float* db2b, ag2v_stream_t stream);
+
+/* ---- K2: layout composition ---------------------------------------------------
+ * Replaces boxes_to_layout (models/layout.py:28-63) incl. _boxes_to_grid (:98-130)
+ * and _pool_samples (:205-237), batched over N (clip, frame) samples.
+ * vecs [N,O,D], boxes [N,O,4] xywh, valid [N,O] uint8 or NULL (the callers' object
+ * mask, models/utils.py:95-102), lin_x [W] / lin_y [H] = torch.linspace(0,1,n) as the
+ * reference computes it (on the CPU), out [N,D,H,W].  All-zero boxes are dropped
+ * (layout.py:40-42).  avg != 0 selects pooling='avg'.  The workspace filled by the
+ * forward is reused by the backward (recompute = 0) or rebuilt from boxes. */
+size_t ag2v_boxes_to_layout_workspace_bytes(int N, int O, int H, int W);
+int ag2v_boxes_to_layout_fwd(const float* vecs, const float* boxes, const uint8_t* valid, const float* lin_x,
+                             const float* lin_y, int N, int O, int D, int H, int W, int avg, void* workspace,
+                             float* out, ag2v_stream_t stream);
+int ag2v_boxes_to_layout_bwd(const float* dout, const float* boxes, const uint8_t* valid, const float* lin_x,
+                             const float* lin_y, int N, int O, int D, int H, int W, int avg, int recompute,
+                             void* workspace, float* dvecs, ag2v_stream_t stream);
+
+/* masks_to_layout (models/layout.py:66-95, _pool_mask_samples :164-202) for one
+ * (clip, frame): vecs [O,D], boxes [O,4] xywh, masks [O,M,M]; S [O,H,W] receives the
+ * sampled masks (kept for the backward); test_mode != 0 composites objects in
+ * ascending order of sampled mass (order = O ints of scratch); out [D,H,W]. */
+int ag2v_masks_to_layout_fwd(const float* vecs, const float* boxes, const float* masks, const float* lin_x,
+                             const float* lin_y, int O, int D, int M, int H, int W, int test_mode, float* S,
+                             int* order, float* out, ag2v_stream_t stream);
+int ag2v_masks_to_layout_bwd(const float* dout, const float* S, int O, int D, int H, int W, float* dvecs,
+                             ag2v_stream_t stream);
+
+/* crop_bbox (models/bilinear.py:102-131 with tensor_linspace :192-221) over a flat
+ * list of crops: feats [NF,C,H,W] NCHW, frame[n] = source image of crop n, boxes
+ * [n,4] xywh, ws/we = torch.linspace(1,0,steps) / (0,1,steps) for WW (x) and HH (y);
+ * out [n,C,HH,WW].  The backward adds into a zero-initialised dfeats (atomics). */
+int ag2v_crop_bbox_fwd(const float* feats, const int* frame, const float* boxes, const float* ws_x,
+                       const float* we_x, const float* ws_y, const float* we_y, int n_crops, int C, int H, int W,
+                       int HH, int WW, float* out, ag2v_stream_t stream);
+int ag2v_crop_bbox_bwd(const float* dout, const int* frame, const float* boxes, const float* ws_x,
+                       const float* we_x, const float* ws_y, const float* we_y, int n_crops, int C, int H, int W,
+                       int HH, int WW, float* dfeats, ag2v_stream_t stream);
+
+/* ---- K3: SPADE ---------------------------------------------------------------
+ * Pieces of SPADE.forward (models/spade_models/networks/normalization.py:96-110),
+ * the LeakyReLU of SPADEResnetBlock (architecture.py:53-54,68) and their backward.
+ * Host code composes them (ag2video_b200/spade.py); the SyncBN all-reduce of the
+ * per-channel sums (sync_batchnorm/batchnorm.py:74-83) sits between stats and finalize. */
+
+/* per-channel sums over x [P,C] NHWC: sums[0..C) = sum x, sums[C..2C) = sum x^2 (doubles) */
+size_t ag2v_chan_partial_floats(long long P, int C, int NS);
+int ag2v_bn_stats(const float* x, long long P, int C, float* partial, double* sums, ag2v_stream_t stream);
+/* F.batch_norm(training) statistics (normalization.py:99): mean/rstd + running update */
+int ag2v_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
+                     float* running_var, float* mean, float* rstd, ag2v_stream_t stream);
+int ag2v_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
+                       float* rstd, ag2v_stream_t stream);
+
+/* OIHW 3x3 weights -> [9][Nout][Cin] (dgrad = 1: transposed + flipped for the input
+ * gradient).  With wb != NULL, (wa, wb) = (mlp_gamma, mlp_beta) are interleaved in
+ * groups of 8 channels so one GEMM yields gamma and beta in the same thread. */
+int ag2v_pack_w3x3(const float* wa, const float* wb, const float* ba, const float* bb, int Co, int Ci, int dgrad,
+                   float* dst, float* bias_dst, ag2v_stream_t stream);
+
+/* 3x3, pad 1 implicit-GEMM convolution on an NHWC view (element strides in_s*; the
+ * nearest down-sample of normalization.py:102 is a strided view of the segmap):
+ *   epilogue 0: +bias   1: relu(+bias) (mlp_shared, :103)
+ *            2: SPADE — Nout = 2C gamma|beta, out = act((x-mean)*rstd*(1+gamma)+beta) (:104-108)
+ *            3: out = gate > 0 ? acc : 0     4: out += acc (gradient into the shared segmap)
+ * impl 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel. */
+int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in_sx, int B, int Hh, int Ww, int Cin,
+                 const float* wpk, const float* bias, int Nout, float* out, long long out_sb, long long out_sy,
+                 long long out_sx, int epilogue, int round_out, const float* x, const float* mean,
+                 const float* rstd, float* gamma_out, float slope, int C, const float* gate, int impl,
+                 ag2v_stream_t stream);
+int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue);
+
+/* SPADE backward, element-wise: pass 1 produces d(gamma|beta) [P,2C], dxhat and the
+ * per-channel sums [4][C] (sum g, sum g*xhat, sum dxhat, sum dxhat*xhat); pass 2 turns
+ * dxhat into dx (batch-norm backward) in place. */
+int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma, const float* mean,
+                       const float* rstd, long long P, int C, int act, float slope, float* dgb, float* dxhat,
+                       float* partial, double* sums, ag2v_stream_t stream);
+int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean, const float* rstd, const double* sums,
+                      double count, int training, long long P, int C, ag2v_stream_t stream);
+
+/* weight gradient of a 3x3 conv: split-K partials, then reduction + scatter to OIHW */
+int ag2v_wgrad3x3_nsplit(int B, int Hh, int Ww, int Nout, int Cin);
+int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, long long x_sy, long long x_sx, int Cin,
+                  int B, int Hh, int Ww, float* part, ag2v_stream_t stream);
+int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
+                      ag2v_stream_t stream);
+int ag2v_double_to_float(const double* src, int n, float* dst, ag2v_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AG2V_H_ */

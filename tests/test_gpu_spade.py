@@ -1,0 +1,135 @@
+"""K3 parity on the GPU: SPADE / SPADEResnetBlock through the C ABI vs golden
+vectors (reference outputs) and vs the CPU fp32 oracle.  The modulation GEMMs
+run in TF32 with fp32 accumulation; the bar (north_star) is 1e-3 relative,
+metric max|err| / max|ref| per tensor."""
+import types
+
+import pytest
+import torch
+
+from _util import golden, load_det, max_rel, rel_l2
+from oracle import ops as oops
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _exact_library_convs():
+    # keep cuDNN (conv_0/1/s, outside the scope) in true fp32 so the comparison isolates our kernels
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+def _grads(m):
+    return {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+
+
+def _impls():
+    import ag2video_b200.spade as sp
+    return sp
+
+
+@pytest.mark.parametrize('impl', [1, 0])
+@pytest.mark.parametrize('name', ['c16_r8', 'c8_r16'])
+def test_spade_golden(name, impl):
+    sp = _impls()
+    sp.CONV_IMPL = impl
+    try:
+        c = golden('spade.pt')[name]
+        m = sp.SPADE('spadesyncbatch3x3', c['C'], c['L'])
+        m.load_state_dict(c['state'], strict=True)
+        m.cuda().train()
+        x, seg = c['x'].cuda().requires_grad_(), c['seg'].cuda().requires_grad_()
+        out = m(x, seg)
+        assert out.shape == c['out'].shape
+        assert max_rel(out, c['out']) <= TOL
+        (out * c['cot'].cuda()).sum().backward()
+        assert max_rel(x.grad, c['dx']) <= TOL
+        assert max_rel(seg.grad, c['dseg']) <= TOL
+        g = _grads(m)
+        for k, v in c['dparams'].items():
+            assert max_rel(g[k], v) <= TOL, k
+        for k, v in c['state_after'].items():
+            assert max_rel(m.state_dict()[k].float(), v.float()) <= 1e-5, k
+        m.eval()
+        with torch.no_grad():
+            assert max_rel(m(x, seg), c['out_eval']) <= TOL
+    finally:
+        sp.CONV_IMPL = 0
+
+
+@pytest.mark.parametrize('name', ['b16_8', 'b8_8'])
+def test_spade_resnet_block_golden(name):
+    sp = _impls()
+    c = golden('spade_block.pt')[name]
+    opt = types.SimpleNamespace(norm_G='spectralspadesyncbatch3x3', semantic_nc=8)
+    m = sp.SPADEResnetBlock(c['fin'], c['fout'], opt)
+    m.load_state_dict(c['state'], strict=True)
+    m.cuda().train()
+    x, seg = c['x'].cuda().requires_grad_(), c['seg'].cuda().requires_grad_()
+    out = m(x, seg)
+    assert max_rel(out, c['out']) <= TOL
+    (out * c['cot'].cuda()).sum().backward()
+    assert max_rel(x.grad, c['dx']) <= TOL and max_rel(seg.grad, c['dseg']) <= TOL
+    g = _grads(m)
+    for k, v in c['dparams'].items():
+        assert max_rel(g[k], v) <= TOL, k
+    for k, v in c['state_after'].items():
+        assert max_rel(m.state_dict()[k].float(), v.float()) <= 1e-4, k
+
+
+@pytest.mark.parametrize('impl', [1, 0])
+@pytest.mark.parametrize('C,L,r,Hs,B,slope', [(128, 512, 32, 128, 2, 0.2), (64, 64, 64, 64, 1, 1.0), (1024, 512, 8, 64, 2, 0.2)])
+def test_spade_vs_oracle_real_widths(C, L, r, Hs, B, slope, impl):
+    """Reference channel widths (label_nc 512, norm_nc up to 1024) at sizes the CPU
+    oracle finishes in seconds; strided segmap (nearest down-sample) included."""
+    sp = _impls()
+    sp.CONV_IMPL = impl
+    try:
+        ref = load_det(oops.SPADE('spadesyncbatch3x3', C, L), 3).train()
+        m = sp.SPADE('spadesyncbatch3x3', C, L)
+        m.load_state_dict(ref.state_dict(), strict=True)
+        m.fused_slope = slope
+        m.cuda().train()
+        g = torch.Generator().manual_seed(1)
+        x_c = (torch.randn(B, C, r, r, generator=g) * 1.3 + 0.2).requires_grad_()
+        seg_c = torch.randn(B, L, Hs, Hs, generator=g).requires_grad_()
+        cot = torch.randn(B, C, r, r, generator=g)
+        o_ref = ref(x_c, seg_c)
+        if slope != 1.0:
+            o_ref = torch.nn.functional.leaky_relu(o_ref, slope)
+        (o_ref * cot).sum().backward()
+        x, seg = x_c.detach().cuda().requires_grad_(), seg_c.detach().cuda().requires_grad_()
+        out = m(x, seg)
+        (out * cot.cuda()).sum().backward()
+        assert max_rel(out, o_ref) <= TOL, rel_l2(out, o_ref)
+        assert max_rel(x.grad, x_c.grad) <= TOL
+        assert max_rel(seg.grad, seg_c.grad) <= TOL
+        gr, gm = _grads(ref), _grads(m)
+        for k in gr:
+            assert max_rel(gm[k], gr[k]) <= TOL, k
+        for k in ('param_free_norm.running_mean', 'param_free_norm.running_var'):
+            assert max_rel(m.state_dict()[k], ref.state_dict()[k]) <= 1e-5, k
+    finally:
+        sp.CONV_IMPL = 0
+
+
+def test_shared_seg_accumulates_like_autograd():
+    """Two SPADE layers on one SharedSeg: the single gradient buffer must equal the
+    sum of the two separate segmap gradients."""
+    sp = _impls()
+    a = load_det(sp.SPADE('spadesyncbatch3x3', 16, 8), 1).cuda().train()
+    b = load_det(sp.SPADE('spadesyncbatch3x3', 8, 8), 2).cuda().train()
+    g = torch.Generator().manual_seed(0)
+    x1, x2 = torch.randn(2, 16, 8, 8, generator=g).cuda(), torch.randn(2, 8, 16, 16, generator=g).cuda()
+    seg0 = torch.randn(2, 8, 32, 32, generator=g).cuda()
+    seg = seg0.clone().requires_grad_()
+    (a(x1, seg).sum() + b(x2, seg).sum()).backward()
+    want = seg.grad.clone()
+    seg2 = seg0.clone().requires_grad_()
+    h = sp.SharedSeg.wrap(seg2)
+    (a(x1, h).sum() + b(x2, h).sum()).backward()
+    assert max_rel(seg2.grad, want) <= 1e-6

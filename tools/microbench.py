@@ -102,6 +102,32 @@ def bench_k1(res):
             res['k1_bwd_%s_%s' % (name, tag)] = t
 
 
+def bench_k3(res):
+    import ag2video_b200.spade as sp
+    for name, C, L, r, Hs, B in [('up3_n0_c128_r256', 128, 512, 256, 256, 2), ('up1_c512_r64', 512, 512, 64, 256, 2),
+                                 ('mid_c1024_r16', 1024, 512, 16, 256, 2)]:
+        m = sp.SPADE('spadesyncbatch3x3', C, L).cuda().train()
+        m.fused_slope = 0.2
+        x = torch.randn(B, C, r, r, device='cuda').contiguous(memory_format=torch.channels_last).requires_grad_()
+        seg = torch.randn(B, L, Hs, Hs, device='cuda').contiguous(memory_format=torch.channels_last).requires_grad_()
+        flops = 2.0 * 9 * B * r * r * (L * 128 + 128 * 2 * C)
+        for impl in (1, 0):
+            sp.CONV_IMPL = impl
+            tag = 'mma' if impl == 1 else 'auto'
+            with torch.no_grad():
+                t = time_fn(lambda: m(x, seg), iters=10, warmup=3, flush=False)
+            t['TFLOPs'] = flops / t['us_median'] / 1e6
+            res['k3_fwd_%s_%s' % (name, tag)] = t
+            out = m(x, seg)
+            cot = torch.randn_like(out)
+            t = time_fn(lambda: torch.autograd.grad(out, [x, seg] + list(m.parameters()), cot, retain_graph=True),
+                        iters=10, warmup=3, flush=False)
+            t['TFLOPs'] = 2 * flops / t['us_median'] / 1e6
+            res['k3_bwd_%s_%s' % (name, tag)] = t
+            del out, cot
+        sp.CONV_IMPL = 0
+
+
 def main():
     which = sys.argv[1:] or ['k1', 'k2']
     res = {'peaks': PEAKS, 'device': torch.cuda.get_device_name(0)}
