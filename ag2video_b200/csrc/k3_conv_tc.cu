@@ -1,6 +1,369 @@
-// placeholder until the tcgen05 kernel lands (replaced in the next commit)
+// K3 — 3x3 implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   out[p, n] = epilogue( sum_{tap, c} in[p + tap, c] * wpk[tap][n][c] )
+//
+// * operands: fp32 in HBM, read as TF32 (kind::tf32), fp32 accumulation in TMEM;
+// * A tile = 128 output pixels as a (batch, rows, cols) box of the NHWC input
+//   view, fetched by ONE 4-D TMA load per (tap, 32-channel chunk): the tap shift is
+//   a coordinate offset and the conv zero padding is TMA's out-of-bounds fill, so
+//   there is no im2col buffer and no halo logic; the strided view that implements
+//   the nearest down-sample of the segmap is expressed in the tensor map strides;
+// * B tile = BN x 32 slab of the packed weights [9][Nout][Cin], 3-D TMA load;
+// * both land in 128-byte-swizzled K-major shared tiles consumed by tcgen05.mma
+//   (M=128, N=BN, K=8 per instruction, 4 instructions per stage);
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
+//   warps 2..5 = epilogue (tcgen05.ld, one accumulator row = one pixel per thread);
+// * 3-stage mbarrier ring; two CTAs per SM so one CTA's epilogue overlaps the
+//   other's main loop.
+#include <cuda.h>
+#include <stdlib.h>
 #include "k3_common.cuh"
+
 namespace ag2v {
-bool conv3x3_tc_supported(const ConvParams&, int) { return false; }
-int conv3x3_tc(const ConvParams&, int, int, cudaStream_t) { return fail(AG2V_ERR_UNSUPPORTED, "tcgen05 conv not built"); }
+
+constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_THREADS = 192;
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) { }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = TMEM lane = pixel row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);      // start address      bits [0,14)
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset  bits [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ float tc_round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct TcGeom { int Wt, Ht, Bt, tiles_x, tiles_y, tiles_b; };
+
+template <int BN>
+struct TcSmem {
+  static constexpr int kA = TC_BM * TC_BK * 4;          // 16 KB
+  static constexpr int kB = BN * TC_BK * 4;             // 16 / 32 KB
+  static constexpr int kStage = kA + kB;
+  static constexpr int kBytes = TC_STAGES * kStage + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI, bool ROUND_OUT>
+__global__ void __launch_bounds__(TC_THREADS)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  ConvParams p, TcGeom gm) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                         // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bars = base + TC_STAGES * TcSmem<BN>::kStage;          // full[S], empty[S], tmem_full, tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem_raw + (bars - raw) + 8 * (2 * TC_STAGES + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tx = tile % gm.tiles_x; tile /= gm.tiles_x;
+  const int ty = tile % gm.tiles_y; tile /= gm.tiles_y;
+  const int tb = tile;
+  const int x0 = tx * gm.Wt, y0 = ty * gm.Ht, b0 = tb * gm.Bt;
+  const int n0 = blockIdx.y * BN;
+  const int KC = p.Cin / TC_BK;
+  const int total = 9 * KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (TC_STAGES + s), 1); }
+    mbar_init(bars + 8 * (2 * TC_STAGES), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+        mbar_wait(bars + 8 * (TC_STAGES + s), ph ^ 1u);                // slot free
+        const int tap = it / KC, kc = it - tap * KC;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const uint32_t a_dst = base + s * TcSmem<BN>::kStage, b_dst = a_dst + TcSmem<BN>::kA;
+        mbar_expect_tx(bars + 8 * s, TcSmem<BN>::kStage);
+        tma_load_4d(a_dst, &map_a, bars + 8 * s, kc * TC_BK, x0 + dx, y0 + dy, b0);
+        tma_load_3d(b_dst, &map_b, bars + 8 * s, kc * TC_BK, n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+        mbar_wait(bars + 8 * s, ph);                                    // TMA bytes landed
+        tc_fence_after();
+        const uint32_t a_s = base + s * TcSmem<BN>::kStage, b_s = a_s + TcSmem<BN>::kA;
+        const uint64_t da = make_sw128_kmajor_desc(a_s), db = make_sw128_kmajor_desc(b_s);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k)                             // +32 bytes along K inside the swizzle atom
+          umma_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bars + 8 * (TC_STAGES + s));                        // frees the smem slot when the MMAs retire
+      }
+      umma_commit(bars + 8 * (2 * TC_STAGES));                          // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warps 2..5, TMEM lane quarter = warp % 4 --------------------
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                                       // accumulator row = pixel within the tile
+    const int xt = m % gm.Wt, yt = (m / gm.Wt) % gm.Ht, bt = m / (gm.Wt * gm.Ht);
+    const int x = x0 + xt, y = y0 + yt, b = b0 + bt;
+    const bool valid = x < p.Ww && y < p.Hh && b < p.B;
+    const long long pp = ((long long)b * p.Hh + y) * p.Ww + x;
+    float* orow = p.out + (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
+    mbar_wait(bars + 8 * (2 * TC_STAGES), 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+      const int n = n0 + ch * 32;
+      if (!valid || n >= p.Nout) continue;
+      if (EPI == EPI_SPADE) {
+        const int c = n >> 1;                                           // 16 channels: [g8 | b8 | g8 | b8]
+        const size_t off = (size_t)pp * p.C + c;
+        float xs[16], mu[16], rs[16], o[16], gm_[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4*>(xs + 4 * i) = *reinterpret_cast<const float4*>(p.x + off + 4 * i);
+          *reinterpret_cast<float4*>(mu + 4 * i) = *reinterpret_cast<const float4*>(p.mean + c + 4 * i);
+          *reinterpret_cast<float4*>(rs + 4 * i) = *reinterpret_cast<const float4*>(p.rstd + c + 4 * i);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int jg = (i >> 3) * 16 + (i & 7), jb = jg + 8;
+          float g = v[jg], bb = v[jb];
+          if (p.bias) { g += p.bias[n + jg]; bb += p.bias[n + jb]; }
+          float r = (xs[i] - mu[i]) * rs[i] * (1.f + g) + bb;
+          if (p.slope != 1.f) r = r > 0.f ? r : r * p.slope;
+          if (ROUND_OUT) r = tc_round_tf32(r);
+          o[i] = r; gm_[i] = g;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4*>(orow + c + 4 * i) = *reinterpret_cast<const float4*>(o + 4 * i);
+          if (p.gamma_out) *reinterpret_cast<float4*>(p.gamma_out + off + 4 * i) = *reinterpret_cast<const float4*>(gm_ + 4 * i);
+        }
+      } else {
+        const int ncols = min(32, p.Nout - n);
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += p.bias[n + j];
+          }
+          if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+        } else if (EPI == EPI_GATE) {
+          const float* gt = p.gate + (size_t)pp * p.Nout + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+              const float4 g4 = *reinterpret_cast<const float4*>(gt + j);
+              v[j] = g4.x > 0.f ? v[j] : 0.f; v[j + 1] = g4.y > 0.f ? v[j + 1] : 0.f;
+              v[j + 2] = g4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = g4.w > 0.f ? v[j + 3] : 0.f;
+            }
+          }
+        } else if (EPI == EPI_ACCUM) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+              const float4 o4 = *reinterpret_cast<const float4*>(orow + n + j);
+              v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
+            }
+          }
+        }
+        if (ROUND_OUT) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tc_round_tf32(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (j < ncols) *reinterpret_cast<float4*>(orow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_acc, BN); }
+}
+
+// ---- host side -----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static bool tc_geometry(const ConvParams& p, TcGeom* g) {
+  if (p.Ww >= TC_BM) { g->Wt = TC_BM; g->Ht = 1; g->Bt = 1; }
+  else {
+    if (!is_pow2(p.Ww)) return false;
+    g->Wt = p.Ww;
+    int rows = TC_BM / g->Wt;
+    if (p.Hh >= rows) { g->Ht = rows; g->Bt = 1; }
+    else { if (!is_pow2(p.Hh)) return false; g->Ht = p.Hh; g->Bt = rows / p.Hh; }
+  }
+  g->tiles_x = ceil_div(p.Ww, g->Wt); g->tiles_y = ceil_div(p.Hh, g->Ht); g->tiles_b = ceil_div(p.B, g->Bt);
+  return true;
+}
+
+bool conv3x3_tc_supported(const ConvParams& p, int epi) {
+  TcGeom g;
+  static const bool disabled = getenv("AG2V_DISABLE_TC") != nullptr;   // debugging aid: route everything to mma.sync
+  if (disabled) return false;
+  if (p.Cin % TC_BK != 0 || p.Cin < TC_BK) return false;
+  if (p.Nout % 32 != 0) return false;
+  if (epi == EPI_SPADE && p.Nout != 2 * p.C) return false;
+  if (!tc_geometry(p, &g)) return false;
+  if (p.in_sx % 4 || p.in_sy % 4 || p.in_sb % 4) return false;
+  if (p.out_sx % 4 || p.out_sy % 4 || p.out_sb % 4) return false;
+  return encode_fn() != nullptr;
+}
+
+template <int BN, int EPI, bool RO>
+static int launch_tc(const ConvParams& p, const TcGeom& g, cudaStream_t stream) {
+  EncodeTiledFn enc = encode_fn();
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Ww, (cuuint64_t)p.Hh, (cuuint64_t)p.B};
+    cuuint64_t strides[3] = {(cuuint64_t)p.in_sx * 4, (cuuint64_t)p.in_sy * 4, (cuuint64_t)p.in_sb * 4};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)g.Wt, (cuuint32_t)g.Ht, (cuuint32_t)g.Bt};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.in, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AG2V_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed with %d (Cin=%d %dx%dx%d strides %lld %lld %lld)", (int)r,
+                                       p.Cin, p.B, p.Hh, p.Ww, p.in_sb, p.in_sy, p.in_sx);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Nout, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Nout * 4};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.wpk, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AG2V_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  const int smem = TcSmem<BN>::kBytes;
+  AG2V_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BN, EPI, RO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(g.tiles_x * g.tiles_y * g.tiles_b, ceil_div(p.Nout, BN));
+  conv3x3_tc_kernel<BN, EPI, RO><<<grid, TC_THREADS, smem, stream>>>(map_a, map_b, p, g);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+int conv3x3_tc(const ConvParams& p, int epi, int round_out, cudaStream_t stream) {
+  TcGeom g;
+  if (!tc_geometry(p, &g)) return fail(AG2V_ERR_UNSUPPORTED, "conv3x3_tc: unsupported spatial shape %dx%d", p.Hh, p.Ww);
+  if (((uintptr_t)p.in & 15) || ((uintptr_t)p.wpk & 15)) return fail(AG2V_ERR_ARG, "conv3x3_tc: operands must be 16-byte aligned");
+  constexpr int BN = 128;
+  switch (epi) {
+    case EPI_BIAS: return round_out ? launch_tc<BN, EPI_BIAS, true>(p, g, stream) : launch_tc<BN, EPI_BIAS, false>(p, g, stream);
+    case EPI_BIAS_RELU: return round_out ? launch_tc<BN, EPI_BIAS_RELU, true>(p, g, stream) : launch_tc<BN, EPI_BIAS_RELU, false>(p, g, stream);
+    case EPI_SPADE: return round_out ? launch_tc<BN, EPI_SPADE, true>(p, g, stream) : launch_tc<BN, EPI_SPADE, false>(p, g, stream);
+    case EPI_GATE: return round_out ? launch_tc<BN, EPI_GATE, true>(p, g, stream) : launch_tc<BN, EPI_GATE, false>(p, g, stream);
+    case EPI_ACCUM: return launch_tc<BN, EPI_ACCUM, false>(p, g, stream);
+  }
+  return fail(AG2V_ERR_ARG, "conv3x3_tc: unknown epilogue %d", epi);
+}
+
+}  // namespace ag2v

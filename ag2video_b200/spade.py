@@ -232,7 +232,7 @@ class _SpadeFn(torch.autograd.Function):
             if shared is not None:
                 buf = shared.grad_buffer()
             else:
-                buf = torch.zeros(B, Lc, Hs, Ws, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
+                buf = torch.empty(B, Lc, Hs, Ws, device=dev, dtype=torch.float32, memory_format=torch.channels_last).zero_()
                 dseg = buf
             _conv(dactv, a_strides, B, r, rw, NHIDDEN, pkt['w1t'], None, Lc, buf, seg_strides, EPI_ACCUM)
         dtoken = torch.zeros(1, device=dev) if (shared is not None and ctx.needs_input_grad[2]) else None
