@@ -7,6 +7,15 @@
 namespace ag2v {
 
 constexpr int kElemThreads = 256;
+
+// tcgen05.mma kind::tf32 reads fp32 words and ignores the low 13 mantissa bits
+// (truncation, a biased error of ~2^-11 per operand).  Every GEMM operand is
+// therefore rounded to nearest TF32 where it is produced.
+__device__ __forceinline__ float elem_round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 constexpr int kMaxSplit = 592;       // 4 CTAs per SM
 
 struct ChanGeom { int cx, py, chunks, nsplit; };
@@ -70,8 +79,9 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
           dxh.x = g.x * (1.f + gv.x); dxh.y = g.y * (1.f + gv.y);
           dxh.z = g.z * (1.f + gv.z); dxh.w = g.w * (1.f + gv.w);
           float* row = a.dgb + (size_t)p * 2 * C;
-          *reinterpret_cast<float4*>(row + gb8_col(c, 0)) = dgam;
-          *reinterpret_cast<float4*>(row + gb8_col(c, 1)) = g;
+          // the GEMM operand copies are rounded to TF32; the sums below use the fp32 values
+          *reinterpret_cast<float4*>(row + gb8_col(c, 0)) = make_float4(elem_round_tf32(dgam.x), elem_round_tf32(dgam.y), elem_round_tf32(dgam.z), elem_round_tf32(dgam.w));
+          *reinterpret_cast<float4*>(row + gb8_col(c, 1)) = make_float4(elem_round_tf32(g.x), elem_round_tf32(g.y), elem_round_tf32(g.z), elem_round_tf32(g.w));
           *reinterpret_cast<float4*>(a.dxhat + off) = dxh;
           s[0].x += g.x; s[0].y += g.y; s[0].z += g.z; s[0].w += g.w;
           s[1].x += dgam.x; s[1].y += dgam.y; s[1].z += dgam.z; s[1].w += dgam.w;
@@ -182,7 +192,7 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ wa, const float* __re
     if (wb) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
     const float* src = is_b ? wb : wa;
     const int t = dgrad ? 8 - tap : tap;
-    dst[i] = src[((size_t)co * Ci + ci) * 9 + t];
+    dst[i] = elem_round_tf32(src[((size_t)co * Ci + ci) * 9 + t]);     // tcgen05 kind::tf32 truncates: round here
   }
   if (bias_dst != nullptr && blockIdx.x == 0) {
     for (int n = threadIdx.x; n < Ntot; n += blockDim.x) {
@@ -218,6 +228,13 @@ __global__ void unpack_db_kernel(const double* __restrict__ s_beta, const double
   if (c >= C) return;
   db_gamma[c] = (float)s_gamma[c];
   db_beta[c] = (float)s_beta[c];
+}
+
+__global__ void round_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = make_float4(elem_round_tf32(v.x), elem_round_tf32(v.y), elem_round_tf32(v.z), elem_round_tf32(v.w));
+  }
 }
 
 __global__ void double_to_float_kernel(const double* __restrict__ src, int n, float* __restrict__ dst) {
@@ -331,6 +348,17 @@ extern "C" int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, 
   long long total = 9LL * (two ? 2 * Co : Co) * Ci;
   int blocks = (int)(ceil_div_ll(total, 256) > 2368 ? 2368 : ceil_div_ll(total, 256));
   unpack_dw_kernel<<<blocks, 256, 0, stream>>>(part, nsplit, Co, Ci, two, dwa, dwb);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// dst = round-to-nearest-TF32(src), same layout, n % 4 == 0 (src == dst allowed)
+extern "C" int ag2v_round_tf32(const float* src, float* dst, long long n, cudaStream_t stream) {
+  AG2V_REQUIRE(src && dst && n > 0 && n % 4 == 0, "round_tf32: bad arguments");
+  AG2V_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "round_tf32: 16-byte alignment required");
+  long long n4 = n / 4;
+  int blocks = (int)(ceil_div_ll(n4, 256 * 4) > 148 * 16 ? 148 * 16 : ceil_div_ll(n4, 256 * 4));
+  round_tf32_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n4);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

@@ -35,6 +35,7 @@ L.register('ag2v_spade_bwd_dx', c_i, [c_p] * 5 + [c_d, c_i, c_ll, c_i, c_p])
 L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_unpack_dw3x3', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_p, c_p])
+L.register('ag2v_round_tf32', c_i, [c_p, c_p, c_ll, c_p])
 L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 5)
 L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p])
 L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_ll, c_ll, c_ll,
@@ -66,12 +67,45 @@ def _cl(t):
     return t.contiguous(memory_format=torch.channels_last)
 
 
+def _seg_operand(seg):
+    """NHWC copy of the segmap rounded to TF32 (it is the A operand of the shared
+    convolution and of its weight gradient; tcgen05's TF32 path truncates)."""
+    src = _cl(seg.detach().float())
+    dst = torch.empty_like(src, memory_format=torch.channels_last)
+    if src.numel() % 4:
+        raise NotImplementedError('segmap element count must be a multiple of 4')
+    L.check(L.lib().ag2v_round_tf32(L.ptr(src), L.ptr(dst), src.numel(), L.stream()))
+    return dst
+
+
+PROFILE = None                     # bench.py sets this to a list to time every GEMM-shaped launch with CUDA events
+
+
+class _Timed:
+    """Records (kind, flops, start, end) around one launch on the current stream."""
+
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.append((self.kind, self.flops, self.s, self.e))
+
+
 def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, epi, round_out=0,
           x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None):
-    L.check(L.lib().ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
-                                 L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
-                                 out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
-                                 L.ptr(gamma_out), float(slope), C, L.ptr(gate), CONV_IMPL, L.stream()))
+    with _Timed('conv3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout):
+        L.check(L.lib().ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
+                                     L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
+                                     out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
+                                     L.ptr(gamma_out), float(slope), C, L.ptr(gate), CONV_IMPL, L.stream()))
 
 
 def _pack(wa, wb, ba, bb, dgrad):
@@ -88,8 +122,9 @@ def _wgrad(dy, Nout, x, x_strides, Cin, B, Hh, Ww, two, like_a, like_b):
     lib = L.lib()
     nsplit = lib.ag2v_wgrad3x3_nsplit(B, Hh, Ww, Nout, Cin)
     part = torch.empty(nsplit * 9 * Nout * Cin, device=dy.device, dtype=torch.float32)
-    L.check(lib.ag2v_wgrad3x3(L.ptr(dy), Nout, L.ptr(x), x_strides[0], x_strides[1], x_strides[2], Cin, B, Hh, Ww,
-                              L.ptr(part), L.stream()))
+    with _Timed('wgrad3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout):
+        L.check(lib.ag2v_wgrad3x3(L.ptr(dy), Nout, L.ptr(x), x_strides[0], x_strides[1], x_strides[2], Cin, B, Hh, Ww,
+                                  L.ptr(part), L.stream()))
     dwa = torch.empty_like(like_a, memory_format=torch.contiguous_format)
     dwb = torch.empty_like(like_b, memory_format=torch.contiguous_format) if two else None
     Co = Nout // 2 if two else Nout
@@ -127,7 +162,7 @@ class _SharedSegFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, seg, handle):
         ctx.handle = handle
-        seg_cl = _cl(seg.detach().float())
+        seg_cl = _seg_operand(seg)
         token = torch.zeros(1, device=seg.device)
         ctx.mark_non_differentiable(seg_cl)
         return seg_cl, token
@@ -146,7 +181,7 @@ class _SpadeFn(torch.autograd.Function):
         lib = L.lib()
         dev = x.device
         x = _cl(x.float())
-        seg = seg if shared is not None else _cl(seg.float())
+        seg = seg if shared is not None else _seg_operand(seg)
         B, C, r, rw = x.shape
         _, Lc, Hs, Ws = seg.shape
         if Hs % r or Ws % rw:

@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — train-step frames/sec of the AG2Vid generation hot path at CATER 256x256.
+
+    python bench.py --gpus N --steps K --warmup W             (ours, B200)
+    python bench.py --impl reference --steps K --warmup W     (CPU arm: the oracle port)
+
+One "step" = one pass of the hot path over one batch of synthetic CATER-shaped
+clips: both action-graph models (K1), all B*F layouts (K2), flow warp +
+conv_dim_in (cuDNN, out of scope) and the SPADE generator for the F-1 generated
+frames (K3), forward + backward + Adam.  Workload = BASELINE.json configs[2]:
+256x256, batch 2 clips per GPU, frames_per_action 4 (8 frames per GPU step).
+The loss is an L1 image + box surrogate: the reference's GAN / feature-matching
+losses need the discriminator, which is outside the path.
+
+Prints ONE JSON line (rank 0).  value = frames/s with inputs resident in HBM;
+e2e = the same through the public API with the pinned-host -> device copy of
+every step's batch and the device -> host read of the loss inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--size', type=int, default=256)
+    ap.add_argument('--batch', type=int, default=2, help='clips per GPU')
+    ap.add_argument('--frames', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--conv-impl', type=int, default=0, help='0 auto, 1 mma.sync, 2 tcgen05')
+    return ap.parse_args()
+
+
+def peaks():
+    p = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p.update(json.load(f))
+            p['source'] = 'measured'
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def surrogate_loss(out, batch):
+    imgs_pred, boxes_pred = out[0], out[1]
+    return (imgs_pred - batch['imgs']).abs().mean() + 10.0 * (boxes_pred - batch['boxes'])[:, 1:].abs().mean()
+
+
+# ------------------------------------------------------------------ CPU arm ---
+def cpu_sample(size, seconds_budget, steps, warmup, threads=None):
+    """The oracle (CPU port of the reference's algorithm, oracle/) on a bounded
+    sample of the workload: ONE clip, TWO frames (one generated frame) at the full
+    resolution, generator forward + backward + Adam.  Returns frames/s and details."""
+    from ag2video_b200.config import make_opt, synthetic_batch
+    from oracle import networks as onet
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    opt = make_opt(size, batch_size=1)
+    model = onet.AG2VideoModel(opt).train()
+    optim = torch.optim.Adam(model.parameters(), lr=opt.learning_rate, betas=(opt.beta1, 0.999))
+    b = synthetic_batch(B=1, F=2, image_size=size, seed=1234)
+
+    def step():
+        out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+        loss = surrogate_loss(out, b)
+        optim.zero_grad(set_to_none=True)
+        loss.backward()
+        optim.step()
+        return float(loss.detach())
+
+    t0 = time.perf_counter()
+    step()                                   # first step also serves as warm-up / cost probe
+    t_probe = time.perf_counter() - t0
+    n_warm = max(0, min(warmup, 1) - 1)
+    for _ in range(n_warm):
+        step()
+    n = max(1, min(steps, int(seconds_budget / max(t_probe, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    return {'value': 2.0 / dt, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+            'sample': '1 clip x 2 frames (1 generated) at %dx%d, generator fwd+bwd+Adam, oracle/ torch CPU fp32, '
+                      '%d timed step(s) of %.1f s' % (size, size, n, dt), 's_per_step': dt, 'steps': n}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    res = cpu_sample(args.size, 150.0, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': 'train-step frames/sec at CATER 256x256', 'value': res['value'],
+        'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': res['steps'], 'warmup': min(args.warmup, 1),
+        'ms_per_step': res['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'AG2Vid CATER %dx%d generator train step (GCN -> layout -> SPADE, fwd+bwd+Adam), '
+                               'batch %d clips/GPU x %d frames' % (args.size, args.size, args.batch, args.frames),
+                   'sample': res['sample']},
+        'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+        'e2e': {'value': res['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm ---
+def run_ours(args):
+    from ag2video_b200 import _lib as L
+    from ag2video_b200 import dist as agdist
+    from ag2video_b200 import spade as sp
+    from ag2video_b200.config import make_opt, synthetic_batch
+    from ag2video_b200.networks import AG2VideoModel
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
+    rank, world, local = agdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    L.check(L.lib().ag2v_check_device())
+    sp.CONV_IMPL = args.conv_impl
+    if world > 1:
+        sp.set_sync_bn(True)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_sample(args.size, 25.0, 1, 0)
+
+    torch.manual_seed(0)
+    opt = make_opt(args.size, batch_size=args.batch, frames_per_action=args.frames)
+    model = AG2VideoModel(opt, dev).train()
+    graph_params = list(model.acts_to_boxes.parameters())
+    gen_params = list(model.acts_to_objs.parameters()) + list(model.layout_to_video.parameters())
+    opt_graph = torch.optim.Adam(graph_params, lr=opt.learning_rate, betas=(opt.beta1, 0.999), fused=True)
+    opt_gen = torch.optim.Adam(gen_params, lr=opt.learning_rate, betas=(opt.beta1, 0.999), fused=True)
+    buckets = agdist.GradBuckets(graph_params + gen_params) if world > 1 else None
+
+    # a small pool of distinct clips per rank in pinned host memory (disjoint seeds per rank = sharding by clip)
+    pool_host = []
+    for i in range(4):
+        b = synthetic_batch(B=args.batch, F=args.frames, image_size=args.size, seed=1234 + 1000 * rank + i)
+        pool_host.append({k: v.pin_memory() for k, v in b.items()})
+    pool_dev = [{k: v.to(dev) for k, v in b.items()} for b in pool_host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
+    loss_host = torch.zeros(1).pin_memory()
+
+    def train_step(batch):
+        out = model(batch['imgs'], batch['objs'], batch['triplets'], batch['actions'], boxes_gt=batch['boxes'], use_gt=True)
+        loss = surrogate_loss(out, batch)
+        opt_graph.zero_grad(set_to_none=True)
+        opt_gen.zero_grad(set_to_none=True)
+        loss.backward()
+        if buckets is not None:
+            buckets.allreduce()
+        opt_graph.step()
+        opt_gen.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(n):
+            if e2e:
+                batch = {k: v.to(dev, non_blocking=True) for k, v in pool_host[i % len(pool_host)].items()}
+                loss = train_step(batch)
+                loss_host.copy_(loss.detach().view(1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()       # the user reads the loss every step
+            else:
+                train_step(pool_dev[i % len(pool_dev)])
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for i in range(args.warmup):
+        train_step(pool_dev[i % len(pool_dev)])
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    sp.PROFILE = []
+    launches0 = L.launch_count()
+    ms_dev = timed(args.steps, e2e=False)
+    launches = L.launch_count() - launches0
+    prof, sp.PROFILE = sp.PROFILE, None
+    ms_e2e = timed(args.steps, e2e=True)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
+
+    frames = world * args.batch * args.frames
+    value = frames * args.steps / (ms_dev / 1e3)
+    e2e = frames * args.steps / (ms_e2e / 1e3)
+
+    # dominant kernel: the implicit-GEMM 3x3 convolution (modulation convs fwd + input gradients)
+    pk = peaks()
+    roof = None
+    if prof:
+        agg = {}
+        for kind, flops, s, e in prof:
+            a = agg.setdefault(kind, [0.0, 0.0, 0])
+            a[0] += flops; a[1] += s.elapsed_time(e); a[2] += 1
+        kind = max(agg, key=lambda k: agg[k][1])
+        fl, ms, n = agg[kind]
+        achieved = fl / (ms / 1e3) / 1e12
+        tf32_peak = pk['bf16_tflops_sustained'] / 2.0
+        roof = {'bound': 'tensor', 'kernel': kind, 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / tf32_peak, 'traffic': None,
+                'peak_basis': 'tf32 operands: half of the %s bf16 sustained peak (%.1f TFLOP/s)' % (pk['source'], pk['bf16_tflops_sustained']),
+                'frac_of_bf16_peak': achieved / pk['bf16_tflops_sustained'],
+                'launches': n, 'avg_launch_us': ms * 1e3 / n, 'share_of_step': ms / ms_dev,
+                'all_kernels': {k: {'TFLOPs': v[0] / (v[1] / 1e3) / 1e12, 'ms_per_step': v[1] / args.steps, 'launches': v[2]}
+                                for k, v in agg.items()}}
+    if rank != 0:
+        return
+    line = {
+        'metric': 'train-step frames/sec at CATER 256x256', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 GEMMs / f32 elsewhere', 'data': 'synthetic',
+        'config': {'workload': 'AG2Vid CATER %dx%d generator train step (GCN -> layout -> SPADE, fwd+bwd+Adam), '
+                               'batch %d clips/GPU x %d frames' % (args.size, args.size, args.batch, args.frames),
+                   'loss': 'L1 image + box surrogate (discriminator is outside the path)',
+                   'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush',
+                   'parallelism': 'dp%d (clips sharded per rank, gradient all-reduce, SyncBN stats for SPADE)' % world,
+                   'conv_impl': args.conv_impl},
+        'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': int(launches),
+        'clocks': sampler.summary() if sampler else None,
+        'roofline': roof,
+        'cpu_baseline': ({k: cpu_base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')} if cpu_base else None),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

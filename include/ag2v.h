@@ -140,6 +140,9 @@ int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, lon
 int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
                       ag2v_stream_t stream);
 int ag2v_double_to_float(const double* src, int n, float* dst, ag2v_stream_t stream);
+/* dst = round-to-nearest TF32 of src (same layout; the tcgen05 TF32 path truncates, so GEMM
+ * operands are rounded where they are produced; this covers the externally produced segmap) */
+int ag2v_round_tf32(const float* src, float* dst, long long n, ag2v_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -67,3 +67,41 @@ def rel_l2(a, b):
 
 def golden(name):
     return torch.load(os.path.join(GOLDEN, name), map_location='cpu', weights_only=False)
+
+
+# ---- "dyadic" data: every TF32 product is exact --------------------------------
+# ReLU / LeakyReLU make the gradients of SPADE discontinuous: an activation whose
+# pre-activation lies within TF32 rounding of zero takes the other branch and its
+# gradient changes by O(1), not O(eps).  To check the backward strictly, tests use
+# segmaps and modulation weights made of small dyadic rationals (few mantissa
+# bits), for which TF32 operands and fp32 accumulation are EXACT, so the forward
+# pre-activations - and therefore every gate - agree with the fp32 reference.
+
+def dy_tensor(name, shape, seed, step, levels, density=1.0):
+    """Values k*step with integer |k| <= levels, a `density` fraction non-zero."""
+    r = _rng(name, seed)
+    k = r.randint(-levels, levels + 1, size=tuple(shape)).astype(np.float32)
+    if density < 1.0:
+        k = k * (r.random_sample(tuple(shape)) < density)
+    return torch.from_numpy((k * step).astype(np.float32))
+
+
+def dyadic_spade_state(state, seed=0, prefix_filter=None):
+    """Overwrite the SPADE modulation parameters inside a state_dict with dyadic values."""
+    out = dict(state)
+    for key, ref in state.items():
+        name = key.replace('.module.', '.')
+        shape = tuple(ref.shape)
+        if name.endswith('mlp_shared.0.weight'):
+            out[key] = dy_tensor(name, shape, seed, 0.125, 1, density=0.5)
+        elif name.endswith('mlp_shared.0.bias'):
+            out[key] = dy_tensor(name, shape, seed, 0.25, 1)
+        elif name.endswith('mlp_gamma.weight') or name.endswith('mlp_beta.weight'):
+            out[key] = dy_tensor(name, shape, seed, 0.0625, 1, density=0.5)
+        elif name.endswith('mlp_gamma.bias') or name.endswith('mlp_beta.bias'):
+            out[key] = dy_tensor(name, shape, seed, 0.125, 4)
+    return out
+
+
+def dyadic_seg(name, shape, seed, density):
+    return dy_tensor(name, shape, seed, 1.0, 1, density=density)

@@ -31,7 +31,7 @@ sys.path.insert(0, REF)
 torch.Tensor.cuda = lambda self, *a, **k: self
 torch.Tensor.get_device = lambda self: 0
 
-from _util import det_state, det_tensor  # noqa: E402
+from _util import det_state, det_tensor, dyadic_seg, dyadic_spade_state  # noqa: E402
 from ag2video_b200.config import cater_vocab, synthetic_batch  # noqa: E402
 
 from models.graph_models.graph import GraphTripleConv  # noqa: E402
@@ -176,12 +176,17 @@ def crop_case():
 # ---------------------------------------------------------------- K3 ------
 def spade_case():
     cases = {}
-    for name, C, L, r, Hs, B in [('c16_r8', 16, 8, 8, 32, 2), ('c8_r16', 8, 16, 16, 16, 3)]:
+    for name, C, L, r, Hs, B in [('c16_r8', 16, 8, 8, 32, 2), ('c8_r16', 8, 16, 16, 16, 3),
+                                 ('dy_c16_r8', 16, 8, 8, 32, 2), ('dy_c8_r16', 8, 16, 16, 16, 3)]:
         m = SPADE('spadesyncbatch3x3', C, L)
         load_det(m, 31)
+        dyadic = name.startswith('dy_')
+        if dyadic:          # exact TF32 products: gates agree, gradients can be compared strictly
+            m.load_state_dict(dyadic_spade_state(m.state_dict(), 31), strict=True)
         m.train()
         x = det_tensor('spade.x.%s' % name, (B, C, r, r), 5).mul(1.5).add(0.3).requires_grad_()
-        seg = det_tensor('spade.seg.%s' % name, (B, L, Hs, Hs), 5).requires_grad_()
+        seg = (dyadic_seg('spade.seg.%s' % name, (B, L, Hs, Hs), 5, 0.5) if dyadic
+               else det_tensor('spade.seg.%s' % name, (B, L, Hs, Hs), 5)).requires_grad_()
         state0 = {k: v.clone() for k, v in m.state_dict().items()}
         out = m(x, seg)
         cot = det_tensor('spade.cot.%s' % name, out.shape, 5)
@@ -199,12 +204,16 @@ def spade_case():
 def block_case():
     cases = {}
     opt = types.SimpleNamespace(norm_G='spectralspadesyncbatch3x3', semantic_nc=8)
-    for name, fin, fout in [('b16_8', 16, 8), ('b8_8', 8, 8)]:
+    for name, fin, fout in [('b16_8', 16, 8), ('b8_8', 8, 8), ('dy_b16_8', 16, 8), ('dy_b8_8', 8, 8)]:
         m = SPADEResnetBlock(fin, fout, opt)
         load_det(m, 41)
+        dyadic = name.startswith('dy_')
+        if dyadic:
+            m.load_state_dict(dyadic_spade_state(m.state_dict(), 41), strict=True)
         m.train()
         x = det_tensor('block.x.%s' % name, (2, fin, 8, 8), 6).requires_grad_()
-        seg = det_tensor('block.seg.%s' % name, (2, 8, 16, 16), 6).requires_grad_()
+        seg = (dyadic_seg('block.seg.%s' % name, (2, 8, 16, 16), 6, 0.5) if dyadic
+               else det_tensor('block.seg.%s' % name, (2, 8, 16, 16), 6)).requires_grad_()
         state0 = {k: v.clone() for k, v in m.state_dict().items()}
         out = m(x, seg)
         cot = det_tensor('block.cot.%s' % name, out.shape, 6)

@@ -82,18 +82,23 @@ def test_conv_epilogues(epi, impl):
 
 
 def test_tc_and_mma_agree_closely():
-    """Same TF32 products in both kernels: differences are accumulation order only."""
+    """Operands pre-rounded to TF32 (tcgen05 truncates, mma.sync rounds in registers):
+    identical products in both kernels, differences are accumulation order only."""
     import ag2video_b200.spade as sp
     g = torch.Generator().manual_seed(5)
     B, r, Cin, Nout = 2, 32, 128, 128
     x = torch.randn(B, Cin, r, r, generator=g).cuda().contiguous(memory_format=torch.channels_last)
     w = (torch.randn(Nout, Cin, 3, 3, generator=g) / 30).cuda()
     wpk, _ = sp._pack(w, None, None, None, False)
+    x = sp._seg_operand(x)          # rounded to TF32 like every GEMM operand of the path
     outs = []
-    for impl in (1, 2):
-        sp.CONV_IMPL = impl
-        out = torch.empty(B, r, r, Nout, device='cuda')
-        sp._conv(x, (r * r * Cin, r * Cin, Cin), B, r, r, Cin, wpk, None, Nout, out, (r * r * Nout, r * Nout, Nout), sp.EPI_BIAS)
-        outs.append(out)
-    sp.CONV_IMPL = 0
-    assert max_rel(outs[0], outs[1]) <= 5e-4
+    old = sp.CONV_IMPL
+    try:
+        for impl in (1, 2):
+            sp.CONV_IMPL = impl
+            out = torch.empty(B, r, r, Nout, device='cuda')
+            sp._conv(x, (r * r * Cin, r * Cin, Cin), B, r, r, Cin, wpk, None, Nout, out, (r * r * Nout, r * Nout, Nout), sp.EPI_BIAS)
+            outs.append(out)
+    finally:
+        sp.CONV_IMPL = old
+    assert max_rel(outs[0], outs[1]) <= 1e-5

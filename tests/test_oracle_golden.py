@@ -84,7 +84,7 @@ def test_crop_bbox_batch_matches_reference():
     assert max_rel(imgs.grad, c['dimgs']) <= TOL
 
 
-@pytest.mark.parametrize('name', ['c16_r8', 'c8_r16'])
+@pytest.mark.parametrize('name', ['c16_r8', 'c8_r16', 'dy_c16_r8', 'dy_c8_r16'])
 def test_spade_matches_reference(name):
     c = golden('spade.pt')[name]
     m = oops.SPADE('spadesyncbatch3x3', c['C'], c['L'])
@@ -103,7 +103,7 @@ def test_spade_matches_reference(name):
         assert max_rel(m(x, seg), c['out_eval']) <= TOL
 
 
-@pytest.mark.parametrize('name', ['b16_8', 'b8_8'])
+@pytest.mark.parametrize('name', ['b16_8', 'b8_8', 'dy_b16_8', 'dy_b8_8'])
 def test_spade_resnet_block_matches_reference(name):
     c = golden('spade_block.pt')[name]
     opt = types.SimpleNamespace(norm_G='spectralspadesyncbatch3x3', semantic_nc=8)
