@@ -169,6 +169,52 @@ __device__ void warp_wgrad(int M, int N, int K, Z z, X x, float* __restrict__ dW
   }
 }
 
+// ---------------------------------------------------------------------------
+// Deterministic incident-edge sums (the scatter_add of graph.py:89-91 and its
+// transpose).  One warp builds, in its private shared list, the rows of the edges
+// touching `node` — subject hits in edge order, then object hits in edge order (bit
+// 30 marks an object hit) — and then adds the source rows in exactly that order,
+// four independent loads in flight at a time.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int build_incident(int node, int b, int E, const int* s_idx, const int* o_idx,
+                                              const uint8_t* __restrict__ ind, int* lst) {
+  const int lane = threadIdx.x & 31;
+  int n = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int* idx = pass ? o_idx : s_idx;
+    for (int e0 = 0; e0 < E; e0 += 32) {
+      const int e = e0 + lane, m = b * E + e;
+      const bool hit = e < E && (ind == nullptr || ind[m] != 0) && idx[m] == node;
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (hit) lst[n + __popc(mask & ((1u << lane) - 1u))] = pass ? (m | (1 << 30)) : m;
+      n += __popc(mask);
+    }
+  }
+  __syncwarp();
+  return n;
+}
+
+// acc[c..c+3] = sum over the list of src[row, (object ? off_o : off_s) + c..c+3]
+__device__ __forceinline__ float4 incident_sum4(const float* src, int ld, int off_s, int off_o, int c,
+                                                const int* lst, int n) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < n; i += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i + j < n) {
+        const int ent = lst[i + j];
+        const int m = ent & ~(1 << 30);
+        v[j] = *reinterpret_cast<const float4*>(src + (size_t)m * ld + ((ent >> 30) ? off_o : off_s) + c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+  }
+  return acc;
+}
+
 struct GcnFwd {
   GcnDims d;
   const float *obj, *pred; const long long* edges; const uint8_t* ind;
@@ -290,21 +336,19 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_fwd_kernel(GcnFwd p) {
   }
   grid.sync();
   {  // stage 3: masked average pooling, subjects then objects, edge order   graph.py:79-100
-    const int total = R * H;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
-      const int node = i / H, c = i - node * H;
-      const int b = node / d.O;
-      float acc = 0.f; float cnt = 0.f;
-      for (int e = 0; e < d.E; ++e) {
-        const int m = b * d.E + e;
-        if (p.ind[m] && s_idx[m] == node) { acc += p.h2[(size_t)m * N2 + c]; cnt += 1.f; }
+    int* lst = reinterpret_cast<int*>(red) + (threadIdx.x >> 5) * 1024;
+    const int groups = (H + 127) >> 7, lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kWarps;
+    for (int task = gwarp; task < R * groups; task += nwarps) {
+      const int node = task / groups, c = (task - node * groups) * 128 + lane * 4;
+      const int n = build_incident(node, node / d.O, d.E, s_idx, o_idx, p.ind, lst);
+      if (c < H) {
+        float4 acc = incident_sum4(p.h2, N2, 0, H + d.Dpo, c, lst, n);
+        if (n > 0) { const float cnt = (float)n; acc.x /= cnt; acc.y /= cnt; acc.z /= cnt; acc.w /= cnt; }
+        *reinterpret_cast<float4*>(p.pooled + (size_t)node * H + c) = acc;
       }
-      for (int e = 0; e < d.E; ++e) {
-        const int m = b * d.E + e;
-        if (p.ind[m] && o_idx[m] == node) { acc += p.h2[(size_t)m * N2 + H + d.Dpo + c]; cnt += 1.f; }
-      }
-      p.pooled[i] = cnt > 0.f ? acc / cnt : acc;
-      if (c == 0) p.cnt[node] = cnt;
+      if (c == 0) p.cnt[node] = (float)n;
+      __syncwarp();
     }
   }
   grid.sync();
@@ -394,14 +438,14 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_bwd_kernel(GcnBwd p) {
   grid.sync();
   {  // F: transpose of the gather — every edge contributes, masked or not (graph.py:67-71)
     const int Din = d.Din, Dp = d.Dp;
-    const int total = R * Din;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
-      const int node = i / Din, c = i - node * Din;
-      const int b = node / d.O;
-      float acc = 0.f;
-      for (int e = 0; e < d.E; ++e) { const int m = b * d.E + e; if (s_idx[m] == node) acc += p.dT[(size_t)m * K1 + c]; }
-      for (int e = 0; e < d.E; ++e) { const int m = b * d.E + e; if (o_idx[m] == node) acc += p.dT[(size_t)m * K1 + Din + Dp + c]; }
-      p.dobj[i] = acc;
+    __syncthreads();
+    int* lst = reinterpret_cast<int*>(red) + (threadIdx.x >> 5) * 1024;
+    const int groups = (Din + 127) >> 7, lane = threadIdx.x & 31;
+    for (int task = gwarp; task < R * groups; task += total_warps) {
+      const int node = task / groups, c = (task - node * groups) * 128 + lane * 4;
+      const int n = build_incident(node, node / d.O, d.E, s_idx, o_idx, nullptr, lst);
+      if (c < Din) *reinterpret_cast<float4*>(p.dobj + (size_t)node * Din + c) = incident_sum4(p.dT, K1, 0, Din + Dp, c, lst, n);
+      __syncwarp();
     }
     const int total_p = M * Dp;
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < total_p; i += gridDim.x * kThreads) {
@@ -415,7 +459,8 @@ static int gcn_check(const GcnDims& d) {
   AG2V_REQUIRE(d.B > 0 && d.O > 0 && d.E > 0, "gcn_layer: empty graph B=%d O=%d E=%d", d.B, d.O, d.E);
   AG2V_REQUIRE(d.Din % 8 == 0 && d.Dp % 8 == 0 && d.H % 8 == 0 && d.Dout % 8 == 0 && d.Dpo % 8 == 0,
                "gcn_layer: feature sizes must be multiples of 8 (Din=%d Dp=%d H=%d Dout=%d Dpo=%d)", d.Din, d.Dp, d.H, d.Dout, d.Dpo);
-  AG2V_REQUIRE(d.M() <= 8192, "gcn_layer: at most 8192 edge rows per call (got %d)", d.M());
+  AG2V_REQUIRE(d.M() <= 8192 && d.E <= 512, "gcn_layer: at most 8192 edge rows per call and 512 edges per clip (got %d, %d)", d.M(), d.E);
+  AG2V_REQUIRE(d.Din % 4 == 0 && d.H % 4 == 0, "gcn_layer: Din and H must be multiples of 4");
   return AG2V_OK;
 }
 

@@ -7,14 +7,15 @@
 
 namespace ag2v {
 int conv3x3_check(const ConvParams& p, int epi);
-int conv3x3_mma(const ConvParams& p, int epi, int round_out, cudaStream_t stream);
+int conv3x3_mma(const ConvParams& p, int epi, int round_out, int precise, cudaStream_t stream);
 int conv3x3_tc(const ConvParams& p, int epi, int round_out, cudaStream_t stream);   // may return AG2V_ERR_UNSUPPORTED
 bool conv3x3_tc_supported(const ConvParams& p, int epi);
 }  // namespace ag2v
 
 using namespace ag2v;
 
-// impl: 0 = auto (tcgen05 when supported), 1 = force mma.sync, 2 = force tcgen05 (error if unsupported)
+// impl: 0 = auto (tcgen05 when supported), 1 = force mma.sync, 2 = force tcgen05 (error if unsupported),
+//       3 = mma.sync with 3xTF32 products (fp32-class accuracy; validation mode)
 extern "C" int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in_sx, int B, int Hh,
                             int Ww, int Cin, const float* wpk, const float* bias, int Nout, float* out,
                             long long out_sb, long long out_sy, long long out_sx, int epilogue, int round_out,
@@ -29,14 +30,15 @@ extern "C" int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, l
   p.gate = gate;
   int rc = conv3x3_check(p, epilogue);
   if (rc) return rc;
-  if (impl == 1) return conv3x3_mma(p, epilogue, round_out, stream);
+  if (impl == 1) return conv3x3_mma(p, epilogue, round_out, 0, stream);
+  if (impl == 3) return conv3x3_mma(p, epilogue, 0, 1, stream);
   if (impl == 2) {
     if (!conv3x3_tc_supported(p, epilogue))
       return fail(AG2V_ERR_UNSUPPORTED, "conv3x3: shape not supported by the tcgen05 kernel (Cin=%d Nout=%d %dx%d)", Cin, Nout, Hh, Ww);
     return conv3x3_tc(p, epilogue, round_out, stream);
   }
   if (conv3x3_tc_supported(p, epilogue)) return conv3x3_tc(p, epilogue, round_out, stream);
-  return conv3x3_mma(p, epilogue, round_out, stream);
+  return conv3x3_mma(p, epilogue, round_out, 0, stream);
 }
 
 extern "C" int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue) {

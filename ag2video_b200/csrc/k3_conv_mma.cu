@@ -41,8 +41,10 @@ __device__ __forceinline__ void mma_16n8k8(float (&c)[4], const uint32_t (&a)[4]
 
 __device__ __forceinline__ int swz(int row, int chunk, int off) { return row * BK + (((chunk ^ (row & 7)) << 2) | off); }
 
-template <int EPI, bool ROUND_OUT>
-__global__ void __launch_bounds__(kConvThreads, 2) conv3x3_mma_kernel(ConvParams p) {
+// PRECISE: every product is split hi/lo (3xTF32, fp32-class accuracy).  Validation mode:
+// it separates logic errors from TF32 rounding in end-to-end comparisons.
+template <int EPI, bool ROUND_OUT, bool PRECISE>
+__global__ void __launch_bounds__(kConvThreads, PRECISE ? 1 : 2) conv3x3_mma_kernel(ConvParams p) {
   extern __shared__ __align__(16) float conv_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -116,23 +118,28 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3x3_mma_kernel(ConvParams
     const float* Bs = As + BM * BK;
 #pragma unroll
     for (int ks = 0; ks < BK / 8; ++ks) {
-      uint32_t bf[4][2];
+      uint32_t bf[4][2], bl[4][2];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int n = wn * 32 + nt * 8 + g;
-        bf[nt][0] = to_tf32(Bs[swz(n, 2 * ks, t)]);
-        bf[nt][1] = to_tf32(Bs[swz(n, 2 * ks + 1, t)]);
+        const float b0 = Bs[swz(n, 2 * ks, t)], b1 = Bs[swz(n, 2 * ks + 1, t)];
+        bf[nt][0] = to_tf32(b0); bf[nt][1] = to_tf32(b1);
+        if (PRECISE) { bl[nt][0] = to_tf32(b0 - __uint_as_float(bf[nt][0])); bl[nt][1] = to_tf32(b1 - __uint_as_float(bf[nt][1])); }
       }
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         const int r = wm * 64 + mt * 16 + g;
-        uint32_t af[4];
-        af[0] = to_tf32(As[swz(r, 2 * ks, t)]);
-        af[1] = to_tf32(As[swz(r + 8, 2 * ks, t)]);
-        af[2] = to_tf32(As[swz(r, 2 * ks + 1, t)]);
-        af[3] = to_tf32(As[swz(r + 8, 2 * ks + 1, t)]);
+        float av[4];
+        av[0] = As[swz(r, 2 * ks, t)]; av[1] = As[swz(r + 8, 2 * ks, t)];
+        av[2] = As[swz(r, 2 * ks + 1, t)]; av[3] = As[swz(r + 8, 2 * ks + 1, t)];
+        uint32_t af[4], al[4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_16n8k8(acc[mt][nt], af, bf[nt]);
+        for (int i = 0; i < 4; ++i) { af[i] = to_tf32(av[i]); if (PRECISE) al[i] = to_tf32(av[i] - __uint_as_float(af[i])); }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          if (PRECISE) { mma_16n8k8(acc[mt][nt], al, bf[nt]); mma_16n8k8(acc[mt][nt], af, bl[nt]); }
+          mma_16n8k8(acc[mt][nt], af, bf[nt]);
+        }
       }
     }
   }
@@ -206,26 +213,36 @@ int conv3x3_check(const ConvParams& p, int epi) {
   return AG2V_OK;
 }
 
-template <int EPI, bool RO>
+template <int EPI, bool RO, bool PR>
 static int launch_mma(const ConvParams& p, cudaStream_t stream) {
   const long long P = (long long)p.B * p.Hh * p.Ww;
   dim3 grid((unsigned)ceil_div_ll(P, BM), (unsigned)ceil_div(p.Nout, BN));
   const size_t smem = (size_t)STAGES * kStageFloats * sizeof(float);
-  AG2V_CUDA(cudaFuncSetAttribute(conv3x3_mma_kernel<EPI, RO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv3x3_mma_kernel<EPI, RO><<<grid, kConvThreads, smem, stream>>>(p);
+  AG2V_CUDA(cudaFuncSetAttribute(conv3x3_mma_kernel<EPI, RO, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv3x3_mma_kernel<EPI, RO, PR><<<grid, kConvThreads, smem, stream>>>(p);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
 
-int conv3x3_mma(const ConvParams& p, int epi, int round_out, cudaStream_t stream) {
+// precise != 0: 3xTF32 products and no output rounding (validation mode)
+int conv3x3_mma(const ConvParams& p, int epi, int round_out, int precise, cudaStream_t stream) {
   int rc = conv3x3_check(p, epi);
   if (rc) return rc;
+  if (precise) {
+    switch (epi) {
+      case EPI_BIAS: return launch_mma<EPI_BIAS, false, true>(p, stream);
+      case EPI_BIAS_RELU: return launch_mma<EPI_BIAS_RELU, false, true>(p, stream);
+      case EPI_SPADE: return launch_mma<EPI_SPADE, false, true>(p, stream);
+      case EPI_GATE: return launch_mma<EPI_GATE, false, true>(p, stream);
+      case EPI_ACCUM: return launch_mma<EPI_ACCUM, false, true>(p, stream);
+    }
+  }
   switch (epi) {
-    case EPI_BIAS: return round_out ? launch_mma<EPI_BIAS, true>(p, stream) : launch_mma<EPI_BIAS, false>(p, stream);
-    case EPI_BIAS_RELU: return round_out ? launch_mma<EPI_BIAS_RELU, true>(p, stream) : launch_mma<EPI_BIAS_RELU, false>(p, stream);
-    case EPI_SPADE: return round_out ? launch_mma<EPI_SPADE, true>(p, stream) : launch_mma<EPI_SPADE, false>(p, stream);
-    case EPI_GATE: return round_out ? launch_mma<EPI_GATE, true>(p, stream) : launch_mma<EPI_GATE, false>(p, stream);
-    case EPI_ACCUM: return launch_mma<EPI_ACCUM, false>(p, stream);
+    case EPI_BIAS: return round_out ? launch_mma<EPI_BIAS, true, false>(p, stream) : launch_mma<EPI_BIAS, false, false>(p, stream);
+    case EPI_BIAS_RELU: return round_out ? launch_mma<EPI_BIAS_RELU, true, false>(p, stream) : launch_mma<EPI_BIAS_RELU, false, false>(p, stream);
+    case EPI_SPADE: return round_out ? launch_mma<EPI_SPADE, true, false>(p, stream) : launch_mma<EPI_SPADE, false, false>(p, stream);
+    case EPI_GATE: return round_out ? launch_mma<EPI_GATE, true, false>(p, stream) : launch_mma<EPI_GATE, false, false>(p, stream);
+    case EPI_ACCUM: return launch_mma<EPI_ACCUM, false, false>(p, stream);
   }
   return fail(AG2V_ERR_ARG, "conv3x3: unknown epilogue %d", epi);
 }

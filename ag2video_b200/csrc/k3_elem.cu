@@ -37,7 +37,7 @@ struct ChanArgs {
   float* part;                      // [nsplit][NS][C]
   // MODE 1
   const float* dout; const float* out; const float* gamma; const float* mean; const float* rstd;
-  float* dgb; float* dxhat; float slope; int act;
+  float* dgb; float* dxhat; float slope; int act; int round_ops;
 };
 
 template <int MODE>
@@ -80,8 +80,13 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
           dxh.z = g.z * (1.f + gv.z); dxh.w = g.w * (1.f + gv.w);
           float* row = a.dgb + (size_t)p * 2 * C;
           // the GEMM operand copies are rounded to TF32; the sums below use the fp32 values
-          *reinterpret_cast<float4*>(row + gb8_col(c, 0)) = make_float4(elem_round_tf32(dgam.x), elem_round_tf32(dgam.y), elem_round_tf32(dgam.z), elem_round_tf32(dgam.w));
-          *reinterpret_cast<float4*>(row + gb8_col(c, 1)) = make_float4(elem_round_tf32(g.x), elem_round_tf32(g.y), elem_round_tf32(g.z), elem_round_tf32(g.w));
+          if (a.round_ops) {
+            *reinterpret_cast<float4*>(row + gb8_col(c, 0)) = make_float4(elem_round_tf32(dgam.x), elem_round_tf32(dgam.y), elem_round_tf32(dgam.z), elem_round_tf32(dgam.w));
+            *reinterpret_cast<float4*>(row + gb8_col(c, 1)) = make_float4(elem_round_tf32(g.x), elem_round_tf32(g.y), elem_round_tf32(g.z), elem_round_tf32(g.w));
+          } else {
+            *reinterpret_cast<float4*>(row + gb8_col(c, 0)) = dgam;
+            *reinterpret_cast<float4*>(row + gb8_col(c, 1)) = g;
+          }
           *reinterpret_cast<float4*>(a.dxhat + off) = dxh;
           s[0].x += g.x; s[0].y += g.y; s[0].z += g.z; s[0].w += g.w;
           s[1].x += dgam.x; s[1].y += dgam.y; s[1].z += dgam.z; s[1].w += dgam.w;
@@ -181,7 +186,7 @@ spade_bwd_dx_kernel(const float* __restrict__ x, float* __restrict__ dxhat, cons
 // With two sources (gamma, beta) the combined channel index follows gb8_col.
 __global__ void pack_w3x3_kernel(const float* __restrict__ wa, const float* __restrict__ wb,
                                  const float* __restrict__ ba, const float* __restrict__ bb, int Co, int Ci,
-                                 int dgrad, float* __restrict__ dst, float* __restrict__ bias_dst) {
+                                 int dgrad, int round_ops, float* __restrict__ dst, float* __restrict__ bias_dst) {
   const int Ntot = wb ? 2 * Co : Co;
   const long long total = 9LL * Ntot * Ci;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -192,7 +197,8 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ wa, const float* __re
     if (wb) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
     const float* src = is_b ? wb : wa;
     const int t = dgrad ? 8 - tap : tap;
-    dst[i] = elem_round_tf32(src[((size_t)co * Ci + ci) * 9 + t]);     // tcgen05 kind::tf32 truncates: round here
+    const float w = src[((size_t)co * Ci + ci) * 9 + t];
+    dst[i] = round_ops ? elem_round_tf32(w) : w;                     // tcgen05 kind::tf32 truncates: round here
   }
   if (bias_dst != nullptr && blockIdx.x == 0) {
     for (int n = threadIdx.x; n < Ntot; n += blockDim.x) {
@@ -297,8 +303,8 @@ extern "C" int ag2v_bn_eval_stats(const float* running_mean, const float* runnin
 // per-channel sums (doubles, [4][C]): sum g, sum g*xhat, sum dxhat, sum dxhat*xhat.
 extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma,
                                   const float* mean, const float* rstd, long long P, int C, int act,
-                                  float slope, float* dgb, float* dxhat, float* partial, double* sums,
-                                  cudaStream_t stream) {
+                                  float slope, int round_ops, float* dgb, float* dxhat, float* partial,
+                                  double* sums, cudaStream_t stream) {
   int rc = chan_check(P, C);
   if (rc) return rc;
   AG2V_REQUIRE(C % 8 == 0, "spade_bwd_pre: C %% 8 == 0 required (C=%d)", C);
@@ -306,7 +312,7 @@ extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const flo
   ChanGeom g = chan_geom(P, C);
   ChanArgs a{};
   a.x = x; a.P = P; a.C = C; a.part = partial; a.dout = dout; a.out = out; a.gamma = gamma;
-  a.mean = mean; a.rstd = rstd; a.dgb = dgb; a.dxhat = dxhat; a.slope = slope; a.act = act;
+  a.mean = mean; a.rstd = rstd; a.dgb = dgb; a.dxhat = dxhat; a.slope = slope; a.act = act; a.round_ops = round_ops;
   chan_partial_kernel<1><<<g.nsplit, kElemThreads, 0, stream>>>(a, g);
   AG2V_LAUNCH_CHECK();
   chan_reduce_kernel<<<ceil_div(4 * C, 256), 256, 0, stream>>>(partial, g.nsplit, 4, C, sums);
@@ -332,12 +338,12 @@ extern "C" int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean
 
 // wa/wb: OIHW [Co, Ci, 3, 3] (wb null for a single conv); see pack_w3x3_kernel.
 extern "C" int ag2v_pack_w3x3(const float* wa, const float* wb, const float* ba, const float* bb, int Co, int Ci,
-                              int dgrad, float* dst, float* bias_dst, cudaStream_t stream) {
+                              int dgrad, int round_ops, float* dst, float* bias_dst, cudaStream_t stream) {
   AG2V_REQUIRE(wa && dst && Co > 0 && Ci > 0, "pack_w3x3: bad arguments");
   AG2V_REQUIRE(!wb || Co % 8 == 0, "pack_w3x3: gamma/beta packing needs Co %% 8 == 0");
   long long total = 9LL * (wb ? 2 * Co : Co) * Ci;
   int blocks = (int)(ceil_div_ll(total, 256) > 2368 ? 2368 : ceil_div_ll(total, 256));
-  pack_w3x3_kernel<<<blocks, 256, 0, stream>>>(wa, wb, ba, bb, Co, Ci, dgrad, dst, bias_dst);
+  pack_w3x3_kernel<<<blocks, 256, 0, stream>>>(wa, wb, ba, bb, Co, Ci, dgrad, round_ops, dst, bias_dst);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

@@ -39,7 +39,8 @@ struct WgradParams {
   int nsplit, chunks_per_split, ctiles;
 };
 
-__global__ void __launch_bounds__(kWgThreads, 2) wgrad3x3_mma_kernel(WgradParams p) {
+template <bool PRECISE>
+__global__ void __launch_bounds__(kWgThreads, PRECISE ? 1 : 2) wgrad3x3_mma_kernel(WgradParams p) {
   extern __shared__ __align__(16) float wg_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -110,23 +111,26 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad3x3_mma_kernel(WgradParams
 #pragma unroll
     for (int ks = 0; ks < WG_K / 8; ++ks) {
       const int k_lo = (ks * 8 + t) * WG_LD, k_hi = (ks * 8 + t + 4) * WG_LD;
-      uint32_t bf[4][2];
+      uint32_t bf[4][2], bl[4][2];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int c = wn * 32 + nt * 8 + g;
-        bf[nt][0] = wg_tf32(Bs[k_lo + c]);
-        bf[nt][1] = wg_tf32(Bs[k_hi + c]);
+        const float b0 = Bs[k_lo + c], b1 = Bs[k_hi + c];
+        bf[nt][0] = wg_tf32(b0); bf[nt][1] = wg_tf32(b1);
+        if (PRECISE) { bl[nt][0] = wg_tf32(b0 - __uint_as_float(bf[nt][0])); bl[nt][1] = wg_tf32(b1 - __uint_as_float(bf[nt][1])); }
       }
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         const int n = wm * 64 + mt * 16 + g;
-        uint32_t af[4];
-        af[0] = wg_tf32(As[k_lo + n]);
-        af[1] = wg_tf32(As[k_lo + n + 8]);
-        af[2] = wg_tf32(As[k_hi + n]);
-        af[3] = wg_tf32(As[k_hi + n + 8]);
+        const float av[4] = {As[k_lo + n], As[k_lo + n + 8], As[k_hi + n], As[k_hi + n + 8]};
+        uint32_t af[4], al[4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) wg_mma(acc[mt][nt], af, bf[nt]);
+        for (int i = 0; i < 4; ++i) { af[i] = wg_tf32(av[i]); if (PRECISE) al[i] = wg_tf32(av[i] - __uint_as_float(af[i])); }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          if (PRECISE) { wg_mma(acc[mt][nt], al, bf[nt]); wg_mma(acc[mt][nt], af, bl[nt]); }
+          wg_mma(acc[mt][nt], af, bf[nt]);
+        }
       }
     }
   }
@@ -176,7 +180,8 @@ extern "C" int ag2v_wgrad3x3_nsplit(int B, int Hh, int Ww, int Nout, int Cin) {
 // dy [B*Hh*Ww, Nout] contiguous; x is a [B, Hh, Ww, Cin] view with element strides.
 // part receives nsplit partial [9][Nout][Cin] blocks (reduce with ag2v_unpack_dw3x3).
 extern "C" int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, long long x_sy,
-                             long long x_sx, int Cin, int B, int Hh, int Ww, float* part, cudaStream_t stream) {
+                             long long x_sx, int Cin, int B, int Hh, int Ww, float* part, int precise,
+                             cudaStream_t stream) {
   AG2V_REQUIRE(dy && x && part, "wgrad3x3: null pointer");
   AG2V_REQUIRE(B > 0 && Hh > 0 && Ww > 0 && Nout > 0 && Cin > 0, "wgrad3x3: bad sizes");
   AG2V_REQUIRE(Nout % 4 == 0 && Cin % 4 == 0, "wgrad3x3: Nout and Cin must be multiples of 4 (Nout=%d Cin=%d)", Nout, Cin);
@@ -188,9 +193,14 @@ extern "C" int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long lon
   int ntiles;
   wgrad_geometry((long long)B * Hh * Ww, Nout, Cin, &p.nsplit, &p.chunks_per_split, &p.ctiles, &ntiles);
   const size_t smem = (size_t)WG_STAGES * kWgStageFloats * sizeof(float);
-  AG2V_CUDA(cudaFuncSetAttribute(wgrad3x3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ntiles * p.ctiles, 9, p.nsplit);
-  wgrad3x3_mma_kernel<<<grid, kWgThreads, smem, stream>>>(p);
+  if (precise) {
+    AG2V_CUDA(cudaFuncSetAttribute(wgrad3x3_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad3x3_mma_kernel<true><<<grid, kWgThreads, smem, stream>>>(p);
+  } else {
+    AG2V_CUDA(cudaFuncSetAttribute(wgrad3x3_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad3x3_mma_kernel<false><<<grid, kWgThreads, smem, stream>>>(p);
+  }
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

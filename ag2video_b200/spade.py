@@ -30,21 +30,25 @@ L.register('ag2v_chan_partial_floats', c_sz, [c_ll, c_i, c_i])
 L.register('ag2v_bn_stats', c_i, [c_p, c_ll, c_i, c_p, c_p, c_p])
 L.register('ag2v_bn_finalize', c_i, [c_p, c_d, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p])
 L.register('ag2v_bn_eval_stats', c_i, [c_p, c_p, c_i, c_f, c_p, c_p, c_p])
-L.register('ag2v_spade_bwd_pre', c_i, [c_p] * 6 + [c_ll, c_i, c_i, c_f] + [c_p] * 4 + [c_p])
+L.register('ag2v_spade_bwd_pre', c_i, [c_p] * 6 + [c_ll, c_i, c_i, c_f, c_i] + [c_p] * 4 + [c_p])
 L.register('ag2v_spade_bwd_dx', c_i, [c_p] * 5 + [c_d, c_i, c_ll, c_i, c_p])
-L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_p, c_p, c_p])
+L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_unpack_dw3x3', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_p, c_p])
 L.register('ag2v_round_tf32', c_i, [c_p, c_p, c_ll, c_p])
 L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 5)
-L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p])
+L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p])
 L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_ll, c_ll, c_ll,
                                  c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_i, c_p])
 L.register('ag2v_conv3x3_tc_supported', c_i, [c_i] * 6)
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_SPADE, EPI_GATE, EPI_ACCUM = 0, 1, 2, 3, 4
 NHIDDEN = 128                      # "Yes, hardcoded" (normalization.py:84)
-CONV_IMPL = 0                      # 0 auto, 1 mma.sync, 2 tcgen05 (tests flip this)
+CONV_IMPL = 0                      # 0 auto, 1 mma.sync, 2 tcgen05, 3 mma.sync 3xTF32 (validation; tests flip this)
+
+
+def _precise():
+    return CONV_IMPL == 3
 
 _sync_group = {'group': None, 'enabled': False}
 
@@ -71,9 +75,11 @@ def _seg_operand(seg):
     """NHWC copy of the segmap rounded to TF32 (it is the A operand of the shared
     convolution and of its weight gradient; tcgen05's TF32 path truncates)."""
     src = _cl(seg.detach().float())
-    dst = torch.empty_like(src, memory_format=torch.channels_last)
+    if _precise():
+        return src
     if src.numel() % 4:
         raise NotImplementedError('segmap element count must be a multiple of 4')
+    dst = torch.empty_like(src, memory_format=torch.channels_last)
     L.check(L.lib().ag2v_round_tf32(L.ptr(src), L.ptr(dst), src.numel(), L.stream()))
     return dst
 
@@ -113,8 +119,8 @@ def _pack(wa, wb, ba, bb, dgrad):
     Ntot = 2 * Co if wb is not None else Co
     dst = torch.empty(9 * Ntot * Ci, device=wa.device, dtype=torch.float32)
     bias = torch.empty(Ntot, device=wa.device, dtype=torch.float32) if not dgrad else None
-    L.check(L.lib().ag2v_pack_w3x3(L.ptr(wa), L.ptr(wb), L.ptr(ba), L.ptr(bb), Co, Ci, int(dgrad), L.ptr(dst),
-                                   L.ptr(bias), L.stream()))
+    L.check(L.lib().ag2v_pack_w3x3(L.ptr(wa), L.ptr(wb), L.ptr(ba), L.ptr(bb), Co, Ci, int(dgrad), int(not _precise()),
+                                   L.ptr(dst), L.ptr(bias), L.stream()))
     return dst, bias
 
 
@@ -124,7 +130,7 @@ def _wgrad(dy, Nout, x, x_strides, Cin, B, Hh, Ww, two, like_a, like_b):
     part = torch.empty(nsplit * 9 * Nout * Cin, device=dy.device, dtype=torch.float32)
     with _Timed('wgrad3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout):
         L.check(lib.ag2v_wgrad3x3(L.ptr(dy), Nout, L.ptr(x), x_strides[0], x_strides[1], x_strides[2], Cin, B, Hh, Ww,
-                                  L.ptr(part), L.stream()))
+                                  L.ptr(part), int(_precise()), L.stream()))
     dwa = torch.empty_like(like_a, memory_format=torch.contiguous_format)
     dwb = torch.empty_like(like_b, memory_format=torch.contiguous_format) if two else None
     Co = Nout // 2 if two else Nout
@@ -238,7 +244,8 @@ class _SpadeFn(torch.autograd.Function):
         part = torch.empty(lib.ag2v_chan_partial_floats(P, C, 4), device=dev, dtype=torch.float32)
         sums = torch.empty(4 * C, device=dev, dtype=torch.float64)
         L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), P, C,
-                                       act, float(slope), L.ptr(dgb), L.ptr(dx), L.ptr(part), L.ptr(sums), L.stream()))
+                                       act, float(slope), int(not _precise()), L.ptr(dgb), L.ptr(dx), L.ptr(part),
+                                       L.ptr(sums), L.stream()))
         db = torch.empty(2 * C, device=dev, dtype=torch.float32)     # [sum g | sum g*xhat] = [d bias_beta | d bias_gamma]
         L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, L.ptr(db), L.stream()))
         if training:
@@ -315,7 +322,7 @@ class SPADE(nn.Module):
         return tuple((t.data_ptr(), t._version) for t in ts)
 
     def _packed(self, w_sh, b_sh, w_g, b_g, w_b, b_b):
-        key = self._key(w_sh, b_sh, w_g, b_g, w_b, b_b)
+        key = self._key(w_sh, b_sh, w_g, b_g, w_b, b_b) + (_precise(),)
         if self._pk is None or self._pk['key'] != key:
             w1, b1 = _pack(w_sh.contiguous(), None, b_sh, None, False)
             w2, b2 = _pack(w_g.contiguous(), w_b.contiguous(), b_g, b_b, False)
@@ -323,7 +330,7 @@ class SPADE(nn.Module):
         return self._pk
 
     def _packed_t(self, w_sh, w_g, w_b):
-        key = self._key(w_sh, w_g, w_b)
+        key = self._key(w_sh, w_g, w_b) + (_precise(),)
         if self._pkt is None or self._pkt['key'] != key:
             w1t, _ = _pack(w_sh.contiguous(), None, None, None, True)
             w2t, _ = _pack(w_g.contiguous(), w_b.contiguous(), None, None, True)

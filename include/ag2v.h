@@ -109,14 +109,16 @@ int ag2v_bn_eval_stats(const float* running_mean, const float* running_var, int 
  * gradient).  With wb != NULL, (wa, wb) = (mlp_gamma, mlp_beta) are interleaved in
  * groups of 8 channels so one GEMM yields gamma and beta in the same thread. */
 int ag2v_pack_w3x3(const float* wa, const float* wb, const float* ba, const float* bb, int Co, int Ci, int dgrad,
-                   float* dst, float* bias_dst, ag2v_stream_t stream);
+                   int round_ops, float* dst, float* bias_dst, ag2v_stream_t stream);
 
 /* 3x3, pad 1 implicit-GEMM convolution on an NHWC view (element strides in_s*; the
  * nearest down-sample of normalization.py:102 is a strided view of the segmap):
  *   epilogue 0: +bias   1: relu(+bias) (mlp_shared, :103)
  *            2: SPADE — Nout = 2C gamma|beta, out = act((x-mean)*rstd*(1+gamma)+beta) (:104-108)
  *            3: out = gate > 0 ? acc : 0     4: out += acc (gradient into the shared segmap)
- * impl 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel. */
+ * impl 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel, 3 = mma.sync with 3xTF32 products
+ * (fp32-class accuracy, validation mode).  round_ops / round_out: round the stored GEMM operands
+ * to nearest TF32 (the tcgen05 TF32 path truncates). */
 int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in_sx, int B, int Hh, int Ww, int Cin,
                  const float* wpk, const float* bias, int Nout, float* out, long long out_sb, long long out_sy,
                  long long out_sx, int epilogue, int round_out, const float* x, const float* mean,
@@ -128,15 +130,15 @@ int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epil
  * per-channel sums [4][C] (sum g, sum g*xhat, sum dxhat, sum dxhat*xhat); pass 2 turns
  * dxhat into dx (batch-norm backward) in place. */
 int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma, const float* mean,
-                       const float* rstd, long long P, int C, int act, float slope, float* dgb, float* dxhat,
-                       float* partial, double* sums, ag2v_stream_t stream);
+                       const float* rstd, long long P, int C, int act, float slope, int round_ops, float* dgb,
+                       float* dxhat, float* partial, double* sums, ag2v_stream_t stream);
 int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean, const float* rstd, const double* sums,
                       double count, int training, long long P, int C, ag2v_stream_t stream);
 
 /* weight gradient of a 3x3 conv: split-K partials, then reduction + scatter to OIHW */
 int ag2v_wgrad3x3_nsplit(int B, int Hh, int Ww, int Nout, int Cin);
 int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, long long x_sy, long long x_sx, int Cin,
-                  int B, int Hh, int Ww, float* part, ag2v_stream_t stream);
+                  int B, int Hh, int Ww, float* part, int precise, ag2v_stream_t stream);
 int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
                       ag2v_stream_t stream);
 int ag2v_double_to_float(const double* src, int n, float* dst, ag2v_stream_t stream);

@@ -41,7 +41,11 @@ def _grads(m):
     return {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
 
 
-def _check(got, want, strict, what):
+def _check(got, want, strict, what, floor=0.0):
+    """`floor`: magnitude below which a tensor is numerically zero (e.g. the gradient of a
+    conv bias that feeds a batch norm is exactly 0 in exact arithmetic)."""
+    if float(want.abs().max()) <= floor and float(got.abs().max()) <= 10 * max(floor, 1e-30):
+        return
     if strict:
         assert max_rel(got, want) <= TOL, (what, max_rel(got, want))
     else:
@@ -91,8 +95,9 @@ def test_spade_resnet_block_golden(name):
     _check(x.grad, c['dx'], strict, 'dx')
     _check(seg.grad, c['dseg'], strict, 'dseg')
     g = _grads(m)
+    scale = max(float(v.abs().max()) for v in c['dparams'].values())
     for k, v in c['dparams'].items():
-        _check(g[k], v, strict, k)
+        _check(g[k], v, strict, k, floor=1e-5 * scale)
     for k, v in c['state_after'].items():
         assert max_rel(m.state_dict()[k].float(), v.float()) <= 1e-4, k
 

@@ -1,0 +1,36 @@
+"""Kernel-time breakdown of one bench step (torch.profiler / CUPTI), top kernels by GPU time.
+Usage on the GPU box: python tools/profile_step.py [size] [batch] > gpurun_out/step_profile.txt"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ag2video_b200.config import make_opt, synthetic_batch  # noqa: E402
+from ag2video_b200.networks import AG2VideoModel  # noqa: E402
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+dev = torch.device('cuda', 0)
+opt = make_opt(size, batch_size=B)
+model = AG2VideoModel(opt, dev).train()
+optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.5, 0.999), fused=True)
+b = synthetic_batch(B=B, F=4, image_size=size, seed=1, device=dev)
+
+
+def step():
+    out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+    loss = (out[0] - b['imgs']).abs().mean() + 10 * (out[1] - b['boxes'])[:, 1:].abs().mean()
+    optim.zero_grad(set_to_none=True)
+    loss.backward()
+    optim.step()
+
+
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=90))
