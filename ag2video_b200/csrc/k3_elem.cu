@@ -16,7 +16,7 @@ __device__ __forceinline__ float elem_round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-constexpr int kMaxSplit = 592;       // 4 CTAs per SM
+constexpr int kMaxSplit = 296;       // 2 CTAs per SM
 
 struct ChanGeom { int cx, py, chunks, nsplit; };
 
@@ -113,14 +113,31 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
   }
 }
 
-// sums[i][c] (double) = sum over splits of part[split][i][c], in split order
-__global__ void chan_reduce_kernel(const float* __restrict__ part, int nsplit, int NS, int C, double* __restrict__ sums) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= NS * C) return;
-  const int i = idx / C, c = idx - i * C;
+// sums[i][c] (double) = sum over splits of part[split][i][c].  Block = 32 columns x 8
+// split lanes (coalesced 128-byte rows); fixed summation order => deterministic.
+__global__ void __launch_bounds__(256) chan_reduce_kernel(const float* __restrict__ part, int nsplit, int NSC,
+                                                          double* __restrict__ sums) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
   double acc = 0.0;
-  for (int s = 0; s < nsplit; ++s) acc += (double)part[((size_t)s * NS + i) * C + c];
-  sums[idx] = acc;
+  if (col < NSC) {
+    int s = ty;
+    for (; s + 24 < nsplit; s += 32) {
+      const float a = part[(size_t)s * NSC + col], b = part[(size_t)(s + 8) * NSC + col];
+      const float c = part[(size_t)(s + 16) * NSC + col], d = part[(size_t)(s + 24) * NSC + col];
+      acc += (double)a; acc += (double)b; acc += (double)c; acc += (double)d;
+    }
+    for (; s < nsplit; s += 8) acc += (double)part[(size_t)s * NSC + col];
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < NSC) {
+    double t = red[0][tx];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) t += red[r][tx];
+    sums[col] = t;
+  }
 }
 
 // F.batch_norm(training=True, momentum, eps): biased variance for normalisation,
@@ -274,7 +291,7 @@ extern "C" int ag2v_bn_stats(const float* x, long long P, int C, float* partial,
   a.x = x; a.P = P; a.C = C; a.part = partial;
   chan_partial_kernel<0><<<g.nsplit, kElemThreads, 0, stream>>>(a, g);
   AG2V_LAUNCH_CHECK();
-  chan_reduce_kernel<<<ceil_div(2 * C, 256), 256, 0, stream>>>(partial, g.nsplit, 2, C, sums);
+  chan_reduce_kernel<<<ceil_div(2 * C, 32), 256, 0, stream>>>(partial, g.nsplit, 2 * C, sums);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
@@ -315,7 +332,7 @@ extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const flo
   a.mean = mean; a.rstd = rstd; a.dgb = dgb; a.dxhat = dxhat; a.slope = slope; a.act = act; a.round_ops = round_ops;
   chan_partial_kernel<1><<<g.nsplit, kElemThreads, 0, stream>>>(a, g);
   AG2V_LAUNCH_CHECK();
-  chan_reduce_kernel<<<ceil_div(4 * C, 256), 256, 0, stream>>>(partial, g.nsplit, 4, C, sums);
+  chan_reduce_kernel<<<ceil_div(4 * C, 32), 256, 0, stream>>>(partial, g.nsplit, 4 * C, sums);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

@@ -193,12 +193,24 @@ class SPADEGenerator(nn.Module):
         return torch.tanh(self.conv_img(F.leaky_relu(x, 0.2)))
 
 
+_GRID = {}
+
+
+def _base_grid(h, w, device):
+    """get_grid of models/utils.py:127-140 (CPU linspace, as there), cached per device:
+    a fresh host->device copy every call would drain the launch queue three times a step."""
+    key = (h, w, str(device))
+    if key not in _GRID:
+        hor = torch.linspace(-1.0, 1.0, w).view(1, 1, 1, w).expand(1, 1, h, w)
+        ver = torch.linspace(-1.0, 1.0, h).view(1, 1, h, 1).expand(1, 1, h, w)
+        _GRID[key] = torch.cat([hor, ver], 1).to(device)
+    return _GRID[key]
+
+
 def flow_warp(image, flow):
     """models/utils.py:113-140 (border padding, align_corners=False)."""
     b, _, h, w = image.shape
-    hor = torch.linspace(-1.0, 1.0, w).to(image.device).view(1, 1, 1, w).expand(b, 1, h, w)
-    ver = torch.linspace(-1.0, 1.0, h).to(image.device).view(1, 1, h, 1).expand(b, 1, h, w)
-    grid = torch.cat([hor, ver], 1)
+    grid = _base_grid(h, w, image.device)
     flow = torch.cat([flow[:, 0:1] / ((w - 1.0) / 2.0), flow[:, 1:2] / ((h - 1.0) / 2.0)], dim=1)
     return F.grid_sample(image, (grid + flow).permute(0, 2, 3, 1), mode='bilinear', padding_mode='border',
                          align_corners=False)

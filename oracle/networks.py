@@ -67,14 +67,14 @@ class Acts2LayoutModel(nn.Module):
         pad_pred = self.vocab['pred_name_to_idx']['__padding__']
         act = actions.unsqueeze(1).expand(B, T, actions.shape[1], actions.shape[2])
         sa, a, oa, f1, f2, x_end, y_end = [act[..., k] for k in range(7)]
-        t = torch.arange(T, dtype=torch.float32).view(1, T, 1)
+        t = torch.arange(T, dtype=torch.float32, device=actions.device).view(1, T, 1)
         rel_t = (t / T) * (f2.float() - f1.float() + 1e-6) + f1.float()        # model.py:118
         inside = (rel_t >= 0) & (rel_t <= 1)
         a = torch.where(inside, a, torch.full_like(a, float(pad_act)))          # model.py:119-121
         temporal_triplets = torch.stack([sa, a, oa], dim=-1).long()
         boxes_pred = [boxes_gt[:, 0]]
         emb = self.attribute_embedding(objs)
-        per_t = [torch.zeros(objs.shape[0], objs.shape[1], self.embedding_dim)]
+        per_t = [torch.zeros(objs.shape[0], objs.shape[1], self.embedding_dim, device=emb.device)]
         for ts in range(1, T):
             prev_boxes = boxes_pred[-1]
             obj_vecs = self.obj_vecs_net(torch.cat([emb, prev_boxes], dim=-1))
@@ -201,8 +201,8 @@ class SPADEGenerator(nn.Module):
 def flow_warp(image, flow):
     """models/utils.py:113-140: border padding, align_corners=False."""
     b, _, h, w = image.shape
-    hor = torch.linspace(-1.0, 1.0, w).view(1, 1, 1, w).expand(b, 1, h, w)
-    ver = torch.linspace(-1.0, 1.0, h).view(1, 1, h, 1).expand(b, 1, h, w)
+    hor = torch.linspace(-1.0, 1.0, w).to(image.device).view(1, 1, 1, w).expand(b, 1, h, w)
+    ver = torch.linspace(-1.0, 1.0, h).to(image.device).view(1, 1, h, 1).expand(b, 1, h, w)
     grid = torch.cat([hor, ver], 1)
     flow = torch.cat([flow[:, 0:1] / ((w - 1.0) / 2.0), flow[:, 1:2] / ((h - 1.0) / 2.0)], dim=1)
     return F.grid_sample(image, (grid + flow).permute(0, 2, 3, 1), mode='bilinear',
@@ -243,8 +243,8 @@ class Layout2VidGenerator(nn.Module):
         B, T = imgs_gt.shape[0], layout.shape[1]
         H = self.opt.image_size[0]
         imgs_prev = imgs_gt[:, :n_prev]
-        conf = torch.zeros(B, T, 1, H, H)
-        flows = torch.zeros(B, T, 2, H, H)
+        conf = torch.zeros(B, T, 1, H, H, device=imgs_gt.device)
+        flows = torch.zeros(B, T, 2, H, H, device=imgs_gt.device)
         for t in range(n_prev, T):
             seg_t = seg[:, t - n_prev:t + 1].reshape(B, -1, H, H)
             if test_mode or self.opt.bp_prev:

@@ -56,7 +56,7 @@ class GraphTripleConv(nn.Module):
         H, P = self.hidden_dim, self.predicate_output_dim
         s_idx = edges[..., 0].long()
         o_idx = edges[..., 1].long()
-        rows = torch.arange(B).view(B, 1).expand(B, E)
+        rows = torch.arange(B, device=obj_vecs.device).view(B, 1).expand(B, E)
         triples = torch.cat([obj_vecs[rows, s_idx], pred_vecs, obj_vecs[rows, o_idx]], dim=-1)
         hidden = self.net1(triples)
         new_s, new_p, new_o = hidden[..., :H], hidden[..., H:H + P], hidden[..., H + P:]
@@ -64,11 +64,11 @@ class GraphTripleConv(nn.Module):
         pooled = []
         for b in range(B):
             keep = pred_indicators[b].bool()
-            acc = torch.zeros(O, H, dtype=obj_vecs.dtype)
+            acc = torch.zeros(O, H, dtype=obj_vecs.dtype, device=obj_vecs.device)
             acc = acc.index_add(0, s_idx[b][keep], new_s[b][keep])
             acc = acc.index_add(0, o_idx[b][keep], new_o[b][keep])
-            cnt = torch.zeros(O, dtype=obj_vecs.dtype)
-            one = torch.ones(int(keep.sum()), dtype=obj_vecs.dtype)
+            cnt = torch.zeros(O, dtype=obj_vecs.dtype, device=obj_vecs.device)
+            one = torch.ones(int(keep.sum()), dtype=obj_vecs.dtype, device=obj_vecs.device)
             cnt = cnt.index_add(0, s_idx[b][keep], one).index_add(0, o_idx[b][keep], one)
             denom = torch.where(cnt > 0, cnt, torch.ones_like(cnt))
             pooled.append(acc / denom.view(O, 1))
@@ -110,7 +110,7 @@ def _sum_objects(sampled, pooling):
     """models/layout.py:205-237: scatter_add on dim 0 with an all-zero index, i.e.
     a sequential sum in object order; 'avg' divides by the object count."""
     O = sampled.shape[0]
-    out = torch.zeros((1,) + tuple(sampled.shape[1:]), dtype=sampled.dtype)
+    out = torch.zeros((1,) + tuple(sampled.shape[1:]), dtype=sampled.dtype, device=sampled.device)
     for o in range(O):
         out[0] = out[0] + sampled[o]
     if pooling == 'avg':
@@ -129,7 +129,7 @@ def boxes_to_layout(vecs, boxes, H, W=None, pooling='sum'):
     if O == 0:
         if pooling not in ('sum', 'avg'):
             raise ValueError('Invalid pooling "%s"' % pooling)
-        return torch.zeros(1, D, H, W, dtype=vecs.dtype)
+        return torch.zeros(1, D, H, W, dtype=vecs.dtype, device=vecs.device)
     grid = boxes_to_grid(boxes, H, W)
     src = vecs.view(O, D, 1, 1).expand(O, D, 8, 8)   # layout.py:52
     sampled = F.grid_sample(src, grid, align_corners=True)
@@ -154,8 +154,8 @@ def masks_to_layout(vecs, boxes, masks, H, W=None, pooling='sum', test_mode=Fals
         import numpy as np
         mass = [torch.sum(sampled[j]).item() for j in range(O)]
         order = list(np.argsort(mass))                       # layout.py:188-189
-        painted = torch.zeros(H, W, dtype=sampled.dtype)
-        canvas = torch.zeros(D, H, W, dtype=sampled.dtype)
+        painted = torch.zeros(H, W, dtype=sampled.dtype, device=sampled.device)
+        canvas = torch.zeros(D, H, W, dtype=sampled.dtype, device=sampled.device)
         for j in order:
             take = (painted == 0).float() * (clean[j, 0] > 0.5).float()
             painted = painted + take
