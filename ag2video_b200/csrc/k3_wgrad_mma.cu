@@ -168,10 +168,23 @@ static void wgrad_geometry(long long P, int Nout, int Cin, int* nsplit, int* cps
 
 }  // namespace ag2v
 
+namespace ag2v {
+bool wgrad3x3_tc_supported(int B, int Hh, int Ww, int Nout, int Cin);
+int wgrad3x3_tc_nsplit(int B, int Hh, int Ww, int Nout, int Cin);
+int wgrad3x3_tc(const float* dy, int Nout, const float* x, long long x_sb, long long x_sy, long long x_sx, int Cin,
+                int B, int Hh, int Ww, float* part, cudaStream_t stream);
+}
+
 using namespace ag2v;
 
-// Number of split-K partials (and so the workspace: nsplit * 9 * Nout * Cin floats).
-extern "C" int ag2v_wgrad3x3_nsplit(int B, int Hh, int Ww, int Nout, int Cin) {
+static bool use_tc(int impl, int B, int Hh, int Ww, int Nout, int Cin) {
+  return (impl == 0 || impl == 2) && wgrad3x3_tc_supported(B, Hh, Ww, Nout, Cin);
+}
+
+// Number of split-K partials (and so the workspace: nsplit * 9 * Nout * Cin floats) for
+// the kernel `impl` selects (0 auto, 1 mma.sync, 2 tcgen05, 3 mma.sync 3xTF32).
+extern "C" int ag2v_wgrad3x3_nsplit(int B, int Hh, int Ww, int Nout, int Cin, int impl) {
+  if (use_tc(impl, B, Hh, Ww, Nout, Cin)) return wgrad3x3_tc_nsplit(B, Hh, Ww, Nout, Cin);
   int nsplit, cps, ct, nt;
   wgrad_geometry((long long)B * Hh * Ww, Nout, Cin, &nsplit, &cps, &ct, &nt);
   return nsplit;
@@ -180,13 +193,17 @@ extern "C" int ag2v_wgrad3x3_nsplit(int B, int Hh, int Ww, int Nout, int Cin) {
 // dy [B*Hh*Ww, Nout] contiguous; x is a [B, Hh, Ww, Cin] view with element strides.
 // part receives nsplit partial [9][Nout][Cin] blocks (reduce with ag2v_unpack_dw3x3).
 extern "C" int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, long long x_sy,
-                             long long x_sx, int Cin, int B, int Hh, int Ww, float* part, int precise,
+                             long long x_sx, int Cin, int B, int Hh, int Ww, float* part, int impl,
                              cudaStream_t stream) {
   AG2V_REQUIRE(dy && x && part, "wgrad3x3: null pointer");
   AG2V_REQUIRE(B > 0 && Hh > 0 && Ww > 0 && Nout > 0 && Cin > 0, "wgrad3x3: bad sizes");
   AG2V_REQUIRE(Nout % 4 == 0 && Cin % 4 == 0, "wgrad3x3: Nout and Cin must be multiples of 4 (Nout=%d Cin=%d)", Nout, Cin);
   AG2V_REQUIRE(x_sx % 4 == 0 && x_sy % 4 == 0 && x_sb % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
                "wgrad3x3: operands must be 16-byte aligned");
+  if (impl == 2 && !wgrad3x3_tc_supported(B, Hh, Ww, Nout, Cin))
+    return fail(AG2V_ERR_UNSUPPORTED, "wgrad3x3: shape not supported by the tcgen05 kernel (Nout=%d Cin=%d %dx%d)", Nout, Cin, Hh, Ww);
+  if (use_tc(impl, B, Hh, Ww, Nout, Cin)) return wgrad3x3_tc(dy, Nout, x, x_sb, x_sy, x_sx, Cin, B, Hh, Ww, part, stream);
+  const int precise = impl == 3;
   WgradParams p;
   p.dy = dy; p.Nout = Nout; p.x = x; p.x_sb = x_sb; p.x_sy = x_sy; p.x_sx = x_sx; p.Cin = Cin;
   p.B = B; p.Hh = Hh; p.Ww = Ww; p.part = part;

@@ -225,6 +225,7 @@ class Layout2VidGenerator(nn.Module):
         self.flows_network = FlowsGenerator(opt)
         cin = opt.gconv_dim * 4 * opt.n_frames_G + 3
         self.conv_dim_in = nn.Sequential(_sn_conv_bn(cin, opt.semantic_nc), nn.LeakyReLU(0.2))
+        self.channels_last = True
 
     def build_layouts(self, objs, obj_vecs, boxes):
         """[B, F+1, D, H, H]: one launch for all (clip, frame) layouts (generator.py:36-54)."""
@@ -250,12 +251,13 @@ class Layout2VidGenerator(nn.Module):
             seg_t = seg[:, t - n_prev:t + 1].reshape(B, -1, H, H)
             prev = imgs_prev[:, -n_prev:] if (test_mode or self.opt.bp_prev) else imgs_gt[:, t - n_prev:t]
             prev = prev.reshape(B, -1, H, H)
-            weight, flow = self.flows_network(torch.cat([seg_t, prev], dim=1).contiguous(memory_format=CL))
+            fmt = CL if self.channels_last else torch.contiguous_format
+            weight, flow = self.flows_network(torch.cat([seg_t, prev], dim=1).contiguous(memory_format=fmt))
             warped = flow_warp(prev[:, -3:], flow)
             diff = prev[:, -3:] - warped
             conf[:, t - 1] = ((diff * diff).sum(dim=1, keepdim=True) < 0.02).float()
             flows[:, t - 1] = flow
-            x = self.conv_dim_in(torch.cat([seg_t, warped], dim=1).contiguous(memory_format=CL))
+            x = self.conv_dim_in(torch.cat([seg_t, warped], dim=1).contiguous(memory_format=fmt))
             img = self.netG(x) + warped
             imgs_prev = torch.cat([imgs_prev, img.unsqueeze(1)], dim=1)
         return imgs_prev, flows, conf
@@ -272,7 +274,14 @@ class AG2VideoModel(nn.Module):
         self.layout_to_video = Layout2VidGenerator(opt)
         if device is not None:
             self.to(device)
-        self.to(memory_format=CL)
+        # channels_last end to end: cuDNN then hands NHWC activations to the SPADE kernels
+        # without a layout copy.  opt.channels_last = False keeps torch's default layout
+        # (the SPADE ops convert internally); tests use it to share cuDNN algorithms with the
+        # eager reference.
+        self.channels_last = bool(getattr(opt, 'channels_last', True))
+        self.layout_to_video.channels_last = self.channels_last
+        if self.channels_last:
+            self.to(memory_format=CL)
 
     def forward(self, imgs, objs, triplets, actions, boxes_gt=None, test_mode=False, use_gt=False, graph_only=False):
         _, boxes_pred, actions_data = self.acts_to_boxes(objs, triplets, actions, boxes_gt, test_mode)

@@ -36,7 +36,7 @@ L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_i, c_p, c_p, c_p
 L.register('ag2v_unpack_dw3x3', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_p, c_p])
 L.register('ag2v_round_tf32', c_i, [c_p, c_p, c_ll, c_p])
-L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 5)
+L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 6)
 L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p])
 L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_ll, c_ll, c_ll,
                                  c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_i, c_p])
@@ -126,11 +126,11 @@ def _pack(wa, wb, ba, bb, dgrad):
 
 def _wgrad(dy, Nout, x, x_strides, Cin, B, Hh, Ww, two, like_a, like_b):
     lib = L.lib()
-    nsplit = lib.ag2v_wgrad3x3_nsplit(B, Hh, Ww, Nout, Cin)
+    nsplit = lib.ag2v_wgrad3x3_nsplit(B, Hh, Ww, Nout, Cin, CONV_IMPL)
     part = torch.empty(nsplit * 9 * Nout * Cin, device=dy.device, dtype=torch.float32)
     with _Timed('wgrad3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout):
         L.check(lib.ag2v_wgrad3x3(L.ptr(dy), Nout, L.ptr(x), x_strides[0], x_strides[1], x_strides[2], Cin, B, Hh, Ww,
-                                  L.ptr(part), int(_precise()), L.stream()))
+                                  L.ptr(part), CONV_IMPL, L.stream()))
     dwa = torch.empty_like(like_a, memory_format=torch.contiguous_format)
     dwb = torch.empty_like(like_b, memory_format=torch.contiguous_format) if two else None
     Co = Nout // 2 if two else Nout

@@ -135,10 +135,11 @@ int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, cons
 int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean, const float* rstd, const double* sums,
                       double count, int training, long long P, int C, ag2v_stream_t stream);
 
-/* weight gradient of a 3x3 conv: split-K partials, then reduction + scatter to OIHW */
-int ag2v_wgrad3x3_nsplit(int B, int Hh, int Ww, int Nout, int Cin);
+/* weight gradient of a 3x3 conv: split-K partials (tcgen05 MN-major kernel or mma.sync,
+ * `impl` as for ag2v_conv3x3), then reduction + scatter to OIHW */
+int ag2v_wgrad3x3_nsplit(int B, int Hh, int Ww, int Nout, int Cin, int impl);
 int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, long long x_sy, long long x_sx, int Cin,
-                  int B, int Hh, int Ww, float* part, int precise, ag2v_stream_t stream);
+                  int B, int Hh, int Ww, float* part, int impl, ag2v_stream_t stream);
 int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
                       ag2v_stream_t stream);
 int ag2v_double_to_float(const double* src, int n, float* dst, ag2v_stream_t stream);

@@ -102,3 +102,47 @@ def test_tc_and_mma_agree_closely():
     finally:
         sp.CONV_IMPL = old
     assert max_rel(outs[0], outs[1]) <= 1e-5
+
+
+@pytest.mark.parametrize('impl', [1, 2])
+@pytest.mark.parametrize('B,r,rw,Cin,Nout,stride,two', [
+    (2, 16, 16, 64, 128, 1, False),      # 2 x 16 pixel chunks
+    (2, 8, 8, 128, 256, 2, True),        # gamma|beta pair, strided input view, batch-spanning chunk
+    (1, 64, 64, 32, 32, 1, False),       # many chunks, split-K
+    (2, 32, 32, 512, 128, 4, False),     # the shared conv at real widths (label_nc 512), stride 4
+])
+def test_wgrad_kernels(B, r, rw, Cin, Nout, stride, two, impl):
+    """dW of a 3x3 conv from both weight-gradient kernels vs torch autograd (fp32)."""
+    import ag2video_b200.spade as sp
+    g = torch.Generator().manual_seed(3)
+    Hs, Ws = r * stride, rw * stride
+    full = sp._seg_operand(torch.randn(B, Cin, Hs, Ws, generator=g).cuda())
+    dy = sp._seg_operand(torch.randn(B, Nout, r, rw, generator=g).cuda())        # NHWC, TF32-rounded like the path
+    view = full[:, :, ::stride, ::stride].contiguous()
+    w = torch.zeros(Nout, Cin, 3, 3, device='cuda', requires_grad=True)
+    F.conv2d(view, w, padding=1).backward(dy)
+    dy_rows = dy.permute(0, 2, 3, 1).reshape(B * r * rw, Nout)
+    if two:      # columns of dy in the gamma|beta interleaved order, two OIHW outputs
+        C = Nout // 2
+        cols = torch.tensor([16 * (c // 8) + 8 * isb + c % 8 for isb in (0, 1) for c in range(C)], device='cuda')
+        dy_pk = torch.empty_like(dy_rows)
+        dy_pk[:, cols] = dy_rows
+        like_a = torch.empty(C, Cin, 3, 3, device='cuda')
+        old = sp.CONV_IMPL
+        sp.CONV_IMPL = impl
+        try:
+            da, db = sp._wgrad(dy_pk.contiguous(), Nout, full, (Hs * Ws * Cin, stride * Ws * Cin, stride * Cin), Cin, B, r, rw,
+                               True, like_a, like_a)
+        finally:
+            sp.CONV_IMPL = old
+        got = torch.cat([da, db], 0)
+    else:
+        like_a = torch.empty(Nout, Cin, 3, 3, device='cuda')
+        old = sp.CONV_IMPL
+        sp.CONV_IMPL = impl
+        try:
+            got, _ = sp._wgrad(dy_rows.contiguous(), Nout, full, (Hs * Ws * Cin, stride * Ws * Cin, stride * Cin), Cin, B, r, rw,
+                               False, like_a, None)
+        finally:
+            sp.CONV_IMPL = old
+    assert max_rel(got, w.grad) <= TOL

@@ -19,26 +19,65 @@ def _exact_library_convs():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def _model(seed, size):
+def _model(seed, size, channels_last=True):
     from ag2video_b200.networks import AG2VideoModel
-    m = AG2VideoModel(make_opt(size, batch_size=2))
+    m = AG2VideoModel(make_opt(size, batch_size=2, channels_last=channels_last))
     m.load_state_dict(det_state(m.state_dict(), seed), strict=True)
-    return m.cuda().to(memory_format=torch.channels_last).train()
+    m = m.cuda().train()
+    return m.to(memory_format=torch.channels_last) if channels_last else m
+
+
+def test_generator64_logic_vs_eager_gpu_reference():
+    """The whole pipeline's LOGIC, end to end, at 2e-4: our generator with the SPADE
+    GEMMs in the 3xTF32 validation mode (fp32-class products) against the oracle modules
+    run eagerly on the same GPU, both in torch's default memory layout so every cuDNN
+    convolution outside the scope is the very same kernel in both.  (Against the CPU
+    golden even the plain eager GPU path is 3e-3 off: cuDNN's fp32 algorithms.)"""
+    import ag2video_b200.spade as sp
+    from oracle import networks as onet
+    c = golden('generator64.pt')
+    old = sp.CONV_IMPL
+    sp.CONV_IMPL = 3
+    try:
+        ref = onet.AG2VideoModel(make_opt(64, batch_size=2))
+        ref.load_state_dict(det_state(ref.state_dict(), c['seed']), strict=True)
+        ref = ref.cuda().train()
+        m = _model(c['seed'], 64, channels_last=False)
+        b = synthetic_batch(B=2, F=4, image_size=64, seed=c['batch_seed'], device='cuda')
+        args = (b['imgs'], b['objs'], b['triplets'], b['actions'])
+        want = ref(*args, boxes_gt=b['boxes'], use_gt=True)
+        got = m(*args, boxes_gt=b['boxes'], use_gt=True)
+        e_img, e_box = max_rel(got[0], want[0]), max_rel(got[1], want[1])
+        print('logic check: imgs %.2e boxes %.2e' % (e_img, e_box))
+        assert e_img <= 2e-4 and e_box <= 2e-5
+        lw = (want[0] - b['imgs']).abs().mean() + (want[1] - b['boxes'])[:, 1:].abs().mean()
+        lg = (got[0] - b['imgs']).abs().mean() + (got[1] - b['boxes'])[:, 1:].abs().mean()
+        lw.backward()
+        lg.backward()
+        gw = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+        gg = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+        from _util import rel_l2
+        worst = max((rel_l2(gg[k], gw[k]), k) for k in gw if float(gw[k].abs().max()) > 1e-7)
+        print('logic check: worst gradient rel-L2 %.2e (%s)' % worst)
+        assert worst[0] <= 1e-2          # a few LeakyReLU gates within fp32 rounding of zero may still flip
+    finally:
+        sp.CONV_IMPL = old
 
 
 @pytest.mark.parametrize('mode', ['validation_3xtf32', 'product_tf32'])
 def test_generator64_matches_reference_golden(mode):
-    """Two passes over the same golden: (1) the SPADE GEMMs in the 3xTF32 validation
-    mode (fp32-class products) - this holds the whole pipeline's LOGIC to 1e-4 end to end;
-    (2) the product path (TF32 operands, tcgen05): every operator is within 1e-3 on its own
-    (tests/test_gpu_spade.py), end to end the rounding of 18 stacked SPADE layers with
-    variance-preserving random weights reaches ~1e-2 on single pixels, while the loss
-    stays within 1e-3 (the bar SURVEY.md 8d sets for the end-to-end step)."""
+    """Against the golden produced by the reference on the CPU.  The plain eager GPU path
+    (oracle modules on the GPU, fp32) is already 3.5e-3 away from this golden on single
+    pixels - cuDNN's fp32 algorithms through 40 layers - so: (1) validation mode must sit
+    at that floor; (2) the product path (TF32 operands, tcgen05; every operator within
+    1e-3 on its own, tests/test_gpu_spade.py) accumulates the rounding of 18 stacked SPADE
+    layers with variance-preserving random weights to ~1e-2 on single pixels, while the
+    loss stays within 1e-3, the bar SURVEY.md 8d sets for the end-to-end step."""
     import ag2video_b200.spade as sp
     old = sp.CONV_IMPL
     sp.CONV_IMPL = 3 if mode == 'validation_3xtf32' else 0
     try:
-        _generator64(1e-4 if mode == 'validation_3xtf32' else 3e-2)
+        _generator64(6e-3 if mode == 'validation_3xtf32' else 3e-2)
     finally:
         sp.CONV_IMPL = old
 
