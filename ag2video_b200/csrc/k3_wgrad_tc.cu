@@ -6,7 +6,8 @@
 // operands have the reduction index as their ROW in memory ([pixel][channel], NHWC),
 // i.e. they are "MN-major" for the tensor core; tcgen05 takes MN-major TF32 operands
 // directly, so no transpose is needed: a TMA box {32 channels, 32 pixels} lands as
-// 32 rows x 128 B = four 8-row swizzle atoms, exactly the canonical MN-major layout.
+// 32 rows x 128 B in the "128B swizzle, 32B atom" pattern, the one MN-major layout the
+// tensor core accepts for 32-bit operands (eight 4-row atoms per box).
 //
 // One CTA owns a 128 (n) x 128 (c) tile for the THREE taps of one kernel row
 // (dy fixed, dx = -1, 0, +1): the dY chunk is loaded once and multiplied with three
@@ -97,9 +98,9 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_cons
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
 #pragma unroll
-          for (int kk = 0; kk < WT_PIX / 8; ++kk) {        // one 8-pixel atom (1024 B) per instruction
-            const uint64_t da = make_sw128_mnmajor_desc(a_s + kk * 1024, WT_BOX);
-            const uint64_t db = make_sw128_mnmajor_desc(b_s + t * 4 * WT_BOX + kk * 1024, WT_BOX);
+          for (int kk = 0; kk < WT_PIX / 8; ++kk) {        // 8 pixels = two 4-row atoms (1024 B) per instruction
+            const uint64_t da = make_sw128b32_mnmajor_desc(a_s + kk * 1024, WT_BOX, 512);
+            const uint64_t db = make_sw128b32_mnmajor_desc(b_s + t * 4 * WT_BOX + kk * 1024, WT_BOX, 512);
             umma_tf32(tmem_acc + (uint32_t)(t * WT_T), da, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
           }
         }
@@ -184,7 +185,7 @@ int wgrad3x3_tc(const float* dy, int Nout, const float* x, long long x_sb, long 
     cuuint64_t dims[4] = {(cuuint64_t)Nout, (cuuint64_t)Ww, (cuuint64_t)Hh, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)Nout * 4, (cuuint64_t)Nout * Ww * 4, (cuuint64_t)Nout * Ww * Hh * 4};
     CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)dy, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(AG2V_ERR_CUDA, "cuTensorMapEncodeTiled(dY) failed with %d", (int)r);
   }
@@ -192,7 +193,7 @@ int wgrad3x3_tc(const float* dy, int Nout, const float* x, long long x_sb, long 
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Ww, (cuuint64_t)Hh, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)x_sx * 4, (cuuint64_t)x_sy * 4, (cuuint64_t)x_sb * 4};
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(AG2V_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed with %d", (int)r);
   }

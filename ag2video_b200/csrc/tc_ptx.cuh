@@ -94,15 +94,18 @@ __device__ __forceinline__ float tc_round_tf32(float x) {
 }
 
 
-// MN-major operand (the reduction index is the ROW of the shared tile): 8 rows x 128 B
-// atoms; atoms along M/N are `lbo_bytes` apart, atoms along K are 1024 B apart.
-__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major TF32 operand (the reduction index is the ROW of the shared tile).  For 32-bit
+// elements the only MN-major layout the tensor core accepts is "128B swizzle with 32B
+// atomicity" (descriptor layout type 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of
+// 128 B whose four 32-byte chunks are XOR-ed with (row & 3); the pattern repeats every 4
+// rows (512 B).  Atoms along M/N are `lbo_bytes` apart, 4-row groups along K `sbo_bytes`.
+__device__ __forceinline__ uint64_t make_sw128b32_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B
   return d;
 }
 
