@@ -74,6 +74,17 @@ def test_conv_bias_relu(shape, impl):
     assert _run(impl, *shape, epi='bias_relu') <= TOL
 
 
+@pytest.mark.parametrize('tile', ['1x128', '2x128', '1x256', '2x256'])
+@pytest.mark.parametrize('epi', ['bias_relu', 'gate', 'accum'])
+def test_tc_tile_shapes(epi, tile, monkeypatch):
+    """Every CTA tile shape of the tcgen05 kernel (1 or 2 M tiles x 128 or 256 columns),
+    including an odd number of M tiles and Nout that does not fill the last column tile."""
+    monkeypatch.setenv('AG2V_TC_TILE', tile)
+    assert _run(2, 3, 8, 8, 64, 288, 1, epi=epi) <= TOL          # 2 M tiles (3 images, 2 per tile), Nout = 256 + 32
+    assert _run(2, 1, 48, 128, 32, 128, 1, epi=epi) <= TOL        # 48 row tiles
+    assert _run(2, 2, 16, 16, 128, 512, 2, epi=epi) <= TOL        # strided view, 4 M tiles
+
+
 @pytest.mark.parametrize('impl', [1, 2])
 @pytest.mark.parametrize('epi', ['bias', 'gate', 'accum'])
 def test_conv_epilogues(epi, impl):

@@ -138,6 +138,29 @@ def test_spade_vs_oracle_real_widths(C, L, r, Hs, B, slope, impl):
         assert max_rel(m.state_dict()[k], ref.state_dict()[k]) <= 1e-5, k
 
 
+@pytest.mark.parametrize('tile', ['2x256', '2x128', '1x256'])
+def test_spade_epilogue_on_every_tc_tile_shape(tile, monkeypatch):
+    """The SPADE epilogue (gamma|beta interleave) under each tcgen05 tile shape vs the mma.sync kernel."""
+    import ag2video_b200.spade as sp
+    outs = []
+    for impl, env in ((1, None), (2, tile)):
+        if env:
+            monkeypatch.setenv('AG2V_TC_TILE', env)
+        sp.CONV_IMPL = impl
+        m = load_det(sp.SPADE('spadesyncbatch3x3', 256, 64), 9)
+        m.load_state_dict(dyadic_spade_state(m.state_dict(), 9), strict=True)
+        m.cuda().train()
+        m.fused_slope = 0.2
+        g = torch.Generator().manual_seed(2)
+        x = torch.randn(3, 256, 16, 16, generator=g).cuda().requires_grad_()
+        seg = dyadic_seg('seg', (3, 64, 32, 32), 4, 0.05).cuda().requires_grad_()
+        out = m(x, seg)
+        (out * torch.randn(out.shape, generator=g).cuda()).sum().backward()
+        outs.append([out, x.grad, seg.grad] + [p.grad for p in m.parameters()])
+    for a, b in zip(*outs):
+        assert max_rel(a, b) <= 2e-5
+
+
 def test_tc_and_mma_kernels_agree_on_a_full_spade():
     """Operands are rounded to TF32 where they are produced, so the tcgen05 and the
     mma.sync kernels see identical products: they may differ in accumulation order only."""
