@@ -14,6 +14,7 @@
 // results are fp32-accurate (~1e-6), which the box recurrence needs.
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -59,37 +60,86 @@ __device__ __forceinline__ void mma_3x(float (&c)[4], const float (&a)[4], const
 
 // ---------------------------------------------------------------------------
 // CTA-level skinny product:  C[m, n] = sum_r A(m, r) * B(r, n),  m < M, all n.
-// CTAs take 8-column tiles; the 8 warps split the reduction in steps of 8 and
+// CTAs take 8-column tiles of n.  The activation block A[:, k-chunk] is staged in
+// shared memory with bulk async copies (cp.async.bulk + mbarrier: one instruction per
+// row segment, no register staging), the CTA's weight slab is prefetched into
+// registers while those copies fly, then the 8 warps split the reduction in steps of 8;
 // their partials are summed in warp order through shared memory (deterministic).
-// A2(m, r) -> (A(m,r), A(m,r+1));  B2(r, n) -> (B(r,n), B(r+1,n));  r even.
+//   A::issue(m, k0, kn, dst, bar)  bulk-copies row m, columns [k0, k0+kn) to smem (kBulk)
+//   A(m, r) -> (A(m,r), A(m,r+1))  element access for the non-bulk (masked) operands
+//   B2(r, n) -> (B(r,n), B(r+1,n)),  r even.
 // ---------------------------------------------------------------------------
+constexpr int kMaxKs = 16;            // k-steps of 8 per warp per chunk  => chunk <= 1024 columns
+constexpr int kXsFloats = 40 * 1024;  // 160 KB activation staging buffer
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct StageCtx { float* red; float* xs; uint32_t bar; uint32_t phase; };
+
 template <class A2, class B2, class Epi>
-__device__ void cta_skinny_gemm(int M, int N, int Kred, A2 a2, B2 b2, Epi epi, float* red /*[8][128][8]*/) {
+__device__ void cta_skinny_gemm(int M, int N, int Kred, A2 a2, B2 b2, Epi epi, StageCtx& cx) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int ntiles = N >> 3, ksteps = Kred >> 3;
+  const int ntiles = N >> 3;
+  float* red = cx.red;
+  float* xs = cx.xs;
+  const uint32_t xs_u32 = smem_u32(xs);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n0 = tile << 3;
     for (int mbase = 0; mbase < M; mbase += kMChunk) {
       const int mrows = min(kMChunk, M - mbase);
       const int mt_n = (mrows + 15) >> 4;
+      int kc_max = (kXsFloats / (mt_n * 16) - 8) & ~7;
+      if (kc_max > kMaxKs * kWarps * 8) kc_max = kMaxKs * kWarps * 8;
       float acc[kMT][4];
 #pragma unroll
       for (int i = 0; i < kMT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-      for (int ks = warp; ks < ksteps; ks += kWarps) {
-        const int r = (ks << 3) + 2 * t;
-        const float2 wb = b2(r, n0 + g);
-        const float b[2] = {wb.x, wb.y};
-#pragma unroll
-        for (int mt = 0; mt < kMT; ++mt) {
-          if (mt < mt_n) {
-            const int m_lo = mbase + mt * 16 + g, m_hi = m_lo + 8;
-            float2 p = (m_lo < M) ? a2(m_lo, r) : make_float2(0.f, 0.f);
-            float2 q = (m_hi < M) ? a2(m_hi, r) : make_float2(0.f, 0.f);
-            const float a[4] = {p.x, q.x, p.y, q.y};
-            mma_3x(acc[mt], a, b);
+      for (int k0 = 0; k0 < Kred; k0 += kc_max) {
+        const int kn = min(kc_max, Kred - k0);
+        const int ld = kn + 8;                          // +8 floats: conflict-free 64-bit fragment reads
+        // ---- stage A[mbase : mbase+mrows, k0 : k0+kn] ----
+        if (A2::kBulk) {
+          if (threadIdx.x == 0) mbar_expect_tx(cx.bar, (uint32_t)(mrows * kn * 4));
+          __syncthreads();
+          if ((int)threadIdx.x < mrows) a2.issue(mbase + threadIdx.x, k0, kn, xs_u32 + (uint32_t)(threadIdx.x * ld) * 4, cx.bar);
+        } else {
+          const int half = kn >> 1;
+          for (int i = threadIdx.x; i < mrows * half; i += kThreads) {
+            const int m = i / half, c2 = (i - m * half) * 2;
+            *reinterpret_cast<float2*>(xs + m * ld + c2) = a2(mbase + m, k0 + c2);
           }
         }
+        // ---- this warp's slice of the weight slab, straight to registers ----
+        const int ksteps = kn >> 3;
+        float2 w[kMaxKs];
+#pragma unroll
+        for (int j = 0; j < kMaxKs; ++j) {
+          const int ks = warp + j * kWarps;
+          w[j] = (ks < ksteps) ? b2(k0 + (ks << 3) + 2 * t, n0 + g) : make_float2(0.f, 0.f);
+        }
+        if (A2::kBulk) { mbar_wait(cx.bar, cx.phase); cx.phase ^= 1u; } else { __syncthreads(); }
+#pragma unroll
+        for (int j = 0; j < kMaxKs; ++j) {
+          const int ks = warp + j * kWarps;
+          if (ks < ksteps) {
+            const float b[2] = {w[j].x, w[j].y};
+            const float* col = xs + (ks << 3) + 2 * t;
+#pragma unroll
+            for (int mt = 0; mt < kMT; ++mt) {
+              if (mt < mt_n) {
+                const int r_lo = mt * 16 + g, r_hi = r_lo + 8;
+                const float2 p = (r_lo < mrows) ? *reinterpret_cast<const float2*>(col + r_lo * ld) : make_float2(0.f, 0.f);
+                const float2 q = (r_hi < mrows) ? *reinterpret_cast<const float2*>(col + r_hi * ld) : make_float2(0.f, 0.f);
+                const float a[4] = {p.x, q.x, p.y, q.y};
+                mma_3x(acc[mt], a, b);
+              }
+            }
+          }
+        }
+        __syncthreads();                                 // everyone is done with xs before the next chunk lands
       }
 #pragma unroll
       for (int mt = 0; mt < kMT; ++mt) {
@@ -103,7 +153,7 @@ __device__ void cta_skinny_gemm(int M, int N, int Kred, A2 a2, B2 b2, Epi epi, f
       for (int i = threadIdx.x; i < mrows * 8; i += kThreads) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += red[(size_t)w * kMChunk * 8 + i];
+        for (int w8 = 0; w8 < kWarps; ++w8) s += red[(size_t)w8 * kMChunk * 8 + i];
         epi(mbase + (i >> 3), n0 + (i & 7), s);
       }
       __syncthreads();
@@ -240,7 +290,19 @@ __device__ __forceinline__ int clamp_idx(long long v, int O) {
 
 // [obj[b, s_e] | pred[b, e] | obj[b, o_e]] row m = (b, e), columns r, r+1 (graph.py:67-70)
 struct GatherT {
+  static constexpr bool kBulk = true;
   const float *obj, *pred; const int *s_idx, *o_idx; int Din, Dp;
+  // columns [k0, k0+kn) of the virtual row [obj[s] | pred | obj[o]]: up to three contiguous pieces
+  __device__ __forceinline__ void issue(int m, int k0, int kn, uint32_t dst, uint32_t bar) const {
+    const int k1 = k0 + kn;
+    const int segb[4] = {0, Din, Din + Dp, 2 * Din + Dp};
+    const float* srcs[3] = {obj + (size_t)s_idx[m] * Din, pred + (size_t)m * Dp, obj + (size_t)o_idx[m] * Din};
+#pragma unroll
+    for (int sgm = 0; sgm < 3; ++sgm) {
+      const int lo = max(k0, segb[sgm]), hi = min(k1, segb[sgm + 1]);
+      if (hi > lo) bulk_g2s(dst + (uint32_t)(lo - k0) * 4, srcs[sgm] + (lo - segb[sgm]), (uint32_t)(hi - lo) * 4, bar);
+    }
+  }
   __device__ __forceinline__ float2 operator()(int m, int r) const {
     const float* src;
     if (r < Din) src = obj + (size_t)s_idx[m] * Din + r;
@@ -250,13 +312,19 @@ struct GatherT {
   }
 };
 struct RowMajor2 {      // X[m, r..r+1], contiguous
+  static constexpr bool kBulk = true;
   const float* x; int ld;
+  __device__ __forceinline__ void issue(int m, int k0, int kn, uint32_t dst, uint32_t bar) const {
+    bulk_g2s(dst, x + (size_t)m * ld + k0, (uint32_t)kn * 4, bar);
+  }
   __device__ __forceinline__ float2 operator()(int m, int r) const {
     return *reinterpret_cast<const float2*>(x + (size_t)m * ld + r);
   }
 };
 struct RowMajorMasked2 {  // X[m, r] where gate[m, r] > 0, else 0
+  static constexpr bool kBulk = false;
   const float *x, *gate; int ld;
+  __device__ __forceinline__ void issue(int, int, int, uint32_t, uint32_t) const {}
   __device__ __forceinline__ float2 operator()(int m, int r) const {
     float2 v = *reinterpret_cast<const float2*>(x + (size_t)m * ld + r);
     float2 q = *reinterpret_cast<const float2*>(gate + (size_t)m * ld + r);
@@ -313,15 +381,19 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_fwd_kernel(GcnFwd p) {
   const GcnDims d = p.d;
   const int M = d.M(), R = d.R(), K1 = d.K1(), N2 = d.N2(), H = d.H;
   float* red = reinterpret_cast<float*>(gcn_smem);
-  int* s_idx = reinterpret_cast<int*>(red + kWarps * kMChunk * 8);
+  float* xs = red + kWarps * kMChunk * 8;
+  uint64_t* barp = reinterpret_cast<uint64_t*>(xs + kXsFloats);
+  int* s_idx = reinterpret_cast<int*>(barp + 2);
   int* o_idx = s_idx + M + 1;
+  StageCtx cx{red, xs, smem_u32(barp), 0u};
+  if (threadIdx.x == 0) { mbar_init(cx.bar, 1); fence_barrier_init(); }
   load_indices(d, p.edges, s_idx, o_idx);
 
   {  // stage 1: h1 = relu(T W1a^T + b1a)                       graph.py:71 (net1[0:2])
     GatherT a{p.obj, p.pred, s_idx, o_idx, d.Din, d.Dp};
     WeightNT2 b{p.W1a, K1};
     const float* bias = p.b1a; float* out = p.h1;
-    cta_skinny_gemm(M, H, K1, a, b, [=](int m, int n, float v) { out[(size_t)m * H + n] = fmaxf(v + bias[n], 0.f); }, red);
+    cta_skinny_gemm(M, H, K1, a, b, [=](int m, int n, float v) { out[(size_t)m * H + n] = fmaxf(v + bias[n], 0.f); }, cx);
   }
   grid.sync();
   {  // stage 2: h2 = relu(h1 W1b^T + b1b); the middle slice is new_p   graph.py:71-75
@@ -332,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_fwd_kernel(GcnFwd p) {
       v = fmaxf(v + bias[n], 0.f);
       out[(size_t)m * N2 + n] = v;
       if (n >= H && n < H + Dpo) np[(size_t)m * Dpo + (n - H)] = v;
-    }, red);
+    }, cx);
   }
   grid.sync();
   {  // stage 3: masked average pooling, subjects then objects, edge order   graph.py:79-100
@@ -356,14 +428,14 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_fwd_kernel(GcnFwd p) {
     RowMajor2 a{p.pooled, H};
     WeightNT2 b{p.W2a, H};
     const float* bias = p.b2a; float* out = p.g1;
-    cta_skinny_gemm(R, H, H, a, b, [=](int m, int n, float v) { out[(size_t)m * H + n] = fmaxf(v + bias[n], 0.f); }, red);
+    cta_skinny_gemm(R, H, H, a, b, [=](int m, int n, float v) { out[(size_t)m * H + n] = fmaxf(v + bias[n], 0.f); }, cx);
   }
   grid.sync();
   {  // stage 5: new_obj = relu(g1 W2b^T + b2b)
     RowMajor2 a{p.g1, H};
     WeightNT2 b{p.W2b, H};
     const float* bias = p.b2b; float* out = p.new_obj; const int Dout = d.Dout;
-    cta_skinny_gemm(R, Dout, H, a, b, [=](int m, int n, float v) { out[(size_t)m * Dout + n] = fmaxf(v + bias[n], 0.f); }, red);
+    cta_skinny_gemm(R, Dout, H, a, b, [=](int m, int n, float v) { out[(size_t)m * Dout + n] = fmaxf(v + bias[n], 0.f); }, cx);
   }
 }
 
@@ -372,8 +444,12 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_bwd_kernel(GcnBwd p) {
   const GcnDims d = p.d;
   const int M = d.M(), R = d.R(), K1 = d.K1(), N2 = d.N2(), H = d.H, Dout = d.Dout, Dpo = d.Dpo;
   float* red = reinterpret_cast<float*>(gcn_smem);
-  int* s_idx = reinterpret_cast<int*>(red + kWarps * kMChunk * 8);
+  float* xs = red + kWarps * kMChunk * 8;
+  uint64_t* barp = reinterpret_cast<uint64_t*>(xs + kXsFloats);
+  int* s_idx = reinterpret_cast<int*>(barp + 2);
   int* o_idx = s_idx + M + 1;
+  StageCtx cx{red, xs, smem_u32(barp), 0u};
+  if (threadIdx.x == 0) { mbar_init(cx.bar, 1); fence_barrier_init(); }
   load_indices(d, p.edges, s_idx, o_idx);
   const int total_warps = gridDim.x * kWarps;
   const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -383,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_bwd_kernel(GcnBwd p) {
     WeightNN2 b{p.W2b, H};
     const float* gate = p.g1; float* out = p.dz4;
     cta_skinny_gemm(R, H, Dout, a, b, [=](int m, int n, float v) {
-      size_t i = (size_t)m * H + n; out[i] = gate[i] > 0.f ? v : 0.f; }, red);
+      size_t i = (size_t)m * H + n; out[i] = gate[i] > 0.f ? v : 0.f; }, cx);
     ElemMasked z{p.d_new_obj, p.new_obj, Dout};
     Elem x{p.g1, H};
     warp_wgrad(R, Dout, H, z, x, p.dW2b, p.db2b, H >> 3, total_warps, gwarp);
@@ -393,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_bwd_kernel(GcnBwd p) {
     RowMajor2 a{p.dz4, H};
     WeightNN2 b{p.W2a, H};
     float* out = p.dpooled;
-    cta_skinny_gemm(R, H, H, a, b, [=](int m, int n, float v) { out[(size_t)m * H + n] = v; }, red);
+    cta_skinny_gemm(R, H, H, a, b, [=](int m, int n, float v) { out[(size_t)m * H + n] = v; }, cx);
     Elem z{p.dz4, H};
     Elem x{p.pooled, H};
     warp_wgrad(R, H, H, z, x, p.dW2a, p.db2a, H >> 3, total_warps, gwarp);
@@ -420,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_bwd_kernel(GcnBwd p) {
     WeightNN2 b{p.W1b, H};
     const float* gate = p.h1; float* out = p.dz1;
     cta_skinny_gemm(M, H, N2, a, b, [=](int m, int n, float v) {
-      size_t i = (size_t)m * H + n; out[i] = gate[i] > 0.f ? v : 0.f; }, red);
+      size_t i = (size_t)m * H + n; out[i] = gate[i] > 0.f ? v : 0.f; }, cx);
     Elem z{p.dz2, N2};
     Elem x{p.h1, H};
     warp_wgrad(M, N2, H, z, x, p.dW1b, p.db1b, H >> 3, total_warps, gwarp);
@@ -430,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_bwd_kernel(GcnBwd p) {
     RowMajor2 a{p.dz1, H};
     WeightNN2 b{p.W1a, K1};
     float* out = p.dT;
-    cta_skinny_gemm(M, K1, H, a, b, [=](int m, int n, float v) { out[(size_t)m * K1 + n] = v; }, red);
+    cta_skinny_gemm(M, K1, H, a, b, [=](int m, int n, float v) { out[(size_t)m * K1 + n] = v; }, cx);
     Elem z{p.dz1, H};
     ElemGatherT x{p.obj, p.pred, s_idx, o_idx, d.Din, d.Dp};
     warp_wgrad(M, H, K1, z, x, p.dW1a, p.db1a, K1 >> 3, total_warps, gwarp);
@@ -459,13 +535,14 @@ static int gcn_check(const GcnDims& d) {
   AG2V_REQUIRE(d.B > 0 && d.O > 0 && d.E > 0, "gcn_layer: empty graph B=%d O=%d E=%d", d.B, d.O, d.E);
   AG2V_REQUIRE(d.Din % 8 == 0 && d.Dp % 8 == 0 && d.H % 8 == 0 && d.Dout % 8 == 0 && d.Dpo % 8 == 0,
                "gcn_layer: feature sizes must be multiples of 8 (Din=%d Dp=%d H=%d Dout=%d Dpo=%d)", d.Din, d.Dp, d.H, d.Dout, d.Dpo);
-  AG2V_REQUIRE(d.M() <= 8192 && d.E <= 512, "gcn_layer: at most 8192 edge rows per call and 512 edges per clip (got %d, %d)", d.M(), d.E);
+  AG2V_REQUIRE(d.M() <= 4096 && d.E <= 512, "gcn_layer: at most 4096 edge rows per call and 512 edges per clip (got %d, %d)", d.M(), d.E);
   AG2V_REQUIRE(d.Din % 4 == 0 && d.H % 4 == 0, "gcn_layer: Din and H must be multiples of 4");
   return AG2V_OK;
 }
 
 static size_t gcn_smem_bytes(const GcnDims& d) {
-  return (size_t)kWarps * kMChunk * 8 * sizeof(float) + 2 * (size_t)(d.M() + 1) * sizeof(int);
+  return (size_t)kWarps * kMChunk * 8 * sizeof(float) + (size_t)kXsFloats * sizeof(float) + 16 +
+         2 * (size_t)(d.M() + 1) * sizeof(int);
 }
 
 }  // namespace ag2v

@@ -1,0 +1,45 @@
+"""A short run that launches each hot kernel a few times at BASELINE shapes, for ncu:
+  ncu --set full --clock-control none --import-source on -k regex:<pattern> -c N -o gpurun_out/prof python tools/ncu_targets.py <what>
+what: spade | layout | gcn"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+what = sys.argv[1] if len(sys.argv) > 1 else 'spade'
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+
+if what == 'spade':
+    import ag2video_b200.spade as sp
+    C, L, r, B = (int(a) for a in (sys.argv[3:7] if len(sys.argv) > 6 else (128, 512, 256, 2)))
+    m = sp.SPADE('spadesyncbatch3x3', C, L).cuda().train()
+    m.fused_slope = 0.2
+    x = torch.randn(B, C, r, r, device='cuda').contiguous(memory_format=torch.channels_last).requires_grad_()
+    seg = torch.randn(B, L, 256, 256, device='cuda').contiguous(memory_format=torch.channels_last).requires_grad_()
+    for _ in range(reps):
+        out = m(x, seg)
+        out.backward(torch.ones_like(out))
+elif what == 'layout':
+    from ag2video_b200.config import synthetic_batch
+    from ag2video_b200.layout import boxes_to_layout_batched
+    N = 8
+    b = synthetic_batch(B=N, F=1, image_size=8, seed=1, n_objects=10, with_images=False)
+    boxes = b['boxes'].reshape(N, -1, 4).cuda()
+    valid = torch.ones(N, boxes.shape[1], dtype=torch.bool, device='cuda')
+    valid[:, -1] = False
+    vecs = torch.randn(N, boxes.shape[1], 512, device='cuda', requires_grad=True)
+    for _ in range(reps):
+        out = boxes_to_layout_batched(vecs, boxes, valid, 256)
+        out.backward(torch.ones_like(out))
+elif what == 'gcn':
+    from ag2video_b200.config import microbench_graph
+    from ag2video_b200.graph import GraphTripleConv
+    m = GraphTripleConv(512, 128, 128, 128, 512).cuda()
+    edges, ind = microbench_graph(B=2, O=10)
+    obj = torch.randn(2, 11, 512, device='cuda', requires_grad=True)
+    pred = torch.randn(2, 40, 128, device='cuda', requires_grad=True)
+    for _ in range(reps):
+        o, p = m(obj, pred, edges.cuda(), ind.cuda())
+        (o.sum() + p.sum()).backward()
+torch.cuda.synchronize()
