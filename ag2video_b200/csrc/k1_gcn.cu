@@ -69,15 +69,39 @@ __device__ __forceinline__ void mma_3x(float (&c)[4], const float (&a)[4], const
 //   A(m, r) -> (A(m,r), A(m,r+1))  element access for the non-bulk (masked) operands
 //   B2(r, n) -> (B(r,n), B(r+1,n)),  r even.
 // ---------------------------------------------------------------------------
-constexpr int kMaxKs = 16;            // k-steps of 8 per warp per chunk  => chunk <= 1024 columns
-constexpr int kXsFloats = 40 * 1024;  // 160 KB activation staging buffer
+constexpr int kKc = 1024;             // reduction columns staged per pass
+constexpr int kXsFloats = 36 * 1024;  // 144 KB activation staging buffer
+constexpr int kWsFloats = 8 * (kKc + 8);   // the CTA's 8-column weight slab for one pass (33 KB)
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-struct StageCtx { float* red; float* xs; uint32_t bar; uint32_t phase; };
+struct StageCtx { float* red; float* xs; float* ws; uint32_t bar; uint32_t phase; };
+
+// compact inner loop (kept small on purpose: a fully unrolled version is ~0.5 MB of SASS and
+// the kernel becomes instruction-fetch bound): MT m16 tiles of accumulators in registers.
+template <int MT>
+__device__ __forceinline__ void skinny_core(const float* xs, const float* ws, int ld, int mrows, int ksteps,
+                                            float (&acc)[kMT][4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+  for (int ks = warp; ks < ksteps; ks += kWarps) {
+    const float2 wv = *reinterpret_cast<const float2*>(ws + g * ld + (ks << 3) + 2 * t);
+    const float b[2] = {wv.x, wv.y};
+    const float* col = xs + (ks << 3) + 2 * t;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r_lo = mt * 16 + g, r_hi = r_lo + 8;
+      const float2 p = (r_lo < mrows) ? *reinterpret_cast<const float2*>(col + r_lo * ld) : make_float2(0.f, 0.f);
+      const float2 q = (r_hi < mrows) ? *reinterpret_cast<const float2*>(col + r_hi * ld) : make_float2(0.f, 0.f);
+      const float a[4] = {p.x, q.x, p.y, q.y};
+      mma_3x(acc[mt], a, b);
+    }
+  }
+}
 
 template <class A2, class B2, class Epi>
 __device__ void cta_skinny_gemm(int M, int N, int Kred, A2 a2, B2 b2, Epi epi, StageCtx& cx) {
@@ -86,24 +110,28 @@ __device__ void cta_skinny_gemm(int M, int N, int Kred, A2 a2, B2 b2, Epi epi, S
   const int ntiles = N >> 3;
   float* red = cx.red;
   float* xs = cx.xs;
-  const uint32_t xs_u32 = smem_u32(xs);
+  float* ws = cx.ws;
+  const uint32_t xs_u32 = smem_u32(xs), ws_u32 = smem_u32(ws);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n0 = tile << 3;
     for (int mbase = 0; mbase < M; mbase += kMChunk) {
       const int mrows = min(kMChunk, M - mbase);
       const int mt_n = (mrows + 15) >> 4;
       int kc_max = (kXsFloats / (mt_n * 16) - 8) & ~7;
-      if (kc_max > kMaxKs * kWarps * 8) kc_max = kMaxKs * kWarps * 8;
+      if (kc_max > kKc) kc_max = kKc;
       float acc[kMT][4];
 #pragma unroll
       for (int i = 0; i < kMT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
       for (int k0 = 0; k0 < Kred; k0 += kc_max) {
         const int kn = min(kc_max, Kred - k0);
         const int ld = kn + 8;                          // +8 floats: conflict-free 64-bit fragment reads
-        // ---- stage A[mbase : mbase+mrows, k0 : k0+kn] ----
-        if (A2::kBulk) {
-          if (threadIdx.x == 0) mbar_expect_tx(cx.bar, (uint32_t)(mrows * kn * 4));
+        // ---- stage A[mbase : mbase+mrows, k0 : k0+kn] and the weight slab B[k0 : k0+kn, n0 : n0+8] ----
+        const uint32_t tx_bytes = (A2::kBulk ? (uint32_t)(mrows * kn * 4) : 0u) + (B2::kBulk ? (uint32_t)(8 * kn * 4) : 0u);
+        if (tx_bytes) {
+          if (threadIdx.x == 0) mbar_expect_tx(cx.bar, tx_bytes);
           __syncthreads();
+        }
+        if (A2::kBulk) {
           if ((int)threadIdx.x < mrows) a2.issue(mbase + threadIdx.x, k0, kn, xs_u32 + (uint32_t)(threadIdx.x * ld) * 4, cx.bar);
         } else {
           const int half = kn >> 1;
@@ -112,34 +140,18 @@ __device__ void cta_skinny_gemm(int M, int N, int Kred, A2 a2, B2 b2, Epi epi, S
             *reinterpret_cast<float2*>(xs + m * ld + c2) = a2(mbase + m, k0 + c2);
           }
         }
-        // ---- this warp's slice of the weight slab, straight to registers ----
+        if (B2::kBulk) {
+          if (threadIdx.x >= 128 && threadIdx.x < 136) b2.issue(n0 + threadIdx.x - 128, k0, kn, ws_u32 + (uint32_t)((threadIdx.x - 128) * ld) * 4, cx.bar);
+        } else {
+          for (int r = threadIdx.x; r < kn; r += kThreads) b2.store_row(k0 + r, n0, ws + r, ld);
+        }
+        if (tx_bytes) { mbar_wait(cx.bar, cx.phase); cx.phase ^= 1u; }
+        if (!A2::kBulk || !B2::kBulk) __syncthreads();
         const int ksteps = kn >> 3;
-        float2 w[kMaxKs];
-#pragma unroll
-        for (int j = 0; j < kMaxKs; ++j) {
-          const int ks = warp + j * kWarps;
-          w[j] = (ks < ksteps) ? b2(k0 + (ks << 3) + 2 * t, n0 + g) : make_float2(0.f, 0.f);
-        }
-        if (A2::kBulk) { mbar_wait(cx.bar, cx.phase); cx.phase ^= 1u; } else { __syncthreads(); }
-#pragma unroll
-        for (int j = 0; j < kMaxKs; ++j) {
-          const int ks = warp + j * kWarps;
-          if (ks < ksteps) {
-            const float b[2] = {w[j].x, w[j].y};
-            const float* col = xs + (ks << 3) + 2 * t;
-#pragma unroll
-            for (int mt = 0; mt < kMT; ++mt) {
-              if (mt < mt_n) {
-                const int r_lo = mt * 16 + g, r_hi = r_lo + 8;
-                const float2 p = (r_lo < mrows) ? *reinterpret_cast<const float2*>(col + r_lo * ld) : make_float2(0.f, 0.f);
-                const float2 q = (r_hi < mrows) ? *reinterpret_cast<const float2*>(col + r_hi * ld) : make_float2(0.f, 0.f);
-                const float a[4] = {p.x, q.x, p.y, q.y};
-                mma_3x(acc[mt], a, b);
-              }
-            }
-          }
-        }
-        __syncthreads();                                 // everyone is done with xs before the next chunk lands
+        if (mt_n <= 2) skinny_core<2>(xs, ws, ld, mrows, ksteps, acc);
+        else if (mt_n <= 5) skinny_core<5>(xs, ws, ld, mrows, ksteps, acc);
+        else skinny_core<8>(xs, ws, ld, mrows, ksteps, acc);
+        __syncthreads();                                 // everyone is done with xs / ws before the next pass lands
       }
 #pragma unroll
       for (int mt = 0; mt < kMT; ++mt) {
@@ -151,10 +163,10 @@ __device__ void cta_skinny_gemm(int M, int N, int Kred, A2 a2, B2 b2, Epi epi, S
       }
       __syncthreads();
       for (int i = threadIdx.x; i < mrows * 8; i += kThreads) {
-        float s = 0.f;
+        float sum = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < kWarps; ++w8) s += red[(size_t)w8 * kMChunk * 8 + i];
-        epi(mbase + (i >> 3), n0 + (i & 7), s);
+        for (int w8 = 0; w8 < kWarps; ++w8) sum += red[(size_t)w8 * kMChunk * 8 + i];
+        epi(mbase + (i >> 3), n0 + (i & 7), sum);
       }
       __syncthreads();
     }
@@ -332,13 +344,28 @@ struct RowMajorMasked2 {  // X[m, r] where gate[m, r] > 0, else 0
   }
 };
 struct WeightNT2 {      // B(r, n) = W[n, r]  (forward: reduce along W's contiguous dim)
+  static constexpr bool kBulk = true;
   const float* w; int ld;
+  // row n of the slab = W[n, k0 : k0+kn], contiguous
+  __device__ __forceinline__ void issue(int n, int k0, int kn, uint32_t dst, uint32_t bar) const {
+    bulk_g2s(dst, w + (size_t)n * ld + k0, (uint32_t)kn * 4, bar);
+  }
+  __device__ __forceinline__ void store_row(int, int, float*, int) const {}
   __device__ __forceinline__ float2 operator()(int r, int n) const {
     return *reinterpret_cast<const float2*>(w + (size_t)n * ld + r);
   }
 };
 struct WeightNN2 {      // B(r, n) = W[r, n]  (input gradient: reduce along W's rows)
+  static constexpr bool kBulk = false;
   const float* w; int ld;
+  __device__ __forceinline__ void issue(int, int, int, uint32_t, uint32_t) const {}
+  // W[r, n0 : n0+8] (32 contiguous bytes) transposed into the [8][ld] slab at column `dst - slab`
+  __device__ __forceinline__ void store_row(int r, int n0, float* dst, int ldw) const {
+    const float4 lo = *reinterpret_cast<const float4*>(w + (size_t)r * ld + n0);
+    const float4 hi = *reinterpret_cast<const float4*>(w + (size_t)r * ld + n0 + 4);
+    dst[0] = lo.x; dst[ldw] = lo.y; dst[2 * ldw] = lo.z; dst[3 * ldw] = lo.w;
+    dst[4 * ldw] = hi.x; dst[5 * ldw] = hi.y; dst[6 * ldw] = hi.z; dst[7 * ldw] = hi.w;
+  }
   __device__ __forceinline__ float2 operator()(int r, int n) const {
     return make_float2(w[(size_t)r * ld + n], w[(size_t)(r + 1) * ld + n]);
   }
@@ -382,10 +409,11 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_fwd_kernel(GcnFwd p) {
   const int M = d.M(), R = d.R(), K1 = d.K1(), N2 = d.N2(), H = d.H;
   float* red = reinterpret_cast<float*>(gcn_smem);
   float* xs = red + kWarps * kMChunk * 8;
-  uint64_t* barp = reinterpret_cast<uint64_t*>(xs + kXsFloats);
+  float* ws = xs + kXsFloats;
+  uint64_t* barp = reinterpret_cast<uint64_t*>(ws + kWsFloats);
   int* s_idx = reinterpret_cast<int*>(barp + 2);
   int* o_idx = s_idx + M + 1;
-  StageCtx cx{red, xs, smem_u32(barp), 0u};
+  StageCtx cx{red, xs, ws, smem_u32(barp), 0u};
   if (threadIdx.x == 0) { mbar_init(cx.bar, 1); fence_barrier_init(); }
   load_indices(d, p.edges, s_idx, o_idx);
 
@@ -445,10 +473,11 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_bwd_kernel(GcnBwd p) {
   const int M = d.M(), R = d.R(), K1 = d.K1(), N2 = d.N2(), H = d.H, Dout = d.Dout, Dpo = d.Dpo;
   float* red = reinterpret_cast<float*>(gcn_smem);
   float* xs = red + kWarps * kMChunk * 8;
-  uint64_t* barp = reinterpret_cast<uint64_t*>(xs + kXsFloats);
+  float* ws = xs + kXsFloats;
+  uint64_t* barp = reinterpret_cast<uint64_t*>(ws + kWsFloats);
   int* s_idx = reinterpret_cast<int*>(barp + 2);
   int* o_idx = s_idx + M + 1;
-  StageCtx cx{red, xs, smem_u32(barp), 0u};
+  StageCtx cx{red, xs, ws, smem_u32(barp), 0u};
   if (threadIdx.x == 0) { mbar_init(cx.bar, 1); fence_barrier_init(); }
   load_indices(d, p.edges, s_idx, o_idx);
   const int total_warps = gridDim.x * kWarps;
@@ -535,13 +564,13 @@ static int gcn_check(const GcnDims& d) {
   AG2V_REQUIRE(d.B > 0 && d.O > 0 && d.E > 0, "gcn_layer: empty graph B=%d O=%d E=%d", d.B, d.O, d.E);
   AG2V_REQUIRE(d.Din % 8 == 0 && d.Dp % 8 == 0 && d.H % 8 == 0 && d.Dout % 8 == 0 && d.Dpo % 8 == 0,
                "gcn_layer: feature sizes must be multiples of 8 (Din=%d Dp=%d H=%d Dout=%d Dpo=%d)", d.Din, d.Dp, d.H, d.Dout, d.Dpo);
-  AG2V_REQUIRE(d.M() <= 4096 && d.E <= 512, "gcn_layer: at most 4096 edge rows per call and 512 edges per clip (got %d, %d)", d.M(), d.E);
+  AG2V_REQUIRE(d.M() <= 1024 && d.E <= 512, "gcn_layer: at most 1024 edge rows per call and 512 edges per clip (got %d, %d)", d.M(), d.E);
   AG2V_REQUIRE(d.Din % 4 == 0 && d.H % 4 == 0, "gcn_layer: Din and H must be multiples of 4");
   return AG2V_OK;
 }
 
 static size_t gcn_smem_bytes(const GcnDims& d) {
-  return (size_t)kWarps * kMChunk * 8 * sizeof(float) + (size_t)kXsFloats * sizeof(float) + 16 +
+  return (size_t)kWarps * kMChunk * 8 * sizeof(float) + (size_t)(kXsFloats + kWsFloats) * sizeof(float) + 16 +
          2 * (size_t)(d.M() + 1) * sizeof(int);
 }
 
