@@ -62,7 +62,7 @@ _H = (0.125, 0.208, 0.292)     # CATER object heights / 240
 
 
 def synthetic_batch(B=2, F=4, image_size=256, seed=1234, n_objects=None, n_actions=None,
-                    device='cpu', with_images=True):
+                    device='cpu', with_images=True, pad_to=None):
     """A seeded CATER-shaped batch with the tensor contract of the reference's
     collate_fn (data/dataset_params.py:8-104): ``imgs [B,F,3,H,W]``, ``objs
     [B,Omax,4]`` (last real row = __image__ dummy = zeros, padding zeros), ``boxes
@@ -75,6 +75,8 @@ def synthetic_batch(B=2, F=4, image_size=256, seed=1234, n_objects=None, n_actio
     n_obj = [n_objects if n_objects is not None else ri(5, 10) for _ in range(B)]
     n_act = [n_actions if n_actions is not None else ri(2, 6) for _ in range(B)]
     Omax, Tmax, Amax = max(n_obj) + 1, max(n_obj), max(n_act)
+    if pad_to is not None:          # fixed shapes (CUDA-graph replay): (objects incl. dummy, actions)
+        Omax, Tmax, Amax = max(Omax, pad_to[0]), max(Tmax, pad_to[0] - 1), max(Amax, pad_to[1])
     objs = torch.zeros(B, Omax, 4, dtype=torch.long)
     boxes = torch.full((B, F, Omax, 4), -1.0)
     triplets = torch.zeros(B, F, Tmax, 3, dtype=torch.long)

@@ -117,6 +117,52 @@ layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ wx_g
     // active objects of this row, up to 64 (two ballots), ascending object order
     unsigned m0 = __ballot_sync(0xffffffffu, lane < O && wy_s[lane * kRB + r] != 0.f);
     unsigned m1 = (O > 32) ? __ballot_sync(0xffffffffu, lane + 32 < O && wy_s[(lane + 32) * kRB + r] != 0.f) : 0u;
+    // Fast path (the common case: at most 4 objects touch a row, W <= 256): the row's x-weights
+    // and y-weights stay in registers across the channel loop, so each output float4 costs one
+    // broadcast LDS per active object instead of three loads.
+    const int n_act = __popc(m0) + __popc(m1);
+    if (VEC4 && n_act <= 4 && W <= 256) {
+      float4 wxa[4][2];
+      float wya[4];
+      int oa[4];
+      {
+        unsigned mm0 = m0, mm1 = m1;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          int o = -1;
+          if (mm0) { o = __ffs(mm0) - 1; mm0 &= mm0 - 1; }
+          else if (mm1) { o = __ffs(mm1) - 1 + 32; mm1 &= mm1 - 1; }
+          oa[a] = o < 0 ? 0 : o;
+          wya[a] = o < 0 ? 0.f : wy_s[o * kRB + r];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int x4 = lane + 32 * k;
+            wxa[a][k] = (o >= 0 && x4 < (W >> 2)) ? reinterpret_cast<const float4*>(wx_s + (size_t)o * W)[x4]
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      for (int c = 0; c < chans; ++c) {
+        float* dst = out + (((size_t)n * D + d0 + c) * H + y0 + r) * W;
+        float coef[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) coef[a] = v_s[oa[a] * kDC + c] * wya[a];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int x4 = lane + 32 * k;
+          if (x4 < (W >> 2)) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {          // object order; inactive slots have coef == 0 and w == 0
+              acc.x = fmaf(coef[a], wxa[a][k].x, acc.x); acc.y = fmaf(coef[a], wxa[a][k].y, acc.y);
+              acc.z = fmaf(coef[a], wxa[a][k].z, acc.z); acc.w = fmaf(coef[a], wxa[a][k].w, acc.w);
+            }
+            reinterpret_cast<float4*>(dst)[x4] = acc;
+          }
+        }
+      }
+      continue;
+    }
     for (int c = 0; c < chans; ++c) {
       float* dst = out + (((size_t)n * D + d0 + c) * H + y0 + r) * W;
       if (VEC4) {

@@ -90,8 +90,8 @@ PROFILE = None                     # bench.py sets this to a list to time every 
 class _Timed:
     """Records (kind, flops, start, end) around one launch on the current stream."""
 
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, tag=None):
+        self.kind, self.flops, self.tag = kind, flops, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -102,12 +102,12 @@ class _Timed:
     def __exit__(self, *a):
         if PROFILE is not None:
             self.e.record()
-            PROFILE.append((self.kind, self.flops, self.s, self.e))
+            PROFILE.append((self.kind, self.flops, self.s, self.e, self.tag))
 
 
 def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, epi, round_out=0,
           x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None):
-    with _Timed('conv3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout):
+    with _Timed('conv3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout, ('epi%d' % epi, Hh, Cin, Nout)):
         L.check(L.lib().ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
                                      L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
                                      out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
@@ -128,7 +128,7 @@ def _wgrad(dy, Nout, x, x_strides, Cin, B, Hh, Ww, two, like_a, like_b):
     lib = L.lib()
     nsplit = lib.ag2v_wgrad3x3_nsplit(B, Hh, Ww, Nout, Cin, CONV_IMPL)
     part = torch.empty(nsplit * 9 * Nout * Cin, device=dy.device, dtype=torch.float32)
-    with _Timed('wgrad3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout):
+    with _Timed('wgrad3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout, ('wgrad', Hh, Cin, Nout)):
         L.check(lib.ag2v_wgrad3x3(L.ptr(dy), Nout, L.ptr(x), x_strides[0], x_strides[1], x_strides[2], Cin, B, Hh, Ww,
                                   L.ptr(part), CONV_IMPL, L.stream()))
     dwa = torch.empty_like(like_a, memory_format=torch.contiguous_format)

@@ -189,7 +189,8 @@ def run_ours(args):
     # a small pool of distinct clips per rank in pinned host memory (disjoint seeds per rank = sharding by clip)
     pool_host = []
     for i in range(4):
-        b = synthetic_batch(B=args.batch, F=args.frames, image_size=args.size, seed=1234 + 1000 * rank + i)
+        b = synthetic_batch(B=args.batch, F=args.frames, image_size=args.size, seed=1234 + 1000 * rank + i,
+                            pad_to=(11, 6))          # CATER maxima: 10 objects + dummy, 6 actions -> static shapes
         pool_host.append({k: v.pin_memory() for k, v in b.items()})
     pool_dev = [{k: v.to(dev) for k, v in b.items()} for b in pool_host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
@@ -307,10 +308,18 @@ def run_ours(args):
     pk = peaks()
     roof = None
     if prof:
-        agg = {}
-        for kind, flops, s, e in prof:
+        agg, by_shape = {}, {}
+        for kind, flops, s, e, tag in prof:
+            ms_ = s.elapsed_time(e)
             a = agg.setdefault(kind, [0.0, 0.0, 0])
-            a[0] += flops; a[1] += s.elapsed_time(e); a[2] += 1
+            a[0] += flops; a[1] += ms_; a[2] += 1
+            a = by_shape.setdefault((kind,) + tuple(tag or ()), [0.0, 0.0, 0])
+            a[0] += flops; a[1] += ms_; a[2] += 1
+        if os.environ.get('AG2V_BENCH_BREAKDOWN') and rank == 0:
+            with open(os.environ['AG2V_BENCH_BREAKDOWN'], 'w') as f:
+                f.write('kind epi r Cin Nout launches ms_per_step TFLOPs\n')
+                for key, (fl_, ms_, n_) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
+                    f.write('%s %d %.3f %.1f\n' % (' '.join(str(k) for k in key), n_, ms_ / prof_steps, fl_ / (ms_ / 1e3) / 1e12))
         kind = max(agg, key=lambda k: agg[k][1])
         fl, ms, n = agg[kind]
         achieved = fl / (ms / 1e3) / 1e12
