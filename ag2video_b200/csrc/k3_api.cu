@@ -20,7 +20,8 @@ extern "C" int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, l
                             int Ww, int Cin, const float* wpk, const float* bias, int Nout, float* out,
                             long long out_sb, long long out_sy, long long out_sx, int epilogue, int round_out,
                             const float* x, const float* mean, const float* rstd, float* gamma_out,
-                            float slope, int C, const float* gate, int impl, cudaStream_t stream) {
+                            float slope, int C, const float* gate, float* splitk_ws, size_t splitk_ws_floats,
+                            int impl, cudaStream_t stream) {
   ConvParams p{};
   p.in = in; p.in_sb = in_sb; p.in_sy = in_sy; p.in_sx = in_sx;
   p.B = B; p.Hh = Hh; p.Ww = Ww; p.Cin = Cin;
@@ -28,6 +29,7 @@ extern "C" int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, l
   p.out = out; p.out_sb = out_sb; p.out_sy = out_sy; p.out_sx = out_sx;
   p.x = x; p.mean = mean; p.rstd = rstd; p.gamma_out = gamma_out; p.slope = slope; p.C = C;
   p.gate = gate;
+  p.splitk_ws = splitk_ws; p.splitk_ws_floats = splitk_ws_floats;
   int rc = conv3x3_check(p, epilogue);
   if (rc) return rc;
   if (impl == 1) return conv3x3_mma(p, epilogue, round_out, 0, stream);
@@ -39,6 +41,16 @@ extern "C" int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, l
   }
   if (conv3x3_tc_supported(p, epilogue)) return conv3x3_tc(p, epilogue, round_out, stream);
   return conv3x3_mma(p, epilogue, round_out, 0, stream);
+}
+
+// Floats of split-K scratch worth passing to ag2v_conv3x3 for this shape (0: not needed).
+extern "C" size_t ag2v_conv3x3_splitk_floats(int B, int Hh, int Ww, int Cin, int Nout) {
+  const long long tiles = ceil_div_ll((long long)B * Hh * Ww, 128) * ceil_div(Nout, 128);
+  const int total = 9 * (Cin / 32);
+  if (tiles * 2 > sm_count() || total < 24 || Cin % 32) return 0;
+  long long ks = ceil_div_ll(sm_count(), tiles);
+  if (ks > total / 8) ks = total / 8;
+  return ks <= 1 ? 0 : (size_t)ks * B * Hh * Ww * Nout;
 }
 
 extern "C" int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue) {

@@ -21,6 +21,7 @@ enum ConvEpilogue : int {
   EPI_SPADE = 2,       // out = act((x-mean)*rstd*(1+g)+b), g/b = acc + bias (normalization.py:104-108)
   EPI_GATE = 3,        // out = gate > 0 ? acc : 0                  (backward through the ReLU)
   EPI_ACCUM = 4,       // out += acc   (gradient w.r.t. the shared full-resolution segmap)
+  EPI_RAW = 5,         // internal: split-K partial sums, finished by conv_finish_kernel
 };
 
 struct ConvParams {
@@ -35,6 +36,8 @@ struct ConvParams {
   const float* x; const float* mean; const float* rstd; float* gamma_out; float slope; int C;
   // EPI_GATE
   const float* gate;
+  // split-K workspace (caller-provided, may be null): ksplit * P * Nout floats
+  float* splitk_ws; size_t splitk_ws_floats;
 };
 
 __host__ __device__ inline int gb8_col(int c, int is_beta) { return 16 * (c >> 3) + 8 * is_beta + (c & 7); }

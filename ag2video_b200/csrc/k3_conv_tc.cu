@@ -13,9 +13,9 @@
 //   (M=128, N=BN, K=8 per instruction, 4 instructions per stage);
 // * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
 //   warps 2..5 = epilogue (tcgen05.ld, one accumulator row = one pixel per thread);
-// * 3/4-stage mbarrier ring.  Tile shape per launch: 1 or 2 M tiles x 128 or 256
-//   columns per CTA (TMEM: 128..512 columns), chosen on the host; the smallest shape
-//   runs two CTAs per SM so one CTA's epilogue overlaps the other's main loop.
+// * persistent CTAs (one per SM) walk a static schedule of work items; 4-6 stage mbarrier
+//   ring for the operands and TWO accumulator stages in TMEM, so the epilogue of one work
+//   item overlaps the main loop of the next.  Work item = 1 or 2 M tiles x 128 or 256 columns.
 #include <stdlib.h>
 #include <string.h>
 #include "k3_common.cuh"
@@ -26,52 +26,128 @@ namespace ag2v {
 constexpr int TC_BM = 128, TC_BK = 32;
 constexpr int TC_THREADS = 192;
 
-struct TcGeom { int Wt, Ht, Bt, tiles_x, tiles_y, tiles_b; };
+struct TcGeom { int Wt, Ht, Bt, tiles_x, tiles_y, tiles_b, mtiles, ntiles, work, ksplit, its_per_split; };
 
-// MT = M tiles (128 pixels each) per CTA, BN = output columns per CTA.  L2 -> smem
-// operand traffic per MMA cycle is (MT*16 KB + BN*128 B) / (MT * BN * 2 cycles):
-//   MT=1,BN=128: 128 B/cycle   MT=2,BN=128 or MT=1,BN=256: 96 B/cycle   MT=2,BN=256: 64 B/cycle
-// which is what decides the tensor-pipe utilisation of this kernel.
+// MT = M tiles (128 pixels each) per work item, BN = output columns per work item.
+// L2 -> smem operand traffic per MMA cycle is (MT*16 KB + BN*128 B) / (MT * BN * 2 cycles):
+//   MT=1,BN=128: 128 B/cycle     MT=2,BN=128 or MT=1,BN=256: 96 B/cycle
+// Two accumulator stages in TMEM (2 * MT * BN <= 512 columns) let the epilogue of one
+// work item overlap the main loop of the next.
 template <int MT, int BN>
 struct TcCfg {
   static constexpr int kA = TC_BM * TC_BK * 4;                 // 16 KB per M tile
   static constexpr int kB = BN * TC_BK * 4;                    // 16 / 32 KB
   static constexpr int kStage = MT * kA + kB;
-  static constexpr int kStages = (MT == 1 && BN == 128) ? 3 : (kStage <= 48 * 1024 ? 4 : 3);
+  static constexpr int kStages = (192 * 1024) / kStage;        // 6 (32 KB stages) or 4 (48 KB stages)
+  static constexpr int kAccStages = 2;
+  static constexpr int kAccCols = MT * BN;
+  static constexpr int kTmemCols = kAccStages * kAccCols;      // 256 or 512
   static constexpr int kBytes = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = MT * BN;                    // 128, 256 or 512
-  static constexpr int kMinBlocks = (MT == 1 && BN == 128) ? 2 : 1;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+// one 32-column chunk of one accumulator row (= one pixel): v[] holds the fp32 sums
+template <int EPI, bool ROUND_OUT>
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float (&v)[32], int n, long long pp, float* orow) {
+  if (EPI == EPI_SPADE) {
+    const int c = n >> 1;                                           // 16 channels: [g8 | b8 | g8 | b8]
+    const size_t off = (size_t)pp * p.C + c;
+    float xs[16], mu[16], rs[16], o[16], gm_[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float4*>(xs + 4 * i) = *reinterpret_cast<const float4*>(p.x + off + 4 * i);
+      *reinterpret_cast<float4*>(mu + 4 * i) = *reinterpret_cast<const float4*>(p.mean + c + 4 * i);
+      *reinterpret_cast<float4*>(rs + 4 * i) = *reinterpret_cast<const float4*>(p.rstd + c + 4 * i);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int jg = (i >> 3) * 16 + (i & 7), jb = jg + 8;
+      float g = v[jg], bb = v[jb];
+      if (p.bias) { g += p.bias[n + jg]; bb += p.bias[n + jb]; }
+      float r = (xs[i] - mu[i]) * rs[i] * (1.f + g) + bb;
+      if (p.slope != 1.f) r = r > 0.f ? r : r * p.slope;
+      if (ROUND_OUT) r = tc_round_tf32(r);
+      o[i] = r; gm_[i] = g;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float4*>(orow + c + 4 * i) = *reinterpret_cast<const float4*>(o + 4 * i);
+      if (p.gamma_out) *reinterpret_cast<float4*>(p.gamma_out + off + 4 * i) = *reinterpret_cast<const float4*>(gm_ + 4 * i);
+    }
+  } else {
+    const int ncols = min(32, p.Nout - n);
+    if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += p.bias[n + j];
+      }
+      if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+    } else if (EPI == EPI_GATE) {
+      const float* gt = p.gate + (size_t)pp * p.Nout + n;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < ncols) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gt + j);
+          v[j] = g4.x > 0.f ? v[j] : 0.f; v[j + 1] = g4.y > 0.f ? v[j + 1] : 0.f;
+          v[j + 2] = g4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = g4.w > 0.f ? v[j + 3] : 0.f;
+        }
+      }
+    } else if (EPI == EPI_ACCUM) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < ncols) {
+          const float4 o4 = *reinterpret_cast<const float4*>(orow + n + j);
+          v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
+        }
+      }
+    }
+    if (ROUND_OUT) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tc_round_tf32(v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      if (j < ncols) *reinterpret_cast<float4*>(orow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+}
+
+// work item w -> (column tile, first M tile); column tile fastest so that CTAs running side by
+// side share the activation tile in L2.  tile -> (x0, y0, b0); a tile past the end gives b0 >= B
+// (every row masked, TMA fills zeros).
+__device__ __forceinline__ void tile_origin(const TcGeom& gm, int tile, int& x0, int& y0, int& b0) {
+  const int tx = tile % gm.tiles_x; tile /= gm.tiles_x;
+  const int ty = tile % gm.tiles_y; tile /= gm.tiles_y;
+  x0 = tx * gm.Wt; y0 = ty * gm.Ht; b0 = tile * gm.Bt;
+}
+
+// Persistent: grid = min(work items, SMs); every role walks the same static schedule
+// w = blockIdx.x, blockIdx.x + gridDim.x, ...
 template <int MT, int BN, int EPI, bool ROUND_OUT>
-__global__ void __launch_bounds__(TC_THREADS, TcCfg<MT, BN>::kMinBlocks)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   ConvParams p, TcGeom gm) {
   using Cfg = TcCfg<MT, BN>;
-  constexpr int S = Cfg::kStages;
+  constexpr int S = Cfg::kStages, AS = Cfg::kAccStages;
   extern __shared__ uint8_t tc_smem_raw[];
   const uint32_t raw = smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                         // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t bars = base + S * Cfg::kStage;                         // full[S], empty[S], tmem_full, tmem slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem_raw + (bars - raw) + 8 * (2 * S + 1));
+  const uint32_t bars = base + S * Cfg::kStage;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * S;            // smem ring
+  const uint32_t bar_tfull = bars + 16 * S, bar_tempty = bar_tfull + 8 * AS;   // accumulator stages
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem_raw + (bars - raw) + 16 * S + 16 * AS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates of the MT consecutive tiles this CTA owns
-  int x0[MT], y0[MT], b0[MT];
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    int tile = blockIdx.x * MT + mt;
-    const int tx = tile % gm.tiles_x; tile /= gm.tiles_x;
-    const int ty = tile % gm.tiles_y; tile /= gm.tiles_y;
-    x0[mt] = tx * gm.Wt; y0[mt] = ty * gm.Ht; b0[mt] = tile * gm.Bt;   // tile past the end => b0 >= B: all rows masked
-  }
-  const int n0 = blockIdx.y * BN;
   const int KC = p.Cin / TC_BK;
   const int total = 9 * KC;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (S + s), 1); }
-    mbar_init(bars + 8 * (2 * S), 1);
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < AS; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
@@ -79,135 +155,144 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < total; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (uint32_t)(it / S) & 1u;
-        mbar_wait(bars + 8 * (S + s), ph ^ 1u);                        // slot free
-        const int tap = it / KC, kc = it - tap * KC;
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        const uint32_t a_dst = base + s * Cfg::kStage, b_dst = a_dst + MT * Cfg::kA;
-        mbar_expect_tx(bars + 8 * s, Cfg::kStage);
+      uint32_t g_it = 0;
+      for (int w = blockIdx.x; w < gm.work; w += gridDim.x) {
+        const int split = w % gm.ksplit, wt = w / gm.ksplit;
+        const int n0 = (wt % gm.ntiles) * BN, mt0 = (wt / gm.ntiles) * MT;
+        const int it0 = split * gm.its_per_split, it1 = min(total, it0 + gm.its_per_split);
+        int x0[MT], y0[MT], b0[MT];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-          tma_load_4d(a_dst + mt * Cfg::kA, &map_a, bars + 8 * s, kc * TC_BK, x0[mt] + dx, y0[mt] + dy, b0[mt]);
-        tma_load_3d(b_dst, &map_b, bars + 8 * s, kc * TC_BK, n0, tap);
+        for (int mt = 0; mt < MT; ++mt) tile_origin(gm, mt0 + mt, x0[mt], y0[mt], b0[mt]);
+        for (int it = it0; it < it1; ++it, ++g_it) {
+          const uint32_t s = g_it % S, ph = (g_it / S) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);                        // slot free
+          const int tap = it / KC, kc = it - tap * KC;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const uint32_t a_dst = base + s * Cfg::kStage, b_dst = a_dst + MT * Cfg::kA;
+          mbar_expect_tx(bar_full + 8 * s, Cfg::kStage);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_4d(a_dst + mt * Cfg::kA, &map_a, bar_full + 8 * s, kc * TC_BK, x0[mt] + dx, y0[mt] + dy, b0[mt]);
+          tma_load_3d(b_dst, &map_b, bar_full + 8 * s, kc * TC_BK, n0, tap);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (uint32_t)(it / S) & 1u;
-        mbar_wait(bars + 8 * s, ph);                                    // TMA bytes landed
+      uint32_t g_it = 0, a_it = 0;
+      for (int w = blockIdx.x; w < gm.work; w += gridDim.x, ++a_it) {
+        const uint32_t as = a_it % AS, aph = (a_it / AS) & 1u;
+        const int split = w % gm.ksplit;
+        const int it0 = split * gm.its_per_split, it1 = min(total, it0 + gm.its_per_split);
+        mbar_wait(bar_tempty + 8 * as, aph ^ 1u);                       // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_s = base + s * Cfg::kStage, b_s = a_s + MT * Cfg::kA;
-        const uint64_t db = make_sw128_kmajor_desc(b_s);
+        const uint32_t acc = tmem_base + as * Cfg::kAccCols;
+        for (int it = it0; it < it1; ++it, ++g_it) {
+          const uint32_t s = g_it % S, ph = (g_it / S) & 1u;
+          mbar_wait(bar_full + 8 * s, ph);                              // TMA bytes landed
+          tc_fence_after();
+          const uint32_t a_s = base + s * Cfg::kStage, b_s = a_s + MT * Cfg::kA;
+          const uint64_t db = make_sw128_kmajor_desc(b_s);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {                           // +32 bytes along K inside the swizzle atom
+          for (int k = 0; k < TC_BK / 8; ++k) {                         // +32 bytes along K inside the swizzle atom
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t da = make_sw128_kmajor_desc(a_s + mt * Cfg::kA);
-            umma_tf32(tmem_acc + (uint32_t)(mt * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t da = make_sw128_kmajor_desc(a_s + mt * Cfg::kA);
+              umma_tf32(acc + (uint32_t)(mt * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(bar_empty + 8 * s);                               // frees the smem slot when the MMAs retire
         }
-        umma_commit(bars + 8 * (S + s));                                // frees the smem slot when the MMAs retire
+        umma_commit(bar_tfull + 8 * as);                                // accumulators of this work item complete
       }
-      umma_commit(bars + 8 * (2 * S));                                  // accumulators complete
     }
   } else {
     // ---- epilogue: warps 2..5, TMEM lane quarter = warp % 4 --------------------
     const int q = warp & 3;
     const int m = q * 32 + lane;                                       // accumulator row = pixel within the tile
     const int xt = m % gm.Wt, yt = (m / gm.Wt) % gm.Ht, bt = m / (gm.Wt * gm.Ht);
-    mbar_wait(bars + 8 * (2 * S), 0);
-    tc_fence_after();
+    uint32_t a_it = 0;
+    for (int w = blockIdx.x; w < gm.work; w += gridDim.x, ++a_it) {
+      const uint32_t as = a_it % AS, aph = (a_it / AS) & 1u;
+      const int split = w % gm.ksplit, wt = w / gm.ksplit;
+      const int n0 = (wt % gm.ntiles) * BN, mt0 = (wt / gm.ntiles) * MT;
+      mbar_wait(bar_tfull + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + as * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-    const int x = x0[mt] + xt, y = y0[mt] + yt, b = b0[mt] + bt;
-    const bool valid = x < p.Ww && y < p.Hh && b < p.B;
-    const long long pp = ((long long)b * p.Hh + y) * p.Ww + x;
-    float* orow = p.out + (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
+      for (int mt = 0; mt < MT; ++mt) {
+        int x0, y0, b0;
+        tile_origin(gm, mt0 + mt, x0, y0, b0);
+        const int x = x0 + xt, y = y0 + yt, b = b0 + bt;
+        const bool valid = x < p.Ww && y < p.Hh && b < p.B;
+        const long long pp = ((long long)b * p.Hh + y) * p.Ww + x;
+        float* orow = (EPI == EPI_RAW)
+            ? p.splitk_ws + ((size_t)split * p.B * p.Hh * p.Ww + (size_t)pp) * p.Nout        // partial sums [split][pixel][n]
+            : p.out + (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      float v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + ch * 32), v);
-      const int n = n0 + ch * 32;
-      if (!valid || n >= p.Nout) continue;
-      if (EPI == EPI_SPADE) {
-        const int c = n >> 1;                                           // 16 channels: [g8 | b8 | g8 | b8]
-        const size_t off = (size_t)pp * p.C + c;
-        float xs[16], mu[16], rs[16], o[16], gm_[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *reinterpret_cast<float4*>(xs + 4 * i) = *reinterpret_cast<const float4*>(p.x + off + 4 * i);
-          *reinterpret_cast<float4*>(mu + 4 * i) = *reinterpret_cast<const float4*>(p.mean + c + 4 * i);
-          *reinterpret_cast<float4*>(rs + 4 * i) = *reinterpret_cast<const float4*>(p.rstd + c + 4 * i);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int jg = (i >> 3) * 16 + (i & 7), jb = jg + 8;
-          float g = v[jg], bb = v[jb];
-          if (p.bias) { g += p.bias[n + jg]; bb += p.bias[n + jb]; }
-          float r = (xs[i] - mu[i]) * rs[i] * (1.f + g) + bb;
-          if (p.slope != 1.f) r = r > 0.f ? r : r * p.slope;
-          if (ROUND_OUT) r = tc_round_tf32(r);
-          o[i] = r; gm_[i] = g;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *reinterpret_cast<float4*>(orow + c + 4 * i) = *reinterpret_cast<const float4*>(o + 4 * i);
-          if (p.gamma_out) *reinterpret_cast<float4*>(p.gamma_out + off + 4 * i) = *reinterpret_cast<const float4*>(gm_ + 4 * i);
-        }
-      } else {
-        const int ncols = min(32, p.Nout - n);
-        if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += p.bias[n + j];
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          float v[32];
+          tmem_ld32(acc + (uint32_t)(mt * BN + ch * 32), v);
+          if (mt == MT - 1 && ch == BN / 32 - 1) {                      // last TMEM read of this stage: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
           }
-          if (EPI == EPI_BIAS_RELU) {
+          const int n = n0 + ch * 32;
+          if (valid && n < p.Nout) {
+            if (EPI == EPI_RAW) {
+              const int ncols = min(32, p.Nout - n);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-        } else if (EPI == EPI_GATE) {
-          const float* gt = p.gate + (size_t)pp * p.Nout + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 g4 = *reinterpret_cast<const float4*>(gt + j);
-              v[j] = g4.x > 0.f ? v[j] : 0.f; v[j + 1] = g4.y > 0.f ? v[j + 1] : 0.f;
-              v[j + 2] = g4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = g4.w > 0.f ? v[j + 3] : 0.f;
-            }
-          }
-        } else if (EPI == EPI_ACCUM) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 o4 = *reinterpret_cast<const float4*>(orow + n + j);
-              v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
+              for (int j = 0; j < 32; j += 4)
+                if (j < ncols) *reinterpret_cast<float4*>(orow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              epilogue_chunk<EPI, ROUND_OUT>(p, v, n, pp, orow);
             }
           }
         }
-        if (ROUND_OUT) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tc_round_tf32(v[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (j < ncols) *reinterpret_cast<float4*>(orow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-    }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_acc, Cfg::kTmemCols); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+}
+
+// Split-K finish: sum the partial tiles in split order (deterministic) and apply the epilogue.
+// One thread per (pixel, 32-column chunk), the granularity of epilogue_chunk.
+template <int EPI, bool ROUND_OUT>
+__global__ void __launch_bounds__(128) conv_finish_kernel(ConvParams p, int ksplit) {
+  const long long P = (long long)p.B * p.Hh * p.Ww;
+  const int chunks = (p.Nout + 31) / 32;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * chunks) return;
+  const long long pp = i / chunks;
+  const int n = (int)(i - pp * chunks) * 32;
+  const int ncols = min(32, p.Nout - n);
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  for (int s = 0; s < ksplit; ++s) {
+    const float* src = p.splitk_ws + ((size_t)s * P + (size_t)pp) * p.Nout + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        const float4 t = *reinterpret_cast<const float4*>(src + j);
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+    }
+  }
+  const int b = (int)(pp / ((long long)p.Hh * p.Ww));
+  const int rem = (int)(pp - (long long)b * p.Hh * p.Ww);
+  const int y = rem / p.Ww, x = rem - y * p.Ww;
+  float* orow = p.out + (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
+  epilogue_chunk<EPI, ROUND_OUT>(p, v, n, pp, orow);
 }
 
 // ---- host side -----------------------------------------------------------------
@@ -235,6 +320,7 @@ static bool tc_geometry(const ConvParams& p, TcGeom* g) {
     else { if (!is_pow2(p.Hh)) return false; g->Ht = p.Hh; g->Bt = rows / p.Hh; }
   }
   g->tiles_x = ceil_div(p.Ww, g->Wt); g->tiles_y = ceil_div(p.Hh, g->Ht); g->tiles_b = ceil_div(p.B, g->Bt);
+  g->mtiles = g->tiles_x * g->tiles_y * g->tiles_b; g->ntiles = 0; g->work = 0;
   return true;
 }
 
@@ -251,8 +337,36 @@ bool conv3x3_tc_supported(const ConvParams& p, int epi) {
   return tma_encode_fn() != nullptr;
 }
 
+// Split the reduction (9 taps x Cin/32 chunks) over CTAs when the output tiles alone cannot fill
+// the chip: low-resolution layers have 1-16 tiles but up to 576 reduction steps.
+static int choose_ksplit(const ConvParams& p, int tiles) {
+  const int total = 9 * (p.Cin / TC_BK);
+  if (p.splitk_ws == nullptr || tiles * 2 > sm_count() || total < 24) return 1;
+  int ks = ceil_div(sm_count(), tiles);
+  if (ks > total / 8) ks = total / 8;                       // at least 8 reduction steps per split
+  const size_t per = (size_t)p.B * p.Hh * p.Ww * p.Nout;
+  while (ks > 1 && (size_t)ks * per > p.splitk_ws_floats) --ks;
+  return ks < 1 ? 1 : ks;
+}
+
+template <int EPI, bool RO>
+static int launch_finish(const ConvParams& p, int ksplit, cudaStream_t stream) {
+  const long long items = (long long)p.B * p.Hh * p.Ww * ((p.Nout + 31) / 32);
+  conv_finish_kernel<EPI, RO><<<(unsigned)ceil_div_ll(items, 128), 128, 0, stream>>>(p, ksplit);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
 template <int MT, int BN, int EPI, bool RO>
-static int launch_tc(const ConvParams& p, const TcGeom& g, cudaStream_t stream) {
+static int launch_tc(const ConvParams& p, const TcGeom& g0, cudaStream_t stream) {
+  TcGeom g = g0;
+  g.ntiles = ceil_div(p.Nout, BN);
+  const int tiles = ceil_div(g.mtiles, MT) * g.ntiles;
+  const int total = 9 * (p.Cin / TC_BK);
+  g.ksplit = (EPI == EPI_RAW) ? choose_ksplit(p, tiles) : 1;
+  g.its_per_split = ceil_div(total, g.ksplit);
+  g.ksplit = ceil_div(total, g.its_per_split);              // no empty splits
+  g.work = tiles * g.ksplit;
   EncodeTiledFn enc = tma_encode_fn();
   CUtensorMap map_a, map_b;
   {
@@ -278,7 +392,7 @@ static int launch_tc(const ConvParams& p, const TcGeom& g, cudaStream_t stream) 
   }
   const int smem = TcCfg<MT, BN>::kBytes;
   AG2V_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<MT, BN, EPI, RO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid(ceil_div(g.tiles_x * g.tiles_y * g.tiles_b, MT), ceil_div(p.Nout, BN));
+  const int grid = g.work < sm_count() ? g.work : sm_count();
   conv3x3_tc_kernel<MT, BN, EPI, RO><<<grid, TC_THREADS, smem, stream>>>(map_a, map_b, p, g);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
@@ -286,6 +400,21 @@ static int launch_tc(const ConvParams& p, const TcGeom& g, cudaStream_t stream) 
 
 template <int MT, int BN>
 static int dispatch_tc(const ConvParams& p, const TcGeom& g, int epi, int round_out, cudaStream_t stream) {
+  const int tiles = ceil_div(g.mtiles, MT) * ceil_div(p.Nout, BN);
+  const int ks = choose_ksplit(p, tiles);
+  if (ks > 1) {                                               // partial tiles, then the finishing pass
+    int rc = launch_tc<MT, BN, EPI_RAW, false>(p, g, stream);
+    if (rc) return rc;
+    const int total = 9 * (p.Cin / TC_BK);
+    const int ksplit = ceil_div(total, ceil_div(total, ks));
+    switch (epi) {
+      case EPI_BIAS: return round_out ? launch_finish<EPI_BIAS, true>(p, ksplit, stream) : launch_finish<EPI_BIAS, false>(p, ksplit, stream);
+      case EPI_BIAS_RELU: return round_out ? launch_finish<EPI_BIAS_RELU, true>(p, ksplit, stream) : launch_finish<EPI_BIAS_RELU, false>(p, ksplit, stream);
+      case EPI_SPADE: return round_out ? launch_finish<EPI_SPADE, true>(p, ksplit, stream) : launch_finish<EPI_SPADE, false>(p, ksplit, stream);
+      case EPI_GATE: return round_out ? launch_finish<EPI_GATE, true>(p, ksplit, stream) : launch_finish<EPI_GATE, false>(p, ksplit, stream);
+      case EPI_ACCUM: return launch_finish<EPI_ACCUM, false>(p, ksplit, stream);
+    }
+  }
   switch (epi) {
     case EPI_BIAS: return round_out ? launch_tc<MT, BN, EPI_BIAS, true>(p, g, stream) : launch_tc<MT, BN, EPI_BIAS, false>(p, g, stream);
     case EPI_BIAS_RELU: return round_out ? launch_tc<MT, BN, EPI_BIAS_RELU, true>(p, g, stream) : launch_tc<MT, BN, EPI_BIAS_RELU, false>(p, g, stream);
@@ -302,11 +431,11 @@ int conv3x3_tc(const ConvParams& p, int epi, int round_out, cudaStream_t stream)
   if (((uintptr_t)p.in & 15) || ((uintptr_t)p.wpk & 15)) return fail(AG2V_ERR_ARG, "conv3x3_tc: operands must be 16-byte aligned");
   // tile shape: widest columns the problem has, two M tiles per CTA once that still fills the chip
   const char* force = getenv("AG2V_TC_TILE");                 // e.g. "2x256": force a tile shape (tests / ablation)
-  const int mtiles = g.tiles_x * g.tiles_y * g.tiles_b;
+  // 256 columns when the problem has them; otherwise two M tiles per work item once that still
+  // leaves every SM at least two work items (TMEM holds 2 stages x 256 columns either way)
   int bn = p.Nout >= 256 ? 256 : 128;
-  int mt = (long long)ceil_div(mtiles, 2) * ceil_div(p.Nout, bn) >= sm_count() ? 2 : 1;
-  if (force) { mt = force[0] == '2' ? 2 : 1; bn = strstr(force, "256") ? 256 : 128; }
-  if (mt == 2 && bn == 256) return dispatch_tc<2, 256>(p, g, epi, round_out, stream);
+  int mt = (bn == 128 && ceil_div(g.mtiles, 2) * ceil_div(p.Nout, 128) >= 2 * sm_count()) ? 2 : 1;
+  if (force) { mt = force[0] == '2' ? 2 : 1; bn = (mt == 1 && strstr(force, "256")) ? 256 : 128; }
   if (mt == 2) return dispatch_tc<2, 128>(p, g, epi, round_out, stream);
   if (bn == 256) return dispatch_tc<1, 256>(p, g, epi, round_out, stream);
   return dispatch_tc<1, 128>(p, g, epi, round_out, stream);

@@ -85,11 +85,11 @@ class Acts2LayoutModel(nn.Module):
         # everything that does not depend on the recurrence is prepared for all timesteps at once
         act_vecs = self.acts_embeddings(temporal_triplets[..., 1])
         act_vecs = torch.cat([act_vecs[..., :-3], x_end.unsqueeze(-1), y_end.unsqueeze(-1), rel_t.unsqueeze(-1)], dim=-1)
-        edges = temporal_triplets[..., [0, 2]]
+        edges = torch.stack([temporal_triplets[..., 0], temporal_triplets[..., 2]], dim=-1)   # (no list index: that is a host->device copy)
         ind = temporal_triplets[..., 1] != self.pad_act
         pred_vecs = act_vecs
         if not self.only_temporal:
-            edges = torch.cat([triplets[..., [0, 2]], edges], dim=2)
+            edges = torch.cat([torch.stack([triplets[..., 0], triplets[..., 2]], dim=-1), edges], dim=2)
             ind = torch.cat([triplets[..., 1] != self.pad_pred, ind], dim=2)
             pred_vecs = torch.cat([self.pred_embeddings(triplets[..., 1]), act_vecs], dim=2)
         edges, ind = edges.contiguous(), ind.contiguous()

@@ -39,7 +39,8 @@ L.register('ag2v_round_tf32', c_i, [c_p, c_p, c_ll, c_p])
 L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 6)
 L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p])
 L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_ll, c_ll, c_ll,
-                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_i, c_p])
+                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_p, c_sz, c_i, c_p])
+L.register('ag2v_conv3x3_splitk_floats', c_sz, [c_i] * 5)
 L.register('ag2v_conv3x3_tc_supported', c_i, [c_i] * 6)
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_SPADE, EPI_GATE, EPI_ACCUM = 0, 1, 2, 3, 4
@@ -107,11 +108,14 @@ class _Timed:
 
 def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, epi, round_out=0,
           x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None):
+    lib = L.lib()
+    nws = lib.ag2v_conv3x3_splitk_floats(B, Hh, Ww, Cin, Nout) if CONV_IMPL in (0, 2) else 0
+    ws = torch.empty(nws, device=out.device, dtype=torch.float32) if nws else None
     with _Timed('conv3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout, ('epi%d' % epi, Hh, Cin, Nout)):
-        L.check(L.lib().ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
-                                     L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
-                                     out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
-                                     L.ptr(gamma_out), float(slope), C, L.ptr(gate), CONV_IMPL, L.stream()))
+        L.check(lib.ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
+                                 L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
+                                 out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
+                                 L.ptr(gamma_out), float(slope), C, L.ptr(gate), L.ptr(ws), nws, CONV_IMPL, L.stream()))
 
 
 def _pack(wa, wb, ba, bb, dgrad):

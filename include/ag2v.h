@@ -122,8 +122,10 @@ int ag2v_pack_w3x3(const float* wa, const float* wb, const float* ba, const floa
 int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in_sx, int B, int Hh, int Ww, int Cin,
                  const float* wpk, const float* bias, int Nout, float* out, long long out_sb, long long out_sy,
                  long long out_sx, int epilogue, int round_out, const float* x, const float* mean,
-                 const float* rstd, float* gamma_out, float slope, int C, const float* gate, int impl,
-                 ag2v_stream_t stream);
+                 const float* rstd, float* gamma_out, float slope, int C, const float* gate, float* splitk_ws,
+                 size_t splitk_ws_floats, int impl, ag2v_stream_t stream);
+/* split-K scratch (floats) that lets low-resolution layers use the whole chip; 0 = none needed */
+size_t ag2v_conv3x3_splitk_floats(int B, int Hh, int Ww, int Cin, int Nout);
 int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue);
 
 /* SPADE backward, element-wise: pass 1 produces d(gamma|beta) [P,2C], dxhat and the

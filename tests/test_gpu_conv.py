@@ -65,6 +65,9 @@ SHAPES = [
     (1, 4, 128, 64, 128, 1),        # full-width row tiles
     (3, 8, 8, 32, 160, 1),          # batch tile hangs over (3 images, 2 per tile); Nout not a multiple of 128
     (1, 16, 256, 32, 64, 1),
+    (2, 128, 128, 32, 128, 1),      # 256 M tiles: persistent CTAs take 2 work items (both TMEM accumulator stages)
+    (1, 128, 256, 64, 256, 1),      # 256-column work items, 3+ per CTA
+    (2, 64, 64, 32, 512, 2),        # 64 M tiles x 2 column tiles, strided view
 ]
 
 
