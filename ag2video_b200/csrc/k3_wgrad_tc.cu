@@ -153,7 +153,7 @@ static bool wt_geometry(int B, int Hh, int Ww, int Nout, int Cin, WtGeom* g) {
   g->chunks = g->tiles_x * g->tiles_y * g->tiles_b;
   g->ntiles = ceil_div(Nout, WT_T); g->ctiles = ceil_div(Cin, WT_T);
   const int groups = g->ntiles * g->ctiles * 3;
-  int ns = ceil_div(sm_count(), groups);
+  int ns = sm_count() / groups;          // floor: one CTA per SM, a single wave (ceil would leave a 2nd wave of stragglers)
   if (ns > g->chunks) ns = g->chunks;
   if (ns > 64) ns = 64;
   if (ns < 1) ns = 1;

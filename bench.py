@@ -168,6 +168,10 @@ def run_ours(args):
     rank, world, local = agdist.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # everything (warm-up, capture, replay) runs on one non-default stream: autograd's
+    # AccumulateGrad nodes remember the stream of their first backward, and CUDA-graph capture
+    # cannot happen on the legacy default stream
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     L.check(L.lib().ag2v_check_device())
     sp.CONV_IMPL = args.conv_impl
     if world > 1:
@@ -233,14 +237,9 @@ def run_ours(args):
     launches_per_step = L.launch_count() - launches0
     if not args.no_graph:
         try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                eager_on_static()
-            torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
                 eager_on_static()
             graph, mode = g, 'cuda_graph'
         except Exception as exc:          # stay eager, but say so in the output

