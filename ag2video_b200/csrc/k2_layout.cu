@@ -273,6 +273,21 @@ static int layout_check(int N, int O, int D, int H, int W) {
   return AG2V_OK;
 }
 
+// Only the per-object separable weight tables + support windows (used by the fused
+// layout->conv kernels of k4_layoutconv.cu); workspace as for ag2v_boxes_to_layout_fwd.
+extern "C" int ag2v_boxes_to_layout_tables(const float* boxes, const uint8_t* valid, const float* lin_x,
+                                           const float* lin_y, int N, int O, int H, int W, void* workspace,
+                                           cudaStream_t stream) {
+  int rc = layout_check(N, O, 1, H, W);
+  if (rc) return rc;
+  if (N == 0 || O == 0) return AG2V_OK;
+  AG2V_REQUIRE(boxes && lin_x && lin_y && workspace, "boxes_to_layout_tables: null pointer");
+  LayoutWs ws = layout_ws_carve(workspace, N, O, H, W);
+  layout_tables_kernel<<<N * O, 256, 0, stream>>>(boxes, valid, lin_x, lin_y, O, H, W, 0, ws.wx, ws.wy, ws.range, ws.scale);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
 extern "C" int ag2v_boxes_to_layout_fwd(const float* vecs, const float* boxes, const uint8_t* valid,
                                         const float* lin_x, const float* lin_y, int N, int O, int D,
                                         int H, int W, int avg, void* workspace, float* out,

@@ -125,3 +125,69 @@ def masks_to_layout(vecs, boxes, masks, H, W=None, pooling='sum', test_mode=Fals
     if pooling != 'sum':
         raise ValueError('Invalid pooling "%s"' % pooling)
     return out
+
+
+# ---- K4: layout fused into its consumer convolution -------------
+L.register('ag2v_boxes_to_layout_tables', L.c_i, [L.c_p] * 4 + [L.c_i] * 4 + [L.c_p] + [L.c_p])
+L.register('ag2v_layout_conv_bwd_workspace_floats', L.c_sz, [L.c_i] * 4)
+L.register('ag2v_layout_conv_fwd', L.c_i, [L.c_p, L.c_p] + [L.c_i] * 5 + [L.c_p] + [L.c_p])
+L.register('ag2v_layout_conv_bwd', L.c_i, [L.c_p, L.c_p] + [L.c_i] * 5 + [L.c_p, L.c_p] + [L.c_p])
+
+
+def layout_tables(boxes, valid, H, W):
+    """Separable weight tables of K2 for boxes [N,S,4] / valid [N,S] (opaque workspace tensor)."""
+    L.need_cuda(boxes, valid)
+    boxes = L.f32c(boxes)
+    N, S = boxes.shape[:2]
+    dev = boxes.device
+    if valid is not None:
+        valid = valid.contiguous()
+        valid = valid.view(torch.uint8) if valid.dtype == torch.bool else (valid != 0).view(torch.uint8)
+    ws = torch.empty(max(L.lib().ag2v_boxes_to_layout_workspace_bytes(N, S, H, W), 16), device=dev, dtype=torch.uint8)
+    L.check(L.lib().ag2v_boxes_to_layout_tables(L.ptr(boxes), L.ptr(valid), L.ptr(_linspace(W, dev)), L.ptr(_linspace(H, dev)),
+                                                N, S, H, W, L.ptr(ws), L.stream()))
+    return ws
+
+
+class _LayoutConvFn(torch.autograd.Function):
+    """base [N,Co,H,W] (channels_last, modified IN PLACE) += sum_s sum_k U[n,s,k,:] * m_s(p+k)."""
+
+    @staticmethod
+    def forward(ctx, base, U, tables, S):
+        L.need_cuda(base, U, tables)
+        N, Co, H, W = base.shape
+        if not base.is_contiguous(memory_format=torch.channels_last) or base.dtype != torch.float32:
+            raise RuntimeError('layout_conv: base must be a float32 channels_last tensor')
+        U = L.f32c(U)
+        L.check(L.lib().ag2v_layout_conv_fwd(L.ptr(U), L.ptr(tables), N, S, Co, H, W, L.ptr(base), L.stream()))
+        ctx.mark_dirty(base)
+        ctx.save_for_backward(tables)
+        ctx.dims = (N, S, Co, H, W)
+        return base
+
+    @staticmethod
+    def backward(ctx, dout):
+        (tables,) = ctx.saved_tensors
+        N, S, Co, H, W = ctx.dims
+        dout = dout.float().contiguous(memory_format=torch.channels_last)
+        lib = L.lib()
+        part = torch.empty(lib.ag2v_layout_conv_bwd_workspace_floats(N, S, Co, H), device=dout.device, dtype=torch.float32)
+        dU = torch.empty(N, S, 9, Co, device=dout.device, dtype=torch.float32)
+        L.check(lib.ag2v_layout_conv_bwd(L.ptr(dout), L.ptr(tables), N, S, Co, H, W, L.ptr(part), L.ptr(dU), L.stream()))
+        return dout, dU, None, None
+
+
+def layout_conv3x3(weight, vec_slots, tables, base):
+    """conv3x3(layout(vec_slots), weight) added in place to ``base`` without ever building the layout.
+    weight [Co, n_slots*D, 3, 3] (the layout channels of the consumer conv), vec_slots: list of
+    [N,O,D] object vectors, one per frame slot (their boxes went into ``tables``, slot-major),
+    base [N,Co,H,W] channels_last (e.g. the convolution of the remaining image channels)."""
+    Co = weight.shape[0]
+    D = vec_slots[0].shape[-1]
+    N, O = vec_slots[0].shape[:2]
+    us = []
+    for j, v in enumerate(vec_slots):
+        wj = weight[:, j * D:(j + 1) * D].permute(2, 3, 0, 1).reshape(9 * Co, D)          # [(k, co), ci]
+        us.append((v.reshape(N * O, D) @ wj.t()).view(N, O, 9, Co))
+    U = torch.cat(us, dim=1)                                                              # [N, slots*O, 9, Co]
+    return _LayoutConvFn.apply(base, U, tables, U.shape[1])

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from torch.nn.utils import spectral_norm
 
 from .graph import GraphTripleConv
-from .layout import boxes_to_layout_batched
+from .layout import boxes_to_layout_batched, layout_conv3x3, layout_tables
 from .spade import SPADEResnetBlock, SharedSeg
 
 CL = torch.channels_last
@@ -239,7 +239,60 @@ class Layout2VidGenerator(nn.Module):
         seg = seg.view(B, T, -1, H, H)
         return torch.cat([seg, seg[:, -1:]], dim=1)
 
+    @staticmethod
+    def _sn_weight(conv):
+        """The spectrally normalised weight torch's hook would hand to the convolution
+        (power iteration in training mode, exactly once per call like a real forward)."""
+        for hook in conv._forward_pre_hooks.values():
+            hook(conv, None)
+        return conv.weight
+
+    def forward_fused(self, imgs_gt, objs, obj_vecs, layout, test_mode=False):
+        """Same computation as ``forward`` with the two convolutions that consume the layout
+        (flows_network.down_flow[0], conv_dim_in[0]) evaluated through the rank-1 structure of
+        the layout (csrc/k4_layoutconv.cu): the [B,F+1,512,H,W] layout, the 1027-channel
+        concatenations and the dense 1027->512 / 1027->32 convolutions never exist."""
+        B, T, O = layout.shape[:3]
+        H = self.opt.image_size[0]
+        n_prev = self.opt.n_frames_G - 1
+        assert n_prev == 1, 'fused path is written for n_frames_G = 2 (the reference default)'
+        att = self.attribute_embedding(objs)
+        vecs = torch.cat([att.unsqueeze(1).expand(B, T, O, att.shape[-1]), obj_vecs], dim=-1)      # [B,T,O,512]
+        D = vecs.shape[-1]
+        valid = real_object_mask(objs, self.opt.vocab)                                               # [B,O]
+        valid2 = torch.cat([valid, valid], dim=1)
+        flow_conv, flow_bn = self.flows_network.down_flow[0][0], self.flows_network.down_flow[0][1]
+        in_conv, in_bn = self.conv_dim_in[0][0], self.conv_dim_in[0][1]
+        imgs_prev = imgs_gt[:, :n_prev]
+        conf = torch.zeros(B, T, 1, H, H, device=imgs_gt.device)
+        flows = torch.zeros(B, T, 2, H, H, device=imgs_gt.device)
+        for t in range(n_prev, T):
+            # frame slots of seg_t: layout(t-1) -> channels [0, D), layout(t) -> channels [D, 2D)
+            tables = layout_tables(torch.cat([layout[:, t - 1], layout[:, t]], dim=1), valid2, H, H)
+            slots = [vecs[:, t - 1], vecs[:, t]]
+            prev = imgs_prev[:, -n_prev:] if (test_mode or self.opt.bp_prev) else imgs_gt[:, t - n_prev:t]
+            prev = prev.reshape(B, -1, H, H).contiguous(memory_format=CL)
+            wf = self._sn_weight(flow_conv)
+            x = layout_conv3x3(wf[:, :2 * D], slots, tables,
+                               F.conv2d(prev, wf[:, 2 * D:], padding=1).contiguous(memory_format=CL))
+            x = self.flows_network.down_flow[1](flow_bn(x))
+            feat = self.flows_network.up_flow(self.flows_network.res_flow(self.flows_network.down_flow[2:](x)))
+            flow = self.flows_network.conv_flow(feat) * self.flows_network.flow_multiplier
+            warped = flow_warp(prev[:, -3:], flow)
+            diff = prev[:, -3:] - warped
+            conf[:, t - 1] = ((diff * diff).sum(dim=1, keepdim=True) < 0.02).float()
+            flows[:, t - 1] = flow
+            wi = self._sn_weight(in_conv)
+            y = layout_conv3x3(wi[:, :2 * D], slots, tables,
+                               F.conv2d(warped.contiguous(memory_format=CL), wi[:, 2 * D:], padding=1).contiguous(memory_format=CL))
+            y = self.conv_dim_in[1](in_bn(y))
+            img = self.netG(y) + warped
+            imgs_prev = torch.cat([imgs_prev, img.unsqueeze(1)], dim=1)
+        return imgs_prev, flows, conf
+
     def forward(self, imgs_gt, objs, obj_vecs, layout, imgs_prev=None, test_mode=False):
+        if getattr(self, 'fuse_layout_conv', False) and self.channels_last:
+            return self.forward_fused(imgs_gt, objs, obj_vecs, layout, test_mode=test_mode)
         seg = self.build_layouts(objs, obj_vecs, layout)
         n_prev = self.opt.n_frames_G - 1
         B, T = imgs_gt.shape[0], layout.shape[1]
@@ -280,6 +333,8 @@ class AG2VideoModel(nn.Module):
         # eager reference.
         self.channels_last = bool(getattr(opt, 'channels_last', True))
         self.layout_to_video.channels_last = self.channels_last
+        # row f1: evaluate the layout's consumer convolutions through its rank-1 structure
+        self.layout_to_video.fuse_layout_conv = bool(getattr(opt, 'fuse_layout_conv', True))
         if self.channels_last:
             self.to(memory_format=CL)
 

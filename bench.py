@@ -331,7 +331,18 @@ def run_ours(args):
                 'measured_in': 'eager pass of %d steps, CUDA events around every launch' % prof_steps,
                 'all_kernels': {k: {'TFLOPs': v[0] / (v[1] / 1e3) / 1e12, 'ms_per_step': v[1] / prof_steps, 'launches': v[2]}
                                 for k, v in agg.items()}}
+    def shutdown():
+        # every rank leaves together; a rank that exits while another still tears NCCL down hangs the job
+        if world > 1:
+            try:
+                dist.barrier()
+                torch.cuda.synchronize()
+                dist.destroy_process_group()
+            except Exception:
+                pass
+
     if rank != 0:
+        shutdown()
         return
     line = {
         'metric': 'train-step frames/sec at CATER 256x256', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
@@ -350,9 +361,8 @@ def run_ours(args):
         'roofline': roof,
         'cpu_baseline': ({k: cpu_base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')} if cpu_base else None),
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    shutdown()
 
 
 def main():

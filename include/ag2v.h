@@ -69,6 +69,21 @@ int ag2v_boxes_to_layout_bwd(const float* dout, const float* boxes, const uint8_
                              const float* lin_y, int N, int O, int D, int H, int W, int avg, int recompute,
                              void* workspace, float* dvecs, ag2v_stream_t stream);
 
+/* ---- K4: layout fused into its consumer convolution ----------
+ * conv3x3(layout)[co,p] = sum_o sum_k U[o,k,co] * m_o(p+k) with U[o,k,:] = W[:,:,k] v[o,:]: the
+ * 1024-channel layout that generator.py:38-54 materialises and the dense 1027->512 / 1027->32
+ * convolutions over it (generator.py:29-33,82-83; flows_generator.py:32) collapse to these
+ * memory-bound kernels (U is a tiny GEMM done by the host).  tables = workspace of
+ * ag2v_boxes_to_layout_workspace_bytes(N,S,H,W) filled by ag2v_boxes_to_layout_tables for
+ * boxes [N,S,4]; out/dout are NHWC [N,H,W,Co], Co in {32, 512}; U/dU are [N,S,9,Co]. */
+int ag2v_boxes_to_layout_tables(const float* boxes, const uint8_t* valid, const float* lin_x, const float* lin_y,
+                                int N, int O, int H, int W, void* workspace, ag2v_stream_t stream);
+size_t ag2v_layout_conv_bwd_workspace_floats(int N, int S, int Co, int H);
+int ag2v_layout_conv_fwd(const float* U, const void* tables, int N, int S, int Co, int H, int W, float* out,
+                         ag2v_stream_t stream);
+int ag2v_layout_conv_bwd(const float* dout, const void* tables, int N, int S, int Co, int H, int W, float* part,
+                         float* dU, ag2v_stream_t stream);
+
 /* masks_to_layout (models/layout.py:66-95, _pool_mask_samples :164-202) for one
  * (clip, frame): vecs [O,D], boxes [O,4] xywh, masks [O,M,M]; S [O,H,W] receives the
  * sampled masks (kept for the backward); test_mode != 0 composites objects in

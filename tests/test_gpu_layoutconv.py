@@ -1,0 +1,75 @@
+"""K4: the layout fused into its consumer convolution vs the unfused
+path (boxes_to_layout followed by a dense 3x3 convolution), forward and backward."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import det_state, max_rel, rel_l2
+from ag2video_b200.config import make_opt, synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_library():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize('Co,H', [(512, 64), (32, 64), (512, 40)])
+def test_layout_conv_matches_dense_conv_of_layout(Co, H):
+    from ag2video_b200.layout import boxes_to_layout_batched, layout_conv3x3, layout_tables
+    b = synthetic_batch(B=3, F=2, image_size=8, seed=4, with_images=False)
+    N, O = 3, b['boxes'].shape[2]
+    D = 32
+    g = torch.Generator().manual_seed(0)
+    boxes = [b['boxes'][:, j].cuda() for j in range(2)]
+    valid = torch.ones(N, O, dtype=torch.bool, device='cuda')
+    valid[:, -1] = False
+    valid[1, 2] = False
+    vecs = [torch.randn(N, O, D, generator=g).cuda().requires_grad_() for _ in range(2)]
+    w = (torch.randn(Co, 2 * D + 3, 3, 3, generator=g) / 10).cuda().requires_grad_()
+    img = torch.randn(N, 3, H, H, generator=g).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    cot = torch.randn(N, Co, H, H, generator=g).cuda()
+    # unfused: the reference's structure
+    seg = torch.cat([boxes_to_layout_batched(vecs[j], boxes[j], valid, H) for j in range(2)], dim=1)
+    ref = F.conv2d(torch.cat([seg, img], dim=1), w, padding=1)
+    (ref * cot).sum().backward()
+    want = [ref.detach(), w.grad.clone(), img.grad.clone()] + [v.grad.clone() for v in vecs]
+    for t in [w, img] + vecs:
+        t.grad = None
+    # fused
+    tables = layout_tables(torch.cat(boxes, dim=1), torch.cat([valid, valid], dim=1), H, H)
+    base = F.conv2d(img, w[:, 2 * D:], padding=1).contiguous(memory_format=torch.channels_last)
+    out = layout_conv3x3(w[:, :2 * D], vecs, tables, base)
+    (out * cot).sum().backward()
+    got = [out.detach(), w.grad, img.grad] + [v.grad for v in vecs]
+    for a, r, name in zip(got, want, ['out', 'dW', 'dimg', 'dvecs0', 'dvecs1']):
+        assert max_rel(a, r) <= 2e-5, (name, max_rel(a, r))
+
+
+def test_fused_generator_equals_unfused():
+    """The whole generator with and without the fused layout->conv path: same weights, same clip."""
+    from ag2video_b200.networks import AG2VideoModel
+    res = []
+    for fuse in (False, True):
+        m = AG2VideoModel(make_opt(64, batch_size=2, fuse_layout_conv=fuse))
+        m.load_state_dict(det_state(m.state_dict(), 3), strict=True)
+        m = m.cuda().to(memory_format=torch.channels_last).train()
+        b = synthetic_batch(B=2, F=4, image_size=64, seed=8, device='cuda')
+        out = m(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+        loss = (out[0] - b['imgs']).abs().mean() + (out[1] - b['boxes'])[:, 1:].abs().mean()
+        loss.backward()
+        res.append((out[0].detach(), out[2].detach(), float(loss.detach()),
+                    {k: p.grad for k, p in m.named_parameters() if p.grad is not None}))
+    (i0, f0, l0, g0), (i1, f1, l1, g1) = res
+    print('fused vs unfused: imgs %.2e flows %.2e loss %.2e' % (max_rel(i1, i0), max_rel(f1, f0), abs(l1 - l0) / abs(l0)))
+    assert max_rel(f1, f0) <= 1e-4 and abs(l1 - l0) <= 1e-4 * abs(l0)
+    assert max_rel(i1, i0) <= 5e-3           # TF32 SPADE stack amplifies the 1e-6 input difference
+    assert set(g0) == set(g1)
+    worst = max((rel_l2(g1[k], g0[k]), k) for k in g0 if float(g0[k].norm()) > 1e-6)
+    print('fused vs unfused: worst gradient rel-L2 %.2e (%s)' % worst)
+    assert worst[0] <= 0.1
