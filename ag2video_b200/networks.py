@@ -22,6 +22,7 @@ from torch.nn.utils import spectral_norm
 from .graph import GraphTripleConv
 from .layout import boxes_to_layout_batched, layout_conv3x3, layout_tables
 from .spade import SPADEResnetBlock, SharedSeg
+from .specnorm import SpectralNormGroup
 
 CL = torch.channels_last
 
@@ -157,8 +158,10 @@ class FlowsGenerator(nn.Module):
         self.up_flow = nn.Sequential(*up)
         self.conv_flow = nn.Sequential(nn.Conv2d(nf, 2, 3, padding=1))
         self.conv_w = nn.Sequential(nn.Conv2d(nf, 1, 3, padding=1), nn.Sigmoid())
+        self.__dict__['_sn'] = SpectralNormGroup(self)
 
     def forward(self, label):
+        self._sn.refresh_stale()
         feat = self.up_flow(self.res_flow(self.down_flow(label)))
         return self.conv_w(feat), self.conv_flow(feat) * self.flow_multiplier
 
@@ -226,6 +229,8 @@ class Layout2VidGenerator(nn.Module):
         cin = opt.gconv_dim * 4 * opt.n_frames_G + 3
         self.conv_dim_in = nn.Sequential(_sn_conv_bn(cin, opt.semantic_nc), nn.LeakyReLU(0.2))
         self.channels_last = True
+        # all 38 spectral-norm weights of a call in one launch (csrc/k5_specnorm.cu)
+        self.__dict__['_sn'] = SpectralNormGroup(self)
 
     def build_layouts(self, objs, obj_vecs, boxes):
         """[B, F+1, D, H, H]: one launch for all (clip, frame) layouts (generator.py:36-54)."""
@@ -268,6 +273,7 @@ class Layout2VidGenerator(nn.Module):
         flows = torch.zeros(B, T, 2, H, H, device=imgs_gt.device)
         for t in range(n_prev, T):
             # frame slots of seg_t: layout(t-1) -> channels [0, D), layout(t) -> channels [D, 2D)
+            self._sn.refresh()             # one power iteration per generator call, like the reference's hooks
             tables = layout_tables(torch.cat([layout[:, t - 1], layout[:, t]], dim=1), valid2, H, H)
             slots = [vecs[:, t - 1], vecs[:, t]]
             prev = imgs_prev[:, -n_prev:] if (test_mode or self.opt.bp_prev) else imgs_gt[:, t - n_prev:t]
@@ -301,6 +307,7 @@ class Layout2VidGenerator(nn.Module):
         conf = torch.zeros(B, T, 1, H, H, device=imgs_gt.device)
         flows = torch.zeros(B, T, 2, H, H, device=imgs_gt.device)
         for t in range(n_prev, T):
+            self._sn.refresh()
             seg_t = seg[:, t - n_prev:t + 1].reshape(B, -1, H, H)
             prev = imgs_prev[:, -n_prev:] if (test_mode or self.opt.bp_prev) else imgs_gt[:, t - n_prev:t]
             prev = prev.reshape(B, -1, H, H)

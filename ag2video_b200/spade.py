@@ -22,6 +22,7 @@ from torch.nn.utils import spectral_norm
 
 from . import _lib as L
 from ._lib import c_f, c_i, c_p, c_sz
+from .specnorm import SpectralNormGroup
 
 c_ll = L.ctypes.c_longlong
 c_d = L.ctypes.c_double
@@ -375,8 +376,10 @@ class SPADEResnetBlock(nn.Module):
         self.norm_1.fused_slope = 0.2
         if self.learned_shortcut:
             self.norm_s = SPADE(cfg, fin, opt.semantic_nc)
+        self.__dict__['_sn'] = SpectralNormGroup(self)        # spectral norm through csrc/k5_specnorm.cu
 
     def forward(self, x, seg):
+        self._sn.refresh_stale()                              # no-op when the generator prepared the weights
         own = None
         if not isinstance(seg, SharedSeg):
             seg = own = SharedSeg.wrap(seg)

@@ -1,0 +1,179 @@
+"""Batched spectral normalisation (csrc/k5_specnorm.cu).
+
+The reference wraps every convolution of SPADEResnetBlock (architecture.py:34-41), of the flow
+network and of conv_dim_in (normalization.py:16-50) in ``torch.nn.utils.spectral_norm``: a
+forward pre-hook that recomputes ``module.weight`` from ``weight_orig / weight_u / weight_v``
+on every call, one power iteration per call in training mode.  ``SpectralNormGroup`` keeps
+those modules exactly as torch built them (same parameters, buffers, state-dict keys and
+per-call semantics) and replaces the arithmetic of the hooks by ONE kernel launch for all
+weights of a call (one more for the backward).
+
+    group = SpectralNormGroup(root_module)   # takes over the hooks of every SN module below root
+    group.refresh()                          # at the start of each root forward
+
+A module whose weight was not refreshed by the group since its last use (stand-alone use of a
+block) refreshes itself through the same kernel, so the per-call contract holds either way.
+"""
+import ctypes
+
+import torch
+from torch.nn.utils.spectral_norm import SpectralNorm
+
+from . import _lib as L
+
+_pp = ctypes.POINTER(ctypes.c_void_p)
+_ip = ctypes.POINTER(ctypes.c_int)
+_sp = ctypes.POINTER(ctypes.c_size_t)
+L.register('ag2v_spectral_norm_sizes', L.c_i, [L.c_i, _ip, _ip, _ip, _sp, _sp, _sp])
+L.register('ag2v_spectral_norm_fwd', L.c_i, [L.c_i, _pp, _pp, _pp, _pp, _ip, _ip, _ip, _ip, L.c_p, L.c_sz, L.c_p, L.c_sz,
+                                             L.c_i, L.c_f, L.c_p])
+L.register('ag2v_spectral_norm_bwd', L.c_i, [L.c_i, _pp, _pp, _pp, _ip, _ip, _ip, _ip, L.c_p, L.c_sz, L.c_p, L.c_sz, L.c_p])
+
+MAX_PER_LAUNCH = 48
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _int_array(values):
+    return (ctypes.c_int * len(values))(*values)
+
+
+def _geometry(ws):
+    """(co, cin, taps, channels_last) per weight; only dense NCHW / channels_last storage."""
+    co, cin, taps, cl = [], [], [], []
+    for w in ws:
+        if w.dtype != torch.float32:
+            raise RuntimeError('spectral norm: float32 weights only')
+        shape = tuple(w.shape) + (1,) * (4 - w.dim())
+        if w.is_contiguous():
+            cl.append(0)
+        elif w.dim() == 4 and w.is_contiguous(memory_format=torch.channels_last):
+            cl.append(1)
+        else:
+            raise RuntimeError('spectral norm: weight must be contiguous or channels_last, strides %s' % (w.stride(),))
+        co.append(shape[0])
+        if w.dim() == 4:
+            cin.append(shape[1])
+            taps.append(shape[2] * shape[3])
+        else:                                   # [out, in] matrices (nn.Linear)
+            cin.append(int(w.numel() // shape[0]))
+            taps.append(1)
+    return co, cin, taps, cl
+
+
+def _sizes(co, cin, taps):
+    save, fwd, bwd = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    L.check(L.lib().ag2v_spectral_norm_sizes(len(co), _int_array(co), _int_array(cin), _int_array(taps),
+                                             ctypes.byref(save), ctypes.byref(fwd), ctypes.byref(bwd)))
+    return save.value, fwd.value, bwd.value
+
+
+class _SpectralNormFn(torch.autograd.Function):
+    """(*weight_orig) -> (*weight); u / v buffers are updated in place when ``training``."""
+
+    @staticmethod
+    def forward(ctx, us, vs, training, eps, *ws):
+        L.need_cuda(*ws)
+        co, cin, taps, cl = _geometry(ws)
+        save_n, fwd_n, _ = _sizes(co, cin, taps)
+        dev = ws[0].device
+        outs = [torch.empty_like(w) for w in ws]                  # keeps the storage order of w
+        save = torch.empty(save_n, device=dev, dtype=torch.float32)
+        scratch = torch.empty(fwd_n, device=dev, dtype=torch.float32)
+        L.check(L.lib().ag2v_spectral_norm_fwd(len(ws), _ptr_array(ws), _ptr_array(outs), _ptr_array(us), _ptr_array(vs),
+                                               _int_array(co), _int_array(cin), _int_array(taps), _int_array(cl),
+                                               L.ptr(save), save_n, L.ptr(scratch), fwd_n, int(training), float(eps),
+                                               L.stream()))
+        ctx.save_for_backward(save, *ws)
+        ctx.geom = (co, cin, taps, cl)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        save, *ws = ctx.saved_tensors
+        co, cin, taps, cl = ctx.geom
+        _, _, bwd_n = _sizes(co, cin, taps)
+        fmt = lambda g, w, c: (torch.zeros_like(w) if g is None else
+                               g.float().contiguous(memory_format=torch.channels_last) if c else g.float().contiguous())
+        gs = [fmt(g, w, c) for g, w, c in zip(gs, ws, cl)]
+        dws = [torch.empty_like(w) for w in ws]
+        scratch = torch.empty(bwd_n, device=save.device, dtype=torch.float32)
+        L.check(L.lib().ag2v_spectral_norm_bwd(len(ws), _ptr_array(ws), _ptr_array(gs), _ptr_array(dws), _int_array(co),
+                                               _int_array(cin), _int_array(taps), _int_array(cl), L.ptr(save),
+                                               save.numel(), L.ptr(scratch), bwd_n, L.stream()))
+        return (None, None, None, None) + tuple(dws)
+
+
+def spectral_normalize(weights, us, vs, training=True, eps=1e-12):
+    """Normalised weights for lists of weight_orig / weight_u / weight_v (any number)."""
+    outs = []
+    for i in range(0, len(weights), MAX_PER_LAUNCH):
+        j = i + MAX_PER_LAUNCH
+        outs += _SpectralNormFn.apply(list(us[i:j]), list(vs[i:j]), training, eps, *weights[i:j])
+    return outs
+
+
+class _Entry:
+    __slots__ = ('module', 'name', 'eps', 'fresh')
+
+    def __init__(self, module, name, eps):
+        self.module, self.name, self.eps, self.fresh = module, name, eps, False
+
+    def tensors(self):
+        m, n = self.module, self.name
+        return getattr(m, n + '_orig'), getattr(m, n + '_u'), getattr(m, n + '_v')
+
+
+def _compute(entries):
+    """One launch per (training, eps) combination for the given entries."""
+    groups = {}
+    for e in entries:
+        groups.setdefault((e.module.training, e.eps), []).append(e)
+    for (training, eps), es in groups.items():
+        trip = [e.tensors() for e in es]
+        outs = spectral_normalize([t[0] for t in trip], [t[1] for t in trip], [t[2] for t in trip], training, eps)
+        for e, w in zip(es, outs):
+            setattr(e.module, e.name, w)
+            e.fresh = True
+
+
+def _make_hook(entry):
+    def hook(module, _inputs):
+        if not entry.fresh:                # nobody prepared this call's weight: do it alone
+            _compute([entry])
+        entry.fresh = False                # consumed by this call
+    return hook
+
+
+class SpectralNormGroup:
+    """Takes over torch's spectral-norm forward pre-hooks of every module under ``root``
+    (modules already taken over by another group are shared, not duplicated)."""
+
+    def __init__(self, root):
+        self.entries = []
+        for module in root.modules():
+            entry = module.__dict__.get('_ag2v_sn_entry')
+            if entry is not None:
+                self.entries.append(entry)
+                continue
+            for key, hook in list(module._forward_pre_hooks.items()):
+                if not isinstance(hook, SpectralNorm):
+                    continue
+                if hook.dim != 0 or hook.n_power_iterations != 1:
+                    raise NotImplementedError('spectral norm with dim=%d, n_power_iterations=%d'
+                                              % (hook.dim, hook.n_power_iterations))
+                del module._forward_pre_hooks[key]
+                entry = _Entry(module, hook.name, hook.eps)
+                module.register_forward_pre_hook(_make_hook(entry))
+                module.__dict__['_ag2v_sn_entry'] = entry
+                self.entries.append(entry)
+
+    def refresh(self):
+        """Compute the weight of every module for the call that is about to happen."""
+        _compute(self.entries)
+
+    def refresh_stale(self):
+        """Same, for the modules whose weight has not been prepared yet (nested use)."""
+        _compute([e for e in self.entries if not e.fresh])

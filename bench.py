@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--conv-impl', type=int, default=0, help='0 auto, 1 mma.sync, 2 tcgen05')
+    ap.add_argument('--no-cudnn-benchmark', action='store_true', help='keep cuDNN heuristics for the out-of-path convolutions')
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -173,6 +174,8 @@ def run_ours(args):
     # cannot happen on the legacy default stream
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     L.check(L.lib().ag2v_check_device())
+    # the library convolutions outside the path (cuDNN): let it pick its algorithms during warm-up
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     sp.CONV_IMPL = args.conv_impl
     if world > 1:
         sp.set_sync_bn(True)

@@ -84,6 +84,26 @@ int ag2v_layout_conv_fwd(const float* U, const void* tables, int N, int S, int C
 int ag2v_layout_conv_bwd(const float* dout, const void* tables, int N, int S, int Co, int H, int W, float* part,
                          float* dU, ag2v_stream_t stream);
 
+/* K5 — spectral normalisation of up to 48 convolution weights in ONE launch (the spectral_norm
+ * wrappers of SPADEResnetBlock, architecture.py:34-41, and of get_nonspade_norm_layer,
+ * normalization.py:16-50; arithmetic of torch/nn/utils/spectral_norm.py compute_weight).
+ * All array arguments are HOST arrays of n entries; w/out/u/v/grad entries are device pointers.
+ * Weight i is [co, cin, kh, kw] with taps = kh*kw, stored contiguous (channels_last[i] = 0) or
+ * channels_last (1).  power_iteration != 0: v <- normalize(W^T u), u <- normalize(W v) written
+ * back to u / v (training mode); else u / v are only read (eval mode).  out = W / (u . W v).
+ * `save` (sizes from ag2v_spectral_norm_sizes) receives sigma, u and v for the backward:
+ * grad_w = G / sigma - (<G,W> / sigma^2) u v^T.  Fixed-order reductions (deterministic). */
+int ag2v_spectral_norm_sizes(int n, const int* co, const int* cin, const int* taps, size_t* save_floats,
+                             size_t* fwd_scratch_floats, size_t* bwd_scratch_floats);
+int ag2v_spectral_norm_fwd(int n, const void* const* w, void* const* out, void* const* u, void* const* v,
+                           const int* co, const int* cin, const int* taps, const int* channels_last, float* save,
+                           size_t save_floats, float* scratch, size_t scratch_floats, int power_iteration, float eps,
+                           ag2v_stream_t stream);
+int ag2v_spectral_norm_bwd(int n, const void* const* w, const void* const* grad_out, void* const* grad_w,
+                           const int* co, const int* cin, const int* taps, const int* channels_last,
+                           const float* save, size_t save_floats, float* scratch, size_t scratch_floats,
+                           ag2v_stream_t stream);
+
 /* masks_to_layout (models/layout.py:66-95, _pool_mask_samples :164-202) for one
  * (clip, frame): vecs [O,D], boxes [O,4] xywh, masks [O,M,M]; S [O,H,W] receives the
  * sampled masks (kept for the backward); test_mode != 0 composites objects in
