@@ -34,6 +34,7 @@ struct ConvParams {
   float* out; long long out_sb, out_sy, out_sx;   // output view [B, Hh, Ww, Nout]
   // EPI_SPADE: Nout == 2*C in gb8 order; out is [.., C]
   const float* x; const float* mean; const float* rstd; float* gamma_out; float slope; int C;
+  long long group_pixels;    // > 0: mean/rstd are [groups][C], group = pixel index / group_pixels
   // EPI_GATE
   const float* gate;
   // split-K workspace (caller-provided, may be null): ksplit * P * Nout floats

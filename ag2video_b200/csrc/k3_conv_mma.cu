@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(kConvThreads, PRECISE ? 1 : 2) conv3x3_mma_ker
           if (p.bias) { g0 += p.bias[ng]; g1 += p.bias[ng + 1]; b0 += p.bias[ng + 8]; b1 += p.bias[ng + 9]; }
           const size_t off = (size_t)pp * p.C + c;
           const float2 xv = *reinterpret_cast<const float2*>(p.x + off);
-          const float2 mu = *reinterpret_cast<const float2*>(p.mean + c);
-          const float2 rs = *reinterpret_cast<const float2*>(p.rstd + c);
+          const size_t sc = (p.group_pixels > 0 ? (size_t)(pp / p.group_pixels) * p.C : 0) + c;
+          const float2 mu = *reinterpret_cast<const float2*>(p.mean + sc);
+          const float2 rs = *reinterpret_cast<const float2*>(p.rstd + sc);
           float o0 = (xv.x - mu.x) * rs.x * (1.f + g0) + b0;
           float o1 = (xv.y - mu.y) * rs.y * (1.f + g1) + b1;
           if (p.slope != 1.f) { o0 = o0 > 0.f ? o0 : o0 * p.slope; o1 = o1 > 0.f ? o1 : o1 * p.slope; }

@@ -55,12 +55,13 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float (&v)[3
   if (EPI == EPI_SPADE) {
     const int c = n >> 1;                                           // 16 channels: [g8 | b8 | g8 | b8]
     const size_t off = (size_t)pp * p.C + c;
+    const size_t sc = (p.group_pixels > 0 ? (size_t)(pp / p.group_pixels) * p.C : 0) + c;
     float xs[16], mu[16], rs[16], o[16], gm_[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       *reinterpret_cast<float4*>(xs + 4 * i) = *reinterpret_cast<const float4*>(p.x + off + 4 * i);
-      *reinterpret_cast<float4*>(mu + 4 * i) = *reinterpret_cast<const float4*>(p.mean + c + 4 * i);
-      *reinterpret_cast<float4*>(rs + 4 * i) = *reinterpret_cast<const float4*>(p.rstd + c + 4 * i);
+      *reinterpret_cast<float4*>(mu + 4 * i) = *reinterpret_cast<const float4*>(p.mean + sc + 4 * i);
+      *reinterpret_cast<float4*>(rs + 4 * i) = *reinterpret_cast<const float4*>(p.rstd + sc + 4 * i);
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {

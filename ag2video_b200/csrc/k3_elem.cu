@@ -38,7 +38,11 @@ struct ChanArgs {
   // MODE 1
   const float* dout; const float* out; const float* gamma; const float* mean; const float* rstd;
   float* dgb; float* dxhat; float slope; int act; int round_ops;
+  int chan_gamma;                   // MODE 1: gamma is a per-channel scale w[c] (affine batch norm) instead of per-pixel 1+gamma
 };
+// Groups: blockIdx.y selects one of G independent pixel ranges of P rows each (the frames of a
+// clip batched into one call keep per-call batch statistics); every per-group array
+// (x .. dxhat, mean/rstd, part, sums) is laid out group-major.
 
 template <int MODE>
 __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, ChanGeom gm) {
@@ -46,6 +50,17 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
   __shared__ float4 red[kElemThreads];
   const int tx = threadIdx.x % gm.cx, ty = threadIdx.x / gm.cx;
   const int C = a.C, c4n = C >> 2;
+  {                                                     // this group's slices
+    const size_t go = (size_t)blockIdx.y * a.P * C;
+    a.x += go;
+    a.part += (size_t)blockIdx.y * gm.nsplit * NS * C;
+    if (MODE == 1) {
+      a.dout += go; a.out += go; a.dxhat += go;
+      if (!a.chan_gamma) a.gamma += go;
+      if (a.dgb) a.dgb += 2 * go;
+      a.mean += (size_t)blockIdx.y * C; a.rstd += (size_t)blockIdx.y * C;
+    }
+  }
   for (int chunk = 0; chunk < gm.chunks; ++chunk) {
     const int c4 = chunk * gm.cx + tx;
     const bool live = c4 < c4n;
@@ -66,7 +81,8 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
         } else {
           const float4 dv = *reinterpret_cast<const float4*>(a.dout + off);
           const float4 ov = *reinterpret_cast<const float4*>(a.out + off);
-          const float4 gv = *reinterpret_cast<const float4*>(a.gamma + off);
+          float4 gv = *reinterpret_cast<const float4*>(a.gamma + (a.chan_gamma ? (size_t)c : off));
+          if (!a.chan_gamma) { gv.x += 1.f; gv.y += 1.f; gv.z += 1.f; gv.w += 1.f; }
           float4 g, xh, dxh;
           const float sl = a.slope;
           g.x = (a.act && !(ov.x > 0.f)) ? dv.x * sl : dv.x;
@@ -76,11 +92,12 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
           xh.x = (xv.x - mu.x) * rs.x; xh.y = (xv.y - mu.y) * rs.y;
           xh.z = (xv.z - mu.z) * rs.z; xh.w = (xv.w - mu.w) * rs.w;
           const float4 dgam = make_float4(g.x * xh.x, g.y * xh.y, g.z * xh.z, g.w * xh.w);
-          dxh.x = g.x * (1.f + gv.x); dxh.y = g.y * (1.f + gv.y);
-          dxh.z = g.z * (1.f + gv.z); dxh.w = g.w * (1.f + gv.w);
+          dxh.x = g.x * gv.x; dxh.y = g.y * gv.y;
+          dxh.z = g.z * gv.z; dxh.w = g.w * gv.w;
           float* row = a.dgb + (size_t)p * 2 * C;
           // the GEMM operand copies are rounded to TF32; the sums below use the fp32 values
-          if (a.round_ops) {
+          if (a.dgb == nullptr) {
+          } else if (a.round_ops) {
             *reinterpret_cast<float4*>(row + gb8_col(c, 0)) = make_float4(elem_round_tf32(dgam.x), elem_round_tf32(dgam.y), elem_round_tf32(dgam.z), elem_round_tf32(dgam.w));
             *reinterpret_cast<float4*>(row + gb8_col(c, 1)) = make_float4(elem_round_tf32(g.x), elem_round_tf32(g.y), elem_round_tf32(g.z), elem_round_tf32(g.w));
           } else {
@@ -120,6 +137,8 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const float* __restric
   __shared__ double red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
+  part += (size_t)blockIdx.y * nsplit * NSC;
+  sums += (size_t)blockIdx.y * NSC;
   double acc = 0.0;
   if (col < NSC) {
     int s = ty;
@@ -142,20 +161,24 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const float* __restric
 
 // F.batch_norm(training=True, momentum, eps): biased variance for normalisation,
 // unbiased for the running estimate (sync_batchnorm/batchnorm.py:63-68,128-145).
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, float eps, float momentum,
+// With G groups the running estimates are updated G times in group order, exactly as G
+// successive calls of the layer would.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, int G, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean, float* __restrict__ rstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = sums[c] / count;
-  double var = sums[C + c] / count - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[c] = (float)m;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean != nullptr) {
-    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
-    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+  for (int g = 0; g < G; ++g) {
+    const double m = sums[(size_t)g * 2 * C + c] / count;
+    double var = sums[(size_t)g * 2 * C + C + c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[(size_t)g * C + c] = (float)m;
+    rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
+      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    }
   }
 }
 
@@ -175,6 +198,8 @@ spade_bwd_dx_kernel(const float* __restrict__ x, float* __restrict__ dxhat, cons
                     const float* __restrict__ rstd, const double* __restrict__ sums, double count, int training,
                     long long P, int C) {
   const long long n4 = P * (C >> 2);
+  x += (size_t)blockIdx.y * P * C; dxhat += (size_t)blockIdx.y * P * C;
+  mean += (size_t)blockIdx.y * C; rstd += (size_t)blockIdx.y * C; sums += (size_t)blockIdx.y * 4 * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % (C >> 2)) << 2;
     const float4 xv = reinterpret_cast<const float4*>(x)[i];
@@ -260,9 +285,41 @@ __global__ void round_tf32_kernel(const float4* __restrict__ src, float4* __rest
   }
 }
 
-__global__ void double_to_float_kernel(const double* __restrict__ src, int n, float* __restrict__ dst) {
+// dst[i] = sum over groups of src[g * gstride + i]
+__global__ void double_to_float_kernel(const double* __restrict__ src, int n, int groups, long long gstride,
+                                       float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = (float)src[i];
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int g = 0; g < groups; ++g) acc += src[(size_t)g * gstride + i];
+  dst[i] = (float)acc;
+}
+
+// Affine batch norm + LeakyReLU (the conv -> SyncBN -> LeakyReLU(0.2) stages of the flow network and
+// of conv_dim_in, normalization.py:16-50 / flows_generator.py):  y = act((x - mean_g) * rstd_g * w + b)
+__global__ void __launch_bounds__(kElemThreads)
+bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const float* __restrict__ weight, const float* __restrict__ bias, long long P, int C, float slope,
+                  float* __restrict__ y) {
+  const long long n4 = P * (C >> 2);
+  x += (size_t)blockIdx.y * P * C; y += (size_t)blockIdx.y * P * C;
+  mean += (size_t)blockIdx.y * C; rstd += (size_t)blockIdx.y * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (C >> 2)) << 2;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 w = *reinterpret_cast<const float4*>(weight + c);
+    const float4 b = *reinterpret_cast<const float4*>(bias + c);
+    float4 o;
+    o.x = (xv.x - mu.x) * rs.x * w.x + b.x; o.y = (xv.y - mu.y) * rs.y * w.y + b.y;
+    o.z = (xv.z - mu.z) * rs.z * w.z + b.z; o.w = (xv.w - mu.w) * rs.w * w.w + b.w;
+    if (slope != 1.f) {
+      o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+      o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+    }
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
 }
 
 }  // namespace ag2v
@@ -282,26 +339,29 @@ extern "C" size_t ag2v_chan_partial_floats(long long P, int C, int NS) {
 }
 
 // sums[0..C) = sum x, sums[C..2C) = sum x^2 over the P rows of x [P, C] (doubles).
-extern "C" int ag2v_bn_stats(const float* x, long long P, int C, float* partial, double* sums, cudaStream_t stream) {
+// x is [groups][P][C]; partial holds groups * ag2v_chan_partial_floats(P, C, 2) floats, sums [groups][2C].
+extern "C" int ag2v_bn_stats(const float* x, long long P, int C, int groups, float* partial, double* sums,
+                             cudaStream_t stream) {
   int rc = chan_check(P, C);
   if (rc) return rc;
-  AG2V_REQUIRE(x && partial && sums, "bn_stats: null pointer");
+  AG2V_REQUIRE(x && partial && sums && groups >= 1 && groups <= 65535, "bn_stats: null pointer or bad group count");
   ChanGeom g = chan_geom(P, C);
   ChanArgs a{};
   a.x = x; a.P = P; a.C = C; a.part = partial;
-  chan_partial_kernel<0><<<g.nsplit, kElemThreads, 0, stream>>>(a, g);
+  chan_partial_kernel<0><<<dim3(g.nsplit, groups), kElemThreads, 0, stream>>>(a, g);
   AG2V_LAUNCH_CHECK();
-  chan_reduce_kernel<<<ceil_div(2 * C, 32), 256, 0, stream>>>(partial, g.nsplit, 2 * C, sums);
+  chan_reduce_kernel<<<dim3(ceil_div(2 * C, 32), groups), 256, 0, stream>>>(partial, g.nsplit, 2 * C, sums);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
 
 // mean/rstd from (possibly all-reduced) sums; updates running stats when given.
-extern "C" int ag2v_bn_finalize(const double* sums, double count, int C, float eps, float momentum,
+// sums [groups][2C] -> mean / rstd [groups][C]; count = elements per channel in ONE group.
+extern "C" int ag2v_bn_finalize(const double* sums, double count, int C, int groups, float eps, float momentum,
                                 float* running_mean, float* running_var, float* mean, float* rstd,
                                 cudaStream_t stream) {
-  AG2V_REQUIRE(sums && mean && rstd && C > 0 && count > 0, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(sums, count, C, eps, momentum, running_mean, running_var, mean, rstd);
+  AG2V_REQUIRE(sums && mean && rstd && C > 0 && count > 0 && groups >= 1, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(sums, count, C, groups, eps, momentum, running_mean, running_var, mean, rstd);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
@@ -319,20 +379,23 @@ extern "C" int ag2v_bn_eval_stats(const float* running_mean, const float* runnin
 // (gb8 columns: d gamma = g*xhat, d beta = g), dxhat [P, C] and the four
 // per-channel sums (doubles, [4][C]): sum g, sum g*xhat, sum dxhat, sum dxhat*xhat.
 extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma,
-                                  const float* mean, const float* rstd, long long P, int C, int act,
-                                  float slope, int round_ops, float* dgb, float* dxhat, float* partial,
-                                  double* sums, cudaStream_t stream) {
+                                  const float* mean, const float* rstd, long long P, int C, int groups, int act,
+                                  float slope, int round_ops, int chan_gamma, float* dgb, float* dxhat,
+                                  float* partial, double* sums, cudaStream_t stream) {
   int rc = chan_check(P, C);
   if (rc) return rc;
-  AG2V_REQUIRE(C % 8 == 0, "spade_bwd_pre: C %% 8 == 0 required (C=%d)", C);
-  AG2V_REQUIRE(dout && out && x && gamma && mean && rstd && dgb && dxhat && partial && sums, "spade_bwd_pre: null pointer");
+  AG2V_REQUIRE(dgb == nullptr || C % 8 == 0, "spade_bwd_pre: C %% 8 == 0 required (C=%d)", C);
+  AG2V_REQUIRE(dout && out && x && gamma && mean && rstd && dxhat && partial && sums && (dgb || chan_gamma),
+               "spade_bwd_pre: null pointer");
+  AG2V_REQUIRE(groups >= 1 && groups <= 65535, "spade_bwd_pre: bad group count %d", groups);
   ChanGeom g = chan_geom(P, C);
   ChanArgs a{};
   a.x = x; a.P = P; a.C = C; a.part = partial; a.dout = dout; a.out = out; a.gamma = gamma;
   a.mean = mean; a.rstd = rstd; a.dgb = dgb; a.dxhat = dxhat; a.slope = slope; a.act = act; a.round_ops = round_ops;
-  chan_partial_kernel<1><<<g.nsplit, kElemThreads, 0, stream>>>(a, g);
+  a.chan_gamma = chan_gamma;
+  chan_partial_kernel<1><<<dim3(g.nsplit, groups), kElemThreads, 0, stream>>>(a, g);
   AG2V_LAUNCH_CHECK();
-  chan_reduce_kernel<<<ceil_div(4 * C, 32), 256, 0, stream>>>(partial, g.nsplit, 4 * C, sums);
+  chan_reduce_kernel<<<dim3(ceil_div(4 * C, 32), groups), 256, 0, stream>>>(partial, g.nsplit, 4 * C, sums);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
@@ -340,15 +403,16 @@ extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const flo
 // SPADE backward pass 2: dxhat -> dx in place (sums as produced by spade_bwd_pre,
 // all-reduced across ranks by the caller under SyncBN; count = global element count).
 extern "C" int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean, const float* rstd,
-                                 const double* sums, double count, int training, long long P, int C,
+                                 const double* sums, double count, int training, long long P, int C, int groups,
                                  cudaStream_t stream) {
   int rc = chan_check(P, C);
   if (rc) return rc;
-  AG2V_REQUIRE(x && dxhat && mean && rstd && sums, "spade_bwd_dx: null pointer");
+  AG2V_REQUIRE(x && dxhat && mean && rstd && sums && groups >= 1 && groups <= 65535, "spade_bwd_dx: bad arguments");
   long long n4 = P * (C / 4);
-  int blocks = (int)(ceil_div_ll(n4, kElemThreads * 4) > 4 * 148 * 8 ? 4 * 148 * 8 : ceil_div_ll(n4, kElemThreads * 4));
+  const long long cap = 4 * 148 * 8 / groups + 1;
+  int blocks = (int)(ceil_div_ll(n4, kElemThreads * 4) > cap ? cap : ceil_div_ll(n4, kElemThreads * 4));
   if (blocks < 1) blocks = 1;
-  spade_bwd_dx_kernel<<<blocks, kElemThreads, 0, stream>>>(x, dxhat, mean, rstd, sums, count, training, P, C);
+  spade_bwd_dx_kernel<<<dim3(blocks, groups), kElemThreads, 0, stream>>>(x, dxhat, mean, rstd, sums, count, training, P, C);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
@@ -386,9 +450,27 @@ extern "C" int ag2v_round_tf32(const float* src, float* dst, long long n, cudaSt
   return AG2V_OK;
 }
 
-extern "C" int ag2v_double_to_float(const double* src, int n, float* dst, cudaStream_t stream) {
-  AG2V_REQUIRE(src && dst && n > 0, "double_to_float: bad arguments");
-  double_to_float_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(src, n, dst);
+// dst[i] = (float) sum_g src[g * group_stride + i], i < n
+extern "C" int ag2v_double_to_float(const double* src, int n, int groups, long long group_stride, float* dst,
+                                    cudaStream_t stream) {
+  AG2V_REQUIRE(src && dst && n > 0 && groups >= 1, "double_to_float: bad arguments");
+  double_to_float_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(src, n, groups, group_stride, dst);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// y = act((x - mean_g) * rstd_g * weight + bias) on [groups][P][C] (NHWC), slope 1 = no activation
+extern "C" int ag2v_bn_act_fwd(const float* x, const float* mean, const float* rstd, const float* weight,
+                               const float* bias, long long P, int C, int groups, float slope, float* y,
+                               cudaStream_t stream) {
+  int rc = chan_check(P, C);
+  if (rc) return rc;
+  AG2V_REQUIRE(x && mean && rstd && weight && bias && y && groups >= 1 && groups <= 65535, "bn_act_fwd: bad arguments");
+  long long n4 = P * (C / 4);
+  const long long cap = 4 * 148 * 8 / groups + 1;
+  int blocks = (int)(ceil_div_ll(n4, kElemThreads * 4) > cap ? cap : ceil_div_ll(n4, kElemThreads * 4));
+  if (blocks < 1) blocks = 1;
+  bn_act_fwd_kernel<<<dim3(blocks, groups), kElemThreads, 0, stream>>>(x, mean, rstd, weight, bias, P, C, slope, y);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

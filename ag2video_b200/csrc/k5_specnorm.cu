@@ -54,6 +54,11 @@ struct SnParams {
   float* partial; // backward: [itemC[n]] partial <G, W>
   int power_iter;
   float eps;
+  // sigma mode (frames of a clip batched into one call): `iters` successive power iterations, one
+  // per frame group, each saving its sigma / u / v; no normalised weight is written — the caller
+  // applies 1/sigma_g to the convolution output of group g instead.
+  int iters, sigma_only;
+  long long it_sigma, it_u, it_v;   // per-iteration strides of sigma / usave / vphys
 };
 
 __device__ __forceinline__ int sn_find(const int* prefix, int n, int item) {
@@ -81,6 +86,10 @@ __global__ void __launch_bounds__(kSnThreads, 1) specnorm_fwd_kernel(const __gri
   const int gwarp = blockIdx.x * kSnWarps + warp, nwarps = gridDim.x * kSnWarps;
   __shared__ float s_sigma;
 
+  for (int it = 0; it < P.iters; ++it) {
+  float* const vphys = P.vphys + it * P.it_v;
+  float* const usave = P.usave + it * P.it_u;
+  float* const sigma_it = P.sigma + it * P.it_sigma;
   // ---- phase A: t = W^T u (physical column order); lane = column, 32 columns per warp item
   for (int item = gwarp; item < P.itemA[P.n]; item += nwarps) {
     const int ti = sn_find(P.itemA, P.n, item);
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(kSnThreads, 1) specnorm_fwd_kernel(const __gri
       } else {
         acc = T.v[sn_logical(T, p)];
       }
-      P.vphys[T.koff + p] = acc;
+      vphys[T.koff + p] = acc;
     }
     const float sq = warp_sum(p < K ? acc * acc : 0.f);
     if (lane == 0) P.tsq[item] = sq;
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(kSnThreads, 1) specnorm_fwd_kernel(const __gri
     const SnTensor& T = P.t[ti];
     const int K = T.cin * T.taps, r = row - T.roff;
     const float* w = T.w + (size_t)r * K;
-    const float* t = P.vphys + T.koff;
+    const float* t = vphys + T.koff;
     float acc = 0.f;
     int p = lane;
     if ((K & 3) == 0 && (T.koff & 3) == 0) {          // rows and the packed vector are 16-byte aligned
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__(kSnThreads, 1) specnorm_fwd_kernel(const __gri
         for (int r = lane; r < T.co; r += 32) {
           const float s = sr[r] / tn, un_r = s / un;
           d = fmaf(un_r, s, d);
-          P.usave[T.roff + r] = un_r;
+          usave[T.roff + r] = un_r;
           T.u[r] = un_r;
         }
         sigma = warp_sum(d);
@@ -184,23 +193,26 @@ __global__ void __launch_bounds__(kSnThreads, 1) specnorm_fwd_kernel(const __gri
         for (int r = lane; r < T.co; r += 32) {
           const float ur = T.u[r];
           d = fmaf(ur, sr[r], d);
-          P.usave[T.roff + r] = ur;
+          usave[T.roff + r] = ur;
         }
         sigma = warp_sum(d);
       }
-      if (lane == 0) { s_sigma = tn; P.sigma[ti] = sigma; }
+      if (lane == 0) { s_sigma = tn; sigma_it[ti] = sigma; }
     }
     __syncthreads();
     if (P.power_iter) {                        // normalised v: saved (physical) and module buffer (logical)
       const float tn = s_sigma;
       for (int p = threadIdx.x; p < K; p += kSnThreads) {
-        const float vn = P.vphys[T.koff + p] / tn;
-        P.vphys[T.koff + p] = vn;
+        const float vn = vphys[T.koff + p] / tn;
+        vphys[T.koff + p] = vn;
         T.v[sn_logical(T, p)] = vn;
       }
     }
   }
   grid.sync();
+
+  }   // iterations
+  if (P.sigma_only) return;
 
   // ---- phase C: out = W / sigma; one CTA per 16K-element chunk
   for (int item = blockIdx.x; item < P.itemC[P.n]; item += gridDim.x) {
@@ -316,20 +328,58 @@ __global__ void __launch_bounds__(kSnThreads, 1) specnorm_bwd_kernel(const __gri
   }
 }
 
+// sigma mode backward: dW = sum_it dsigma[it] u_it v_it^T  (the direct path G/sigma reaches
+// weight_orig through the convolution itself, which runs on the unnormalised weight)
+__global__ void __launch_bounds__(kSnThreads) specnorm_sigma_bwd_kernel(const __grid_constant__ SnParams P,
+                                                                        const float* __restrict__ dsigma) {
+  for (int item = blockIdx.x; item < P.itemC[P.n]; item += gridDim.x) {
+    const int ti = sn_find(P.itemC, P.n, item);
+    const SnTensor& T = P.t[ti];
+    const int K = T.cin * T.taps;
+    const long long total = (long long)T.co * K;
+    const long long i0 = (long long)(item - P.itemC[ti]) * kSnChunk;
+    const long long i1 = i0 + kSnChunk < total ? i0 + kSnChunk : total;
+    if ((K & 3) == 0) {
+      for (long long i = i0 + 4 * threadIdx.x; i < i1; i += 4 * kSnThreads) {
+        const int r = (int)(i / K), p = (int)(i - (long long)r * K);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < P.iters; ++it) {
+          const float cu = dsigma[it * P.n + ti] * P.usave[it * P.it_u + T.roff + r];
+          const float4 v4 = *reinterpret_cast<const float4*>(P.vphys + it * P.it_v + T.koff + p);
+          o.x = fmaf(cu, v4.x, o.x); o.y = fmaf(cu, v4.y, o.y); o.z = fmaf(cu, v4.z, o.z); o.w = fmaf(cu, v4.w, o.w);
+        }
+        *reinterpret_cast<float4*>(T.out + i) = o;
+      }
+    } else {
+      for (long long i = i0 + threadIdx.x; i < i1; i += kSnThreads) {
+        const int r = (int)(i / K), p = (int)(i - (long long)r * K);
+        float o = 0.f;
+        for (int it = 0; it < P.iters; ++it)
+          o = fmaf(dsigma[it * P.n + ti] * P.usave[it * P.it_u + T.roff + r], P.vphys[it * P.it_v + T.koff + p], o);
+        T.out[i] = o;
+      }
+    }
+  }
+}
+
 static int fill_params(SnParams& P, int n, const void* const* w, void* const* out, const void* const* g,
                        void* const* u, void* const* v, const int* co, const int* cin, const int* taps,
                        const int* cl, float* save, size_t save_floats, float* scratch, size_t scratch_floats,
-                       bool backward) {
+                       bool backward, int iters = 1, bool sigma_only = false) {
   AG2V_REQUIRE(n >= 1 && n <= kSnMax, "spectral norm: n=%d outside [1,%d]", n, kSnMax);
+  AG2V_REQUIRE(iters >= 1 && iters <= 64, "spectral norm: iters=%d outside [1,64]", iters);
   int koff = 0, roff = 0;
   P.itemA[0] = 0; P.itemC[0] = 0;
   for (int i = 0; i < n; ++i) {
-    AG2V_REQUIRE(w[i] && out[i] && co[i] > 0 && cin[i] > 0 && taps[i] > 0, "spectral norm: bad weight %d", i);
-    AG2V_REQUIRE(((uintptr_t)w[i] & 15) == 0 && ((uintptr_t)out[i] & 15) == 0, "spectral norm: weight %d not 16-byte aligned", i);
+    const bool need_w = !(sigma_only && backward), need_out = !(sigma_only && !backward);
+    AG2V_REQUIRE((!need_w || w[i]) && (!need_out || out[i]) && co[i] > 0 && cin[i] > 0 && taps[i] > 0,
+                 "spectral norm: bad weight %d", i);
+    AG2V_REQUIRE((!need_w || ((uintptr_t)w[i] & 15) == 0) && (!need_out || ((uintptr_t)out[i] & 15) == 0),
+                 "spectral norm: weight %d not 16-byte aligned", i);
     SnTensor& T = P.t[i];
-    T.w = (const float*)w[i]; T.out = (float*)out[i];
-    T.g = backward ? (const float*)g[i] : nullptr;
-    if (backward) AG2V_REQUIRE(g[i] && ((uintptr_t)g[i] & 15) == 0, "spectral norm: gradient %d null or misaligned", i);
+    T.w = need_w ? (const float*)w[i] : nullptr; T.out = need_out ? (float*)out[i] : nullptr;
+    T.g = backward && !sigma_only ? (const float*)g[i] : nullptr;
+    if (backward && !sigma_only) AG2V_REQUIRE(g[i] && ((uintptr_t)g[i] & 15) == 0, "spectral norm: gradient %d null or misaligned", i);
     T.u = backward ? nullptr : (float*)u[i];
     T.v = backward ? nullptr : (float*)v[i];
     if (!backward) AG2V_REQUIRE(u[i] && v[i], "spectral norm: u/v of weight %d is null", i);
@@ -342,13 +392,16 @@ static int fill_params(SnParams& P, int n, const void* const* w, void* const* ou
   }
   for (int i = n; i < kSnMax; ++i) { P.t[i] = P.t[n - 1]; P.itemA[i + 1] = P.itemA[n]; P.itemC[i + 1] = P.itemC[n]; }
   P.n = n; P.rows = roff;
-  // saved: sigma[n] | usave[rows] | vphys[sum K], each section padded to a multiple of 4 floats
+  // saved: sigma[iters][n] | usave[iters][rows] | vphys[iters][sum K], rows padded to multiples of 4 floats
   const int n4 = (n + 3) & ~3, r4 = (roff + 3) & ~3;
-  AG2V_REQUIRE(save && ((uintptr_t)save & 15) == 0 && save_floats >= (size_t)n4 + r4 + koff,
-               "spectral norm: saved buffer too small or misaligned (%zu < %zu)", save_floats, (size_t)n4 + r4 + koff);
-  P.sigma = save; P.usave = save + n4; P.vphys = save + n4 + r4;
-  const size_t need = backward ? (size_t)P.itemC[n] + n : (size_t)roff + P.itemA[n];
-  AG2V_REQUIRE(scratch && scratch_floats >= need, "spectral norm: scratch too small (%zu < %zu)", scratch_floats, need);
+  const size_t save_need = (size_t)iters * ((size_t)n4 + r4 + koff);
+  AG2V_REQUIRE(save && ((uintptr_t)save & 15) == 0 && save_floats >= save_need,
+               "spectral norm: saved buffer too small or misaligned (%zu < %zu)", save_floats, save_need);
+  P.sigma = save; P.usave = save + (size_t)iters * n4; P.vphys = save + (size_t)iters * (n4 + r4);
+  P.iters = iters; P.sigma_only = sigma_only ? 1 : 0;
+  P.it_sigma = n4; P.it_u = r4; P.it_v = koff;
+  const size_t need = backward ? (sigma_only ? 0 : (size_t)P.itemC[n] + n) : (size_t)roff + P.itemA[n];
+  AG2V_REQUIRE(need == 0 || (scratch && scratch_floats >= need), "spectral norm: scratch too small (%zu < %zu)", scratch_floats, need);
   P.sraw = scratch; P.tsq = scratch + roff; P.partial = scratch;
   return AG2V_OK;
 }
@@ -398,5 +451,39 @@ extern "C" int ag2v_spectral_norm_bwd(int n, const void* const* w, const void* c
   P.eps = 0.f;
   void* args[] = {&P};
   AG2V_COOP_LAUNCH(specnorm_bwd_kernel, dim3(sm_count()), dim3(kSnThreads), args, 0, stream);
+  return AG2V_OK;
+}
+
+// Sigma mode: `iters` successive power iterations (one per frame group of a batched call); writes
+// no weight.  save (iters * ag2v_spectral_norm_sizes floats) starts with sigma [iters][(n+3)&~3].
+extern "C" int ag2v_spectral_norm_sigma_fwd(int n, const void* const* w, void* const* u, void* const* v, const int* co,
+                                            const int* cin, const int* taps, const int* channels_last, int iters,
+                                            float* save, size_t save_floats, float* scratch, size_t scratch_floats,
+                                            int power_iteration, float eps, cudaStream_t stream) {
+  if (int rc = check_arch()) return rc;
+  SnParams P;
+  if (int rc = fill_params(P, n, w, nullptr, nullptr, u, v, co, cin, taps, channels_last, save, save_floats, scratch,
+                           scratch_floats, false, iters, true)) return rc;
+  P.power_iter = power_iteration ? 1 : 0;
+  P.eps = eps;
+  void* args[] = {&P};
+  AG2V_COOP_LAUNCH(specnorm_fwd_kernel, dim3(sm_count()), dim3(kSnThreads), args, 0, stream);
+  return AG2V_OK;
+}
+
+// grad_w[i] = sum_it dsigma[it][i] * u_it v_it^T  (dsigma: device array [iters][n])
+extern "C" int ag2v_spectral_norm_sigma_bwd(int n, const float* dsigma, void* const* grad_w, const int* co,
+                                            const int* cin, const int* taps, const int* channels_last, int iters,
+                                            const float* save, size_t save_floats, cudaStream_t stream) {
+  if (int rc = check_arch()) return rc;
+  AG2V_REQUIRE(dsigma, "spectral norm: dsigma is null");
+  SnParams P;
+  if (int rc = fill_params(P, n, nullptr, grad_w, nullptr, nullptr, nullptr, co, cin, taps, channels_last,
+                           const_cast<float*>(save), save_floats, nullptr, 0, true, iters, true)) return rc;
+  P.power_iter = 0;
+  P.eps = 0.f;
+  const int items = P.itemC[n];
+  specnorm_sigma_bwd_kernel<<<items < 4 * sm_count() ? items : 4 * sm_count(), kSnThreads, 0, stream>>>(P, dsigma);
+  AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

@@ -21,8 +21,8 @@ from torch.nn.utils import spectral_norm
 
 from .graph import GraphTripleConv
 from .layout import boxes_to_layout_batched, layout_conv3x3, layout_tables
-from .spade import SPADEResnetBlock, SharedSeg
-from .specnorm import SpectralNormGroup
+from .spade import SPADEResnetBlock, SharedSeg, bn_act
+from .specnorm import SpectralNormGroup, conv_scaled
 
 CL = torch.channels_last
 
@@ -109,8 +109,9 @@ class Acts2LayoutModel(nn.Module):
 
 
 class _BN2d(nn.Module):
-    """SynchronizedBatchNorm2d(affine=True) on one device = F.batch_norm
-    (sync_batchnorm/batchnorm.py:63-68); cuDNN, outside the hot-path scope."""
+    """SynchronizedBatchNorm2d(affine=True) (sync_batchnorm/batchnorm.py:63-68) with the
+    LeakyReLU that follows it in every use folded in (``slope``); ``groups`` as in SPADE.forward.
+    Statistics / normalisation / backward run on the K3 element-wise kernels (spade.bn_act)."""
 
     def __init__(self, c):
         super().__init__()
@@ -120,8 +121,9 @@ class _BN2d(nn.Module):
         self.register_buffer('running_var', torch.ones(c))
         self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
 
-    def forward(self, x):
-        return F.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training, 0.1, 1e-5)
+    def forward(self, x, groups=1, slope=1.0):
+        return bn_act(x, self.weight, self.bias, self.running_mean, self.running_var, self.training, 0.1, 1e-5,
+                      slope=slope, groups=groups)
 
 
 def _sn_conv_bn(cin, cout, stride=1):
@@ -135,9 +137,9 @@ class _FlowResBlock(nn.Module):
         self.conv_1 = spectral_norm(nn.Conv2d(c, c, 3, padding=1))
         self.bn_0, self.bn_1 = _BN2d(c), _BN2d(c)
 
-    def forward(self, x):
-        dx = self.conv_0(F.leaky_relu(self.bn_0(x), 0.2))
-        return x + self.conv_1(F.leaky_relu(self.bn_1(dx), 0.2))
+    def forward(self, x, groups=1):
+        dx = conv_scaled(self.conv_0, self.bn_0(x, groups, 0.2))
+        return x + conv_scaled(self.conv_1, self.bn_1(dx, groups, 0.2))
 
 
 class FlowsGenerator(nn.Module):
@@ -160,9 +162,28 @@ class FlowsGenerator(nn.Module):
         self.conv_w = nn.Sequential(nn.Conv2d(nf, 1, 3, padding=1), nn.Sigmoid())
         self.__dict__['_sn'] = SpectralNormGroup(self)
 
-    def forward(self, label):
-        self._sn.refresh_stale()
-        feat = self.up_flow(self.res_flow(self.down_flow(label)))
+    @staticmethod
+    def _stage(conv_bn, x, groups, first=None):
+        """conv -> BN -> LeakyReLU(0.2); ``first`` = the convolution's output computed elsewhere."""
+        z = conv_scaled(conv_bn[0], x) if first is None else first
+        return conv_bn[1](z, groups, 0.2)
+
+    def features(self, label, groups=1, first=None):
+        """up_flow(res_flow(down_flow(label))).  ``first``: output of down_flow[0]'s convolution when
+        the caller evaluated it itself (the fused layout convolution)."""
+        x = self._stage(self.down_flow[0], label, groups, first)
+        for i in range(2, len(self.down_flow), 2):
+            x = self._stage(self.down_flow[i], x, groups)
+        for block in self.res_flow:
+            x = block(x, groups)
+        for i in range(0, len(self.up_flow), 3):
+            x = self._stage(self.up_flow[i + 1], self.up_flow[i](x), groups)
+        return x
+
+    def forward(self, label, groups=1):
+        if groups == 1:
+            self._sn.refresh_stale()
+        feat = self.features(label, groups)
         return self.conv_w(feat), self.conv_flow(feat) * self.flow_multiplier
 
 
@@ -184,15 +205,15 @@ class SPADEGenerator(nn.Module):
         self.up_3 = SPADEResnetBlock(2 * nf, nf, opt)
         self.conv_img = nn.Conv2d(nf, 3, 3, padding=1)
 
-    def forward(self, layout):
+    def forward(self, layout, groups=1):
         seg = SharedSeg.wrap(layout)                       # one NHWC copy + one gradient buffer for all 18 SPADEs
         up = lambda z: F.interpolate(z, scale_factor=2, mode='nearest')
         x = self.fc(F.interpolate(layout, size=(self.sh, self.sw)))
-        x = self.head_0(x, seg)
-        x = self.G_middle_0(up(x), seg)
-        x = self.G_middle_1(x, seg)
+        x = self.head_0(x, seg, groups)
+        x = self.G_middle_0(up(x), seg, groups)
+        x = self.G_middle_1(x, seg, groups)
         for name in ('up_0', 'up_1', 'up_2', 'up_3'):
-            x = getattr(self, name)(up(x), seg)
+            x = getattr(self, name)(up(x), seg, groups)
         return torch.tanh(self.conv_img(F.leaky_relu(x, 0.2)))
 
 
@@ -244,55 +265,81 @@ class Layout2VidGenerator(nn.Module):
         seg = seg.view(B, T, -1, H, H)
         return torch.cat([seg, seg[:, -1:]], dim=1)
 
-    @staticmethod
-    def _sn_weight(conv):
-        """The spectrally normalised weight torch's hook would hand to the convolution
-        (power iteration in training mode, exactly once per call like a real forward)."""
-        for hook in conv._forward_pre_hooks.values():
-            hook(conv, None)
-        return conv.weight
+    def _generate(self, slots, tables, prev, groups):
+        """One generator call on a batch of (previous frame, layout pair) items: flow network,
+        warp, conv_dim_in, SPADE generator (generator.py:66-90).  The two convolutions that consume
+        the layout run through its rank-1 structure (csrc/k4_layoutconv.cu): the [.,1024,H,W]
+        layout pair, the 1027-channel concatenations and the dense 1027->32 / 1027->512
+        convolutions never exist.  Returns (image, flow, confidence)."""
+        D = slots[0].shape[-1]
+        fn = self.flows_network
+        flow_cb, in_cb = fn.down_flow[0], self.conv_dim_in[0]
+
+        def layout_conv(conv_bn, img):
+            entry = conv_bn[0].__dict__['_ag2v_sn_entry']
+            if entry.scale is None:                      # weight / sigma was materialised (refresh)
+                for hook in conv_bn[0]._forward_pre_hooks.values():
+                    hook(conv_bn[0], None)
+                w = conv_bn[0].weight
+            else:                                        # sigma mode: raw weight, output scaled per image
+                w = conv_bn[0].weight_orig
+            base = F.conv2d(img, w[:, 2 * D:], padding=1).contiguous(memory_format=CL)
+            z = layout_conv3x3(w[:, :2 * D], slots, tables, base)
+            return z if entry.scale is None else z * entry.scale
+
+        feat = fn.features(None, groups, first=layout_conv(flow_cb, prev))
+        flow = fn.conv_flow(feat) * fn.flow_multiplier
+        warped = flow_warp(prev[:, -3:], flow)
+        diff = prev[:, -3:] - warped
+        conf = ((diff * diff).sum(dim=1, keepdim=True) < 0.02).float()
+        y = in_cb[1](layout_conv(in_cb, warped.contiguous(memory_format=CL)), groups, 0.2)
+        return self.netG(y, groups) + warped, flow, conf
 
     def forward_fused(self, imgs_gt, objs, obj_vecs, layout, test_mode=False):
-        """Same computation as ``forward`` with the two convolutions that consume the layout
-        (flows_network.down_flow[0], conv_dim_in[0]) evaluated through the rank-1 structure of
-        the layout (csrc/k4_layoutconv.cu): the [B,F+1,512,H,W] layout, the 1027-channel
-        concatenations and the dense 1027->512 / 1027->32 convolutions never exist."""
+        """Same computation as ``forward`` on the fused kernels.  In training (ground-truth
+        previous frames: not test_mode, bp_prev = 0) the T-1 generator calls of the reference's
+        frame loop are independent given the inputs; they run as ONE call on a group-major batch
+        of (T-1)*B images with per-group batch-norm statistics and per-group spectral-norm sigmas,
+        i.e. exactly the arithmetic of T-1 successive calls."""
         B, T, O = layout.shape[:3]
         H = self.opt.image_size[0]
         n_prev = self.opt.n_frames_G - 1
         assert n_prev == 1, 'fused path is written for n_frames_G = 2 (the reference default)'
         att = self.attribute_embedding(objs)
         vecs = torch.cat([att.unsqueeze(1).expand(B, T, O, att.shape[-1]), obj_vecs], dim=-1)      # [B,T,O,512]
-        D = vecs.shape[-1]
         valid = real_object_mask(objs, self.opt.vocab)                                               # [B,O]
         valid2 = torch.cat([valid, valid], dim=1)
-        flow_conv, flow_bn = self.flows_network.down_flow[0][0], self.flows_network.down_flow[0][1]
-        in_conv, in_bn = self.conv_dim_in[0][0], self.conv_dim_in[0][1]
+        dev = imgs_gt.device
+        sequential = test_mode or bool(self.opt.bp_prev) or not getattr(self, 'batch_frames', True)
+        if not sequential and T > n_prev:
+            G = T - n_prev                                                     # frame groups, n = g*B + b
+            gm = lambda x: x.transpose(0, 1).reshape(G * B, *x.shape[2:])      # [B,G,...] -> group-major batch
+            boxes2 = torch.cat([gm(layout[:, :T - 1]), gm(layout[:, 1:])], dim=1)
+            tables = layout_tables(boxes2, valid2.repeat(G, 1), H, H)
+            slots = [gm(vecs[:, :T - 1]), gm(vecs[:, 1:])]
+            prev = gm(imgs_gt[:, :T - 1]).contiguous(memory_format=CL)
+            self._sn.refresh_sigma(G, B)                                       # G power iterations, in frame order
+            try:
+                img, flow, cf = self._generate(slots, tables, prev, G)
+            finally:
+                self._sn.end_sigma()
+            ug = lambda x: x.view(G, B, *x.shape[1:]).transpose(0, 1)          # back to [B,G,...]
+            imgs = torch.cat([imgs_gt[:, :n_prev], ug(img)], dim=1)
+            pad = lambda x: torch.cat([ug(x), torch.zeros(B, 1, *x.shape[1:], device=dev)], dim=1)
+            return imgs, pad(flow), pad(cf)
         imgs_prev = imgs_gt[:, :n_prev]
-        conf = torch.zeros(B, T, 1, H, H, device=imgs_gt.device)
-        flows = torch.zeros(B, T, 2, H, H, device=imgs_gt.device)
+        conf = torch.zeros(B, T, 1, H, H, device=dev)
+        flows = torch.zeros(B, T, 2, H, H, device=dev)
         for t in range(n_prev, T):
-            # frame slots of seg_t: layout(t-1) -> channels [0, D), layout(t) -> channels [D, 2D)
             self._sn.refresh()             # one power iteration per generator call, like the reference's hooks
+            # frame slots of seg_t: layout(t-1) -> channels [0, D), layout(t) -> channels [D, 2D)
             tables = layout_tables(torch.cat([layout[:, t - 1], layout[:, t]], dim=1), valid2, H, H)
             slots = [vecs[:, t - 1], vecs[:, t]]
             prev = imgs_prev[:, -n_prev:] if (test_mode or self.opt.bp_prev) else imgs_gt[:, t - n_prev:t]
             prev = prev.reshape(B, -1, H, H).contiguous(memory_format=CL)
-            wf = self._sn_weight(flow_conv)
-            x = layout_conv3x3(wf[:, :2 * D], slots, tables,
-                               F.conv2d(prev, wf[:, 2 * D:], padding=1).contiguous(memory_format=CL))
-            x = self.flows_network.down_flow[1](flow_bn(x))
-            feat = self.flows_network.up_flow(self.flows_network.res_flow(self.flows_network.down_flow[2:](x)))
-            flow = self.flows_network.conv_flow(feat) * self.flows_network.flow_multiplier
-            warped = flow_warp(prev[:, -3:], flow)
-            diff = prev[:, -3:] - warped
-            conf[:, t - 1] = ((diff * diff).sum(dim=1, keepdim=True) < 0.02).float()
+            img, flow, cf = self._generate(slots, tables, prev, 1)
+            conf[:, t - 1] = cf
             flows[:, t - 1] = flow
-            wi = self._sn_weight(in_conv)
-            y = layout_conv3x3(wi[:, :2 * D], slots, tables,
-                               F.conv2d(warped.contiguous(memory_format=CL), wi[:, 2 * D:], padding=1).contiguous(memory_format=CL))
-            y = self.conv_dim_in[1](in_bn(y))
-            img = self.netG(y) + warped
             imgs_prev = torch.cat([imgs_prev, img.unsqueeze(1)], dim=1)
         return imgs_prev, flows, conf
 

@@ -22,25 +22,26 @@ from torch.nn.utils import spectral_norm
 
 from . import _lib as L
 from ._lib import c_f, c_i, c_p, c_sz
-from .specnorm import SpectralNormGroup
+from .specnorm import SpectralNormGroup, conv_scaled
 
 c_ll = L.ctypes.c_longlong
 c_d = L.ctypes.c_double
 
 L.register('ag2v_chan_partial_floats', c_sz, [c_ll, c_i, c_i])
-L.register('ag2v_bn_stats', c_i, [c_p, c_ll, c_i, c_p, c_p, c_p])
-L.register('ag2v_bn_finalize', c_i, [c_p, c_d, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p])
+L.register('ag2v_bn_stats', c_i, [c_p, c_ll, c_i, c_i, c_p, c_p, c_p])
+L.register('ag2v_bn_finalize', c_i, [c_p, c_d, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p])
+L.register('ag2v_bn_act_fwd', c_i, [c_p] * 5 + [c_ll, c_i, c_i, c_f, c_p, c_p])
 L.register('ag2v_bn_eval_stats', c_i, [c_p, c_p, c_i, c_f, c_p, c_p, c_p])
-L.register('ag2v_spade_bwd_pre', c_i, [c_p] * 6 + [c_ll, c_i, c_i, c_f, c_i] + [c_p] * 4 + [c_p])
-L.register('ag2v_spade_bwd_dx', c_i, [c_p] * 5 + [c_d, c_i, c_ll, c_i, c_p])
+L.register('ag2v_spade_bwd_pre', c_i, [c_p] * 6 + [c_ll, c_i, c_i, c_i, c_f, c_i, c_i] + [c_p] * 4 + [c_p])
+L.register('ag2v_spade_bwd_dx', c_i, [c_p] * 5 + [c_d, c_i, c_ll, c_i, c_i, c_p])
 L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_unpack_dw3x3', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
-L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_p, c_p])
+L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_i, c_ll, c_p, c_p])
 L.register('ag2v_round_tf32', c_i, [c_p, c_p, c_ll, c_p])
 L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 6)
 L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p])
 L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_ll, c_ll, c_ll,
-                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_p, c_sz, c_i, c_p])
+                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_ll, c_p, c_p, c_sz, c_i, c_p])
 L.register('ag2v_conv3x3_splitk_floats', c_sz, [c_i] * 5)
 L.register('ag2v_conv3x3_tc_supported', c_i, [c_i] * 6)
 
@@ -108,7 +109,7 @@ class _Timed:
 
 
 def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, epi, round_out=0,
-          x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None):
+          x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None, group_pixels=0):
     lib = L.lib()
     nws = lib.ag2v_conv3x3_splitk_floats(B, Hh, Ww, Cin, Nout) if CONV_IMPL in (0, 2) else 0
     ws = torch.empty(nws, device=out.device, dtype=torch.float32) if nws else None
@@ -116,7 +117,8 @@ def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, ep
         L.check(lib.ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
                                  L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
                                  out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
-                                 L.ptr(gamma_out), float(slope), C, L.ptr(gate), L.ptr(ws), nws, CONV_IMPL, L.stream()))
+                                 L.ptr(gamma_out), float(slope), C, group_pixels, L.ptr(gate), L.ptr(ws), nws, CONV_IMPL,
+                                 L.stream()))
 
 
 def _pack(wa, wb, ba, bb, dgrad):
@@ -187,7 +189,7 @@ class _SharedSegFn(torch.autograd.Function):
 
 class _SpadeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, seg, token, w_sh, b_sh, w_g, b_g, w_b, b_b, mod, shared, slope):
+    def forward(ctx, x, seg, token, w_sh, b_sh, w_g, b_g, w_b, b_b, mod, shared, slope, groups=1):
         L.need_cuda(x, seg, w_sh)
         lib = L.lib()
         dev = x.device
@@ -204,18 +206,22 @@ class _SpadeFn(torch.autograd.Function):
         P = B * r * rw
         training = mod.training
         bn = mod.param_free_norm
-        mean = torch.empty(C, device=dev, dtype=torch.float32)
-        rstd = torch.empty(C, device=dev, dtype=torch.float32)
-        count = float(P)
+        if B % groups:
+            raise ValueError('SPADE: batch %d is not a multiple of groups=%d' % (B, groups))
+        G = groups if training else 1              # statistics per group of B/G images (one reference call each)
+        Pg = P // G
+        mean = torch.empty(G * C, device=dev, dtype=torch.float32)
+        rstd = torch.empty(G * C, device=dev, dtype=torch.float32)
+        count = float(Pg)
         if training:
-            part = torch.empty(lib.ag2v_chan_partial_floats(P, C, 2), device=dev, dtype=torch.float32)
-            sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
-            L.check(lib.ag2v_bn_stats(L.ptr(x), P, C, L.ptr(part), L.ptr(sums), L.stream()))
+            part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 2), device=dev, dtype=torch.float32)
+            sums = torch.empty(G * 2 * C, device=dev, dtype=torch.float64)
+            L.check(lib.ag2v_bn_stats(L.ptr(x), Pg, C, G, L.ptr(part), L.ptr(sums), L.stream()))
             dist, world = _world()
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
-                count = float(P * world)
-            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, bn.eps, bn.momentum, L.ptr(bn.running_mean),
+                count = float(Pg * world)
+            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, G, bn.eps, bn.momentum, L.ptr(bn.running_mean),
                                          L.ptr(bn.running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
         else:
             L.check(lib.ag2v_bn_eval_stats(L.ptr(bn.running_mean), L.ptr(bn.running_var), C, bn.eps, L.ptr(mean),
@@ -228,17 +234,19 @@ class _SpadeFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         gamma = torch.empty(B, r, rw, C, device=dev, dtype=torch.float32) if need_grad else None
         _conv(actv, (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN), B, r, rw, NHIDDEN, pk['w2'], pk['b2'], 2 * C, out,
-              (r * rw * C, rw * C, C), EPI_SPADE, x=x, mean=mean, rstd=rstd, gamma_out=gamma, slope=slope, C=C)
+              (r * rw * C, rw * C, C), EPI_SPADE, x=x, mean=mean, rstd=rstd, gamma_out=gamma, slope=slope, C=C,
+              group_pixels=Pg if G > 1 else 0)
         if need_grad:
             ctx.save_for_backward(x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b)
-        ctx.meta = (B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope)
+        ctx.meta = (B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G)
         ctx.mod, ctx.shared = mod, shared
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b = ctx.saved_tensors
-        B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope = ctx.meta
+        B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G = ctx.meta
+        Pg = P // G
         mod, shared = ctx.mod, ctx.shared
         lib = L.lib()
         dev = x.device
@@ -246,20 +254,19 @@ class _SpadeFn(torch.autograd.Function):
         act = 0 if slope == 1.0 else 1
         dgb = torch.empty(P, 2 * C, device=dev, dtype=torch.float32)
         dx = torch.empty(B, C, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
-        part = torch.empty(lib.ag2v_chan_partial_floats(P, C, 4), device=dev, dtype=torch.float32)
-        sums = torch.empty(4 * C, device=dev, dtype=torch.float64)
-        L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), P, C,
-                                       act, float(slope), int(not _precise()), L.ptr(dgb), L.ptr(dx), L.ptr(part),
+        part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 4), device=dev, dtype=torch.float32)
+        sums = torch.empty(G * 4 * C, device=dev, dtype=torch.float64)
+        L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), Pg, C, G,
+                                       act, float(slope), int(not _precise()), 0, L.ptr(dgb), L.ptr(dx), L.ptr(part),
                                        L.ptr(sums), L.stream()))
         db = torch.empty(2 * C, device=dev, dtype=torch.float32)     # [sum g | sum g*xhat] = [d bias_beta | d bias_gamma]
-        L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, L.ptr(db), L.stream()))
+        L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 4 * C, L.ptr(db), L.stream()))
         if training:
             dist, world = _world()
-            if world > 1:
-                tail = sums[2 * C:]
-                dist.all_reduce(tail, group=_sync_group['group'])
+            if world > 1:              # db (local sums) is already extracted; the BN backward needs global sums
+                dist.all_reduce(sums, group=_sync_group['group'])
         L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
-                                      int(training), P, C, L.stream()))
+                                      int(training), Pg, C, G, L.stream()))
         a_strides = (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN)
         # gamma / beta convolutions: weight gradient, then input gradient gated by the ReLU of actv
         dw_g, dw_b = _wgrad(dgb, 2 * C, actv, a_strides, NHIDDEN, B, r, rw, True, w_g, w_b)
@@ -270,9 +277,9 @@ class _SpadeFn(torch.autograd.Function):
         # shared convolution: bias / weight gradients, then the gradient w.r.t. the (strided) segmap
         part1 = torch.empty(lib.ag2v_chan_partial_floats(P, NHIDDEN, 2), device=dev, dtype=torch.float32)
         sums1 = torch.empty(2 * NHIDDEN, device=dev, dtype=torch.float64)
-        L.check(lib.ag2v_bn_stats(L.ptr(dactv), P, NHIDDEN, L.ptr(part1), L.ptr(sums1), L.stream()))
+        L.check(lib.ag2v_bn_stats(L.ptr(dactv), P, NHIDDEN, 1, L.ptr(part1), L.ptr(sums1), L.stream()))
         db_sh = torch.empty(NHIDDEN, device=dev, dtype=torch.float32)
-        L.check(lib.ag2v_double_to_float(L.ptr(sums1), NHIDDEN, L.ptr(db_sh), L.stream()))
+        L.check(lib.ag2v_double_to_float(L.ptr(sums1), NHIDDEN, 1, 0, L.ptr(db_sh), L.stream()))
         dw_sh, _ = _wgrad(dactv, NHIDDEN, seg, seg_strides, Lc, B, r, rw, False, w_sh, None)
         dseg = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
@@ -283,7 +290,77 @@ class _SpadeFn(torch.autograd.Function):
                 dseg = buf
             _conv(dactv, a_strides, B, r, rw, NHIDDEN, pkt['w1t'], None, Lc, buf, seg_strides, EPI_ACCUM)
         dtoken = torch.zeros(1, device=dev) if (shared is not None and ctx.needs_input_grad[2]) else None
-        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None
+        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None
+
+
+class _BnActFn(torch.autograd.Function):
+    """act(batch_norm(x) * weight + bias) on an NHWC batch of ``groups`` reference calls
+    (group-major), statistics and running-stat updates per group: the conv -> SyncBN ->
+    LeakyReLU(0.2) stages around the SPADE generator (normalization.py:16-50)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, slope, groups):
+        L.need_cuda(x, weight, bias)
+        lib = L.lib()
+        dev = x.device
+        x = _cl(x.float())
+        B, C, H, W = x.shape
+        if C % 4 or B % groups:
+            raise NotImplementedError('bn_act: channels %% 4 == 0 and batch %% groups == 0 required (got C=%d, B=%d, groups=%d)'
+                                      % (C, B, groups))
+        P = B * H * W
+        G = groups if training else 1
+        Pg = P // G
+        mean = torch.empty(G * C, device=dev, dtype=torch.float32)
+        rstd = torch.empty(G * C, device=dev, dtype=torch.float32)
+        count = float(Pg)
+        if training:
+            part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 2), device=dev, dtype=torch.float32)
+            sums = torch.empty(G * 2 * C, device=dev, dtype=torch.float64)
+            L.check(lib.ag2v_bn_stats(L.ptr(x), Pg, C, G, L.ptr(part), L.ptr(sums), L.stream()))
+            dist, world = _world()
+            if world > 1:
+                dist.all_reduce(sums, group=_sync_group['group'])
+                count = float(Pg * world)
+            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, G, eps, momentum, L.ptr(running_mean), L.ptr(running_var),
+                                         L.ptr(mean), L.ptr(rstd), L.stream()))
+        else:
+            L.check(lib.ag2v_bn_eval_stats(L.ptr(running_mean), L.ptr(running_var), C, eps, L.ptr(mean), L.ptr(rstd), L.stream()))
+        w, b = L.f32c(weight), L.f32c(bias)
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        L.check(lib.ag2v_bn_act_fwd(L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(w), L.ptr(b), Pg, C, G, float(slope), L.ptr(y),
+                                    L.stream()))
+        ctx.save_for_backward(x, y, mean, rstd, w)
+        ctx.meta = (C, Pg, G, count, training, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, mean, rstd, w = ctx.saved_tensors
+        C, Pg, G, count, training, slope = ctx.meta
+        lib = L.lib()
+        dev = x.device
+        dout = _cl(dout.float())
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 4), device=dev, dtype=torch.float32)
+        sums = torch.empty(G * 4 * C, device=dev, dtype=torch.float64)
+        L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(y), L.ptr(x), L.ptr(w), L.ptr(mean), L.ptr(rstd), Pg, C, G,
+                                       0 if slope == 1.0 else 1, float(slope), 0, 1, None, L.ptr(dx), L.ptr(part),
+                                       L.ptr(sums), L.stream()))
+        db = torch.empty(2 * C, device=dev, dtype=torch.float32)           # [d bias | d weight]
+        L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 4 * C, L.ptr(db), L.stream()))
+        if training:
+            dist, world = _world()
+            if world > 1:
+                dist.all_reduce(sums, group=_sync_group['group'])
+        L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
+                                      int(training), Pg, C, G, L.stream()))
+        return dx, db[C:], db[:C], None, None, None, None, None, None, None
+
+
+def bn_act(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5, slope=1.0, groups=1):
+    return _BnActFn.apply(x, weight, bias, running_mean, running_var, bool(training), float(momentum), float(eps),
+                          float(slope), int(groups))
 
 
 class _ParamFreeNorm(nn.Module):
@@ -342,13 +419,15 @@ class SPADE(nn.Module):
             self._pkt = dict(key=key, w1t=w1t, w2t=w2t)
         return self._pkt
 
-    def forward(self, x, segmap):
+    def forward(self, x, segmap, groups=1):
+        """``groups`` > 1: the batch holds that many reference calls (group-major); batch statistics
+        and running-stat updates are per group, as if the layer were called once per group."""
         shared = segmap if isinstance(segmap, SharedSeg) else None
         seg = shared.seg if shared is not None else segmap
         token = shared.token if shared is not None else None
         return _SpadeFn.apply(x, seg, token, self.mlp_shared[0].weight, self.mlp_shared[0].bias,
                               self.mlp_gamma.weight, self.mlp_gamma.bias, self.mlp_beta.weight, self.mlp_beta.bias,
-                              self, shared, float(self.fused_slope))
+                              self, shared, float(self.fused_slope), int(groups))
 
 
 class SPADEResnetBlock(nn.Module):
@@ -378,14 +457,16 @@ class SPADEResnetBlock(nn.Module):
             self.norm_s = SPADE(cfg, fin, opt.semantic_nc)
         self.__dict__['_sn'] = SpectralNormGroup(self)        # spectral norm through csrc/k5_specnorm.cu
 
-    def forward(self, x, seg):
-        self._sn.refresh_stale()                              # no-op when the generator prepared the weights
-        own = None
+    def forward(self, x, seg, groups=1):
+        """``groups`` > 1: the batch holds that many reference calls (see SPADE.forward); the caller
+        has put the spectral norms in sigma mode (SpectralNormGroup.refresh_sigma)."""
+        if groups == 1:
+            self._sn.refresh_stale()                          # no-op when the generator prepared the weights
         if not isinstance(seg, SharedSeg):
-            seg = own = SharedSeg.wrap(seg)
-        x_s = self.conv_s(self.norm_s(x, seg)) if self.learned_shortcut else x
-        dx = self.conv_0(self.norm_0(x, seg))
-        dx = self.conv_1(self.norm_1(dx, seg))
+            seg = SharedSeg.wrap(seg)
+        x_s = conv_scaled(self.conv_s, self.norm_s(x, seg, groups)) if self.learned_shortcut else x
+        dx = conv_scaled(self.conv_0, self.norm_0(x, seg, groups))
+        dx = conv_scaled(self.conv_1, self.norm_1(dx, seg, groups))
         return x_s + dx
 
     def actvn(self, x):

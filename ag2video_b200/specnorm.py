@@ -29,6 +29,10 @@ L.register('ag2v_spectral_norm_fwd', L.c_i, [L.c_i, _pp, _pp, _pp, _pp, _ip, _ip
                                              L.c_i, L.c_f, L.c_p])
 L.register('ag2v_spectral_norm_bwd', L.c_i, [L.c_i, _pp, _pp, _pp, _ip, _ip, _ip, _ip, L.c_p, L.c_sz, L.c_p, L.c_sz, L.c_p])
 
+L.register('ag2v_spectral_norm_sigma_fwd', L.c_i, [L.c_i, _pp, _pp, _pp, _ip, _ip, _ip, _ip, L.c_i, L.c_p, L.c_sz, L.c_p, L.c_sz,
+                                                   L.c_i, L.c_f, L.c_p])
+L.register('ag2v_spectral_norm_sigma_bwd', L.c_i, [L.c_i, L.c_p, _pp, _ip, _ip, _ip, _ip, L.c_i, L.c_p, L.c_sz, L.c_p])
+
 MAX_PER_LAUNCH = 48
 
 
@@ -106,6 +110,55 @@ class _SpectralNormFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(dws)
 
 
+class _SpectralSigmaFn(torch.autograd.Function):
+    """(*weight_orig) -> sigma [iters, n]: ``iters`` successive power iterations (one per frame group
+    of a batched call).  The convolutions then run on weight_orig and scale group g's output by
+    1 / sigma[g]; autograd brings back d sigma, whose weight gradient is sum_g dsigma_g u_g v_g^T."""
+
+    @staticmethod
+    def forward(ctx, us, vs, training, eps, iters, *ws):
+        L.need_cuda(*ws)
+        co, cin, taps, cl = _geometry(ws)
+        save_n, fwd_n, _ = _sizes(co, cin, taps)
+        dev = ws[0].device
+        k = iters if training else 1               # eval mode: u / v are fixed, every group sees the same sigma
+        save = torch.empty(k * save_n, device=dev, dtype=torch.float32)
+        scratch = torch.empty(fwd_n, device=dev, dtype=torch.float32)
+        L.check(L.lib().ag2v_spectral_norm_sigma_fwd(len(ws), _ptr_array(ws), _ptr_array(us), _ptr_array(vs), _int_array(co),
+                                                     _int_array(cin), _int_array(taps), _int_array(cl), k, L.ptr(save),
+                                                     save.numel(), L.ptr(scratch), fwd_n, int(training), float(eps),
+                                                     L.stream()))
+        n = len(ws)
+        n4 = (n + 3) & ~3
+        sigma = save[:k * n4].view(k, n4)[:, :n]
+        sigma = sigma.expand(iters, n).contiguous() if k != iters else sigma.contiguous()
+        ctx.save_for_backward(save, *ws)
+        ctx.geom, ctx.k, ctx.iters = (co, cin, taps, cl), k, iters
+        return sigma
+
+    @staticmethod
+    def backward(ctx, dsigma):
+        save, *ws = ctx.saved_tensors
+        co, cin, taps, cl = ctx.geom
+        if ctx.k != ctx.iters:
+            dsigma = dsigma.sum(dim=0, keepdim=True)
+        dsigma = dsigma.float().contiguous()
+        dws = [torch.empty_like(w) for w in ws]
+        L.check(L.lib().ag2v_spectral_norm_sigma_bwd(len(ws), L.ptr(dsigma), _ptr_array(dws), _int_array(co), _int_array(cin),
+                                                     _int_array(taps), _int_array(cl), ctx.k, L.ptr(save), save.numel(),
+                                                     L.stream()))
+        return (None, None, None, None, None) + tuple(dws)
+
+
+def spectral_sigmas(weights, us, vs, iters, training=True, eps=1e-12):
+    """sigma [iters, n] for lists of weight_orig / weight_u / weight_v."""
+    outs = []
+    for i in range(0, len(weights), MAX_PER_LAUNCH):
+        j = i + MAX_PER_LAUNCH
+        outs.append(_SpectralSigmaFn.apply(list(us[i:j]), list(vs[i:j]), training, eps, iters, *weights[i:j]))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
+
 def spectral_normalize(weights, us, vs, training=True, eps=1e-12):
     """Normalised weights for lists of weight_orig / weight_u / weight_v (any number)."""
     outs = []
@@ -116,10 +169,11 @@ def spectral_normalize(weights, us, vs, training=True, eps=1e-12):
 
 
 class _Entry:
-    __slots__ = ('module', 'name', 'eps', 'fresh')
+    __slots__ = ('module', 'name', 'eps', 'fresh', 'scale')
 
     def __init__(self, module, name, eps):
         self.module, self.name, self.eps, self.fresh = module, name, eps, False
+        self.scale = None          # sigma mode: [N,1,1,1] per-image 1/sigma of the current batched call
 
     def tensors(self):
         m, n = self.module, self.name
@@ -137,6 +191,7 @@ def _compute(entries):
         for e, w in zip(es, outs):
             setattr(e.module, e.name, w)
             e.fresh = True
+            e.scale = None
 
 
 def _make_hook(entry):
@@ -174,6 +229,41 @@ class SpectralNormGroup:
         """Compute the weight of every module for the call that is about to happen."""
         _compute(self.entries)
 
+    def refresh_sigma(self, groups, images_per_group):
+        """Sigma mode for a call that batches ``groups`` reference calls (group-major batch of
+        groups * images_per_group images): one power iteration per group, in order; afterwards
+        ``conv_scaled`` evaluates each convolution on weight_orig with a per-image 1/sigma."""
+        modes = {(e.module.training, e.eps) for e in self.entries}
+        if len(modes) != 1:
+            raise RuntimeError('spectral norm sigma mode: modules disagree on training mode / eps')
+        (training, eps), = modes
+        trip = [e.tensors() for e in self.entries]
+        sigma = spectral_sigmas([t[0] for t in trip], [t[1] for t in trip], [t[2] for t in trip], groups, training, eps)
+        inv_img = sigma.reciprocal().repeat_interleave(images_per_group, dim=0)      # [N, n]
+        for i, e in enumerate(self.entries):
+            e.scale = inv_img[:, i].view(-1, 1, 1, 1)
+            e.fresh = False
+        return sigma
+
     def refresh_stale(self):
         """Same, for the modules whose weight has not been prepared yet (nested use)."""
-        _compute([e for e in self.entries if not e.fresh])
+        _compute([e for e in self.entries if not e.fresh and e.scale is None])
+
+    def end_sigma(self):
+        """Leave sigma mode (the autograd graph of the finished call keeps what it needs)."""
+        for e in self.entries:
+            e.scale = None
+
+
+def conv_scaled(conv, x):
+    """``conv(x)`` for a spectrally normalised nn.Conv2d.  In sigma mode (after
+    ``refresh_sigma``) the convolution runs on weight_orig and image n of the output is scaled by
+    1/sigma of its group; otherwise this is a plain module call (hooks or ``refresh``)."""
+    entry = conv.__dict__.get('_ag2v_sn_entry')
+    if entry is None or entry.scale is None:
+        return conv(x)
+    z = torch.nn.functional.conv2d(x, getattr(conv, entry.name + '_orig'), None, conv.stride, conv.padding,
+                                   conv.dilation, conv.groups)
+    if conv.bias is None:
+        return z * entry.scale
+    return torch.addcmul(conv.bias.view(1, -1, 1, 1), z, entry.scale)

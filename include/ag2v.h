@@ -104,6 +104,19 @@ int ag2v_spectral_norm_bwd(int n, const void* const* w, const void* const* grad_
                            const float* save, size_t save_floats, float* scratch, size_t scratch_floats,
                            ag2v_stream_t stream);
 
+/* K5 sigma mode, for a call that batches `iters` frame groups: `iters` successive power iterations,
+ * each saving its sigma / u / v (save: iters * save_floats of ag2v_spectral_norm_sizes; it starts
+ * with sigma [iters][(n+3)&~3]).  No weight is written: group g's convolution runs on weight_orig
+ * and its output is scaled by 1/sigma_g.  Backward of the sigmas: grad_w[i] = sum_it
+ * dsigma[it][i] u_it v_it^T (dsigma: device array [iters][n]). */
+int ag2v_spectral_norm_sigma_fwd(int n, const void* const* w, void* const* u, void* const* v, const int* co,
+                                 const int* cin, const int* taps, const int* channels_last, int iters, float* save,
+                                 size_t save_floats, float* scratch, size_t scratch_floats, int power_iteration,
+                                 float eps, ag2v_stream_t stream);
+int ag2v_spectral_norm_sigma_bwd(int n, const float* dsigma, void* const* grad_w, const int* co, const int* cin,
+                                 const int* taps, const int* channels_last, int iters, const float* save,
+                                 size_t save_floats, ag2v_stream_t stream);
+
 /* masks_to_layout (models/layout.py:66-95, _pool_mask_samples :164-202) for one
  * (clip, frame): vecs [O,D], boxes [O,4] xywh, masks [O,M,M]; S [O,H,W] receives the
  * sampled masks (kept for the backward); test_mode != 0 composites objects in
@@ -131,12 +144,23 @@ int ag2v_crop_bbox_bwd(const float* dout, const int* frame, const float* boxes, 
  * Host code composes them (ag2video_b200/spade.py); the SyncBN all-reduce of the
  * per-channel sums (sync_batchnorm/batchnorm.py:74-83) sits between stats and finalize. */
 
-/* per-channel sums over x [P,C] NHWC: sums[0..C) = sum x, sums[C..2C) = sum x^2 (doubles) */
+/* Groups: the frames of a clip can be batched into ONE call while keeping the per-call batch
+ * statistics of the reference's frame loop (generator.py:56-94 calls every layer once per frame):
+ * every activation is then [groups][P][C] (group-major batch) and statistics are per group. */
+
+/* per-channel sums over x [groups][P,C] NHWC: sums[g][0..C) = sum x, sums[g][C..2C) = sum x^2 (doubles);
+ * partial: groups * ag2v_chan_partial_floats(P, C, NS) floats */
 size_t ag2v_chan_partial_floats(long long P, int C, int NS);
-int ag2v_bn_stats(const float* x, long long P, int C, float* partial, double* sums, ag2v_stream_t stream);
-/* F.batch_norm(training) statistics (normalization.py:99): mean/rstd + running update */
-int ag2v_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
-                     float* running_var, float* mean, float* rstd, ag2v_stream_t stream);
+int ag2v_bn_stats(const float* x, long long P, int C, int groups, float* partial, double* sums, ag2v_stream_t stream);
+/* F.batch_norm(training) statistics (normalization.py:99): mean/rstd [groups][C] + running update
+ * (once per group, in group order); count = elements per channel of one group */
+int ag2v_bn_finalize(const double* sums, double count, int C, int groups, float eps, float momentum,
+                     float* running_mean, float* running_var, float* mean, float* rstd, ag2v_stream_t stream);
+/* y = act((x - mean_g) * rstd_g * weight + bias): the affine SyncBN + LeakyReLU(0.2) stages
+ * (normalization.py:16-50); slope 1 = no activation.  Its backward is ag2v_spade_bwd_pre with
+ * chan_gamma = 1 (gamma := weight [C], dgb = NULL) followed by ag2v_spade_bwd_dx. */
+int ag2v_bn_act_fwd(const float* x, const float* mean, const float* rstd, const float* weight, const float* bias,
+                    long long P, int C, int groups, float slope, float* y, ag2v_stream_t stream);
 int ag2v_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
                        float* rstd, ag2v_stream_t stream);
 
@@ -153,24 +177,26 @@ int ag2v_pack_w3x3(const float* wa, const float* wb, const float* ba, const floa
  *            3: out = gate > 0 ? acc : 0     4: out += acc (gradient into the shared segmap)
  * impl 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel, 3 = mma.sync with 3xTF32 products
  * (fp32-class accuracy, validation mode).  round_ops / round_out: round the stored GEMM operands
- * to nearest TF32 (the tcgen05 TF32 path truncates). */
+ * to nearest TF32 (the tcgen05 TF32 path truncates).  group_pixels > 0 (epilogue 2): mean / rstd
+ * are [groups][C] and pixel p uses group p / group_pixels. */
 int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in_sx, int B, int Hh, int Ww, int Cin,
                  const float* wpk, const float* bias, int Nout, float* out, long long out_sb, long long out_sy,
                  long long out_sx, int epilogue, int round_out, const float* x, const float* mean,
-                 const float* rstd, float* gamma_out, float slope, int C, const float* gate, float* splitk_ws,
-                 size_t splitk_ws_floats, int impl, ag2v_stream_t stream);
+                 const float* rstd, float* gamma_out, float slope, int C, long long group_pixels, const float* gate,
+                 float* splitk_ws, size_t splitk_ws_floats, int impl, ag2v_stream_t stream);
 /* split-K scratch (floats) that lets low-resolution layers use the whole chip; 0 = none needed */
 size_t ag2v_conv3x3_splitk_floats(int B, int Hh, int Ww, int Cin, int Nout);
 int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue);
 
 /* SPADE backward, element-wise: pass 1 produces d(gamma|beta) [P,2C], dxhat and the
- * per-channel sums [4][C] (sum g, sum g*xhat, sum dxhat, sum dxhat*xhat); pass 2 turns
- * dxhat into dx (batch-norm backward) in place. */
+ * per-channel sums [groups][4][C] (sum g, sum g*xhat, sum dxhat, sum dxhat*xhat); pass 2 turns
+ * dxhat into dx (batch-norm backward) in place.  chan_gamma = 1: `gamma` is a per-channel scale
+ * [C] (affine batch norm) and dgb may be NULL. */
 int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma, const float* mean,
-                       const float* rstd, long long P, int C, int act, float slope, int round_ops, float* dgb,
-                       float* dxhat, float* partial, double* sums, ag2v_stream_t stream);
+                       const float* rstd, long long P, int C, int groups, int act, float slope, int round_ops,
+                       int chan_gamma, float* dgb, float* dxhat, float* partial, double* sums, ag2v_stream_t stream);
 int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean, const float* rstd, const double* sums,
-                      double count, int training, long long P, int C, ag2v_stream_t stream);
+                      double count, int training, long long P, int C, int groups, ag2v_stream_t stream);
 
 /* weight gradient of a 3x3 conv: split-K partials (tcgen05 MN-major kernel or mma.sync,
  * `impl` as for ag2v_conv3x3), then reduction + scatter to OIHW */
@@ -179,7 +205,9 @@ int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, lon
                   int B, int Hh, int Ww, float* part, int impl, ag2v_stream_t stream);
 int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
                       ag2v_stream_t stream);
-int ag2v_double_to_float(const double* src, int n, float* dst, ag2v_stream_t stream);
+/* dst[i] = (float) sum over groups of src[g * group_stride + i] */
+int ag2v_double_to_float(const double* src, int n, int groups, long long group_stride, float* dst,
+                         ag2v_stream_t stream);
 /* dst = round-to-nearest TF32 of src (same layout; the tcgen05 TF32 path truncates, so GEMM
  * operands are rounded where they are produced; this covers the externally produced segmap) */
 int ag2v_round_tf32(const float* src, float* dst, long long n, ag2v_stream_t stream);
