@@ -16,7 +16,7 @@
 namespace ag2v {
 
 enum ConvEpilogue : int {
-  EPI_BIAS = 0,        // out = acc + bias
+  EPI_BIAS = 0,        // out = acc * scale[group] + bias + res   (scale / bias / res optional)
   EPI_BIAS_RELU = 1,   // out = relu(acc + bias)                    (mlp_shared, normalization.py:103)
   EPI_SPADE = 2,       // out = act((x-mean)*rstd*(1+g)+b), g/b = acc + bias (normalization.py:104-108)
   EPI_GATE = 3,        // out = gate > 0 ? acc : 0                  (backward through the ReLU)
@@ -35,6 +35,9 @@ struct ConvParams {
   // EPI_SPADE: Nout == 2*C in gb8 order; out is [.., C]
   const float* x; const float* mean; const float* rstd; float* gamma_out; float slope; int C;
   long long group_pixels;    // > 0: mean/rstd are [groups][C], group = pixel index / group_pixels
+  // EPI_BIAS extras (the spectrally normalised convolutions of SPADEResnetBlock run on weight_orig):
+  // scale [groups] = 1/sigma per frame group (group = pixel / group_pixels), res = dense [P, Nout] residual
+  const float* scale; const float* res;
   // EPI_GATE
   const float* gate;
   // split-K workspace (caller-provided, may be null): ksplit * P * Nout floats

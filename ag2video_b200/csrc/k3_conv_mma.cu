@@ -184,7 +184,15 @@ __global__ void __launch_bounds__(kConvThreads, PRECISE ? 1 : 2) conv3x3_mma_ker
           if (n >= p.Nout) continue;
           float v0 = acc[mt][nt][half * 2 + 0], v1 = acc[mt][nt][half * 2 + 1];
           if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
+            if (EPI == EPI_BIAS && p.scale) {
+              const float sc = p.scale[p.group_pixels > 0 ? pp / p.group_pixels : 0];
+              v0 *= sc; v1 *= sc;
+            }
             if (p.bias) { v0 += p.bias[n]; v1 += p.bias[n + 1]; }
+            if (EPI == EPI_BIAS && p.res) {
+              const float2 r2 = *reinterpret_cast<const float2*>(p.res + (size_t)pp * p.Nout + n);
+              v0 += r2.x; v1 += r2.y;
+            }
             if (EPI == EPI_BIAS_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
           } else if (EPI == EPI_GATE) {
             const float2 gt = *reinterpret_cast<const float2*>(p.gate + (size_t)pp * p.Nout + n);

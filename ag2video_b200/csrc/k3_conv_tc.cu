@@ -81,9 +81,24 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float (&v)[3
   } else {
     const int ncols = min(32, p.Nout - n);
     if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
+      if (EPI == EPI_BIAS && p.scale) {
+        const float sc = p.scale[p.group_pixels > 0 ? pp / p.group_pixels : 0];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= sc;
+      }
       if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += p.bias[n + j];
+      }
+      if (EPI == EPI_BIAS && p.res) {
+        const float* rr = p.res + (size_t)pp * p.Nout + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < ncols) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
+            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+          }
+        }
       }
       if (EPI == EPI_BIAS_RELU) {
 #pragma unroll

@@ -31,7 +31,9 @@ static ChanGeom chan_geom(long long P, int C) {
 }
 
 // MODE 0: s0 = sum x, s1 = sum x^2                      (F.batch_norm statistics)
-// MODE 1: SPADE backward, pass 1 (see spade_bwd_pre below)
+// MODE 1: SPADE backward, pass 1 (see spade_bwd_pre below); s4 = sum dout*out serves the
+//         spectral norm of the convolution that consumed `out` (d sigma, see spade.py)
+// MODE 3: gradient of a scaled convolution output: dxhat = tf32(dout * scale[group]), s0 = sum dout
 struct ChanArgs {
   const float* x; long long P; int C;
   float* part;                      // [nsplit][NS][C]
@@ -46,14 +48,15 @@ struct ChanArgs {
 
 template <int MODE>
 __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, ChanGeom gm) {
-  constexpr int NS = MODE == 0 ? 2 : 4;
+  constexpr int NS = MODE == 0 ? 2 : (MODE == 1 ? 5 : 1);
   __shared__ float4 red[kElemThreads];
   const int tx = threadIdx.x % gm.cx, ty = threadIdx.x / gm.cx;
   const int C = a.C, c4n = C >> 2;
   {                                                     // this group's slices
     const size_t go = (size_t)blockIdx.y * a.P * C;
-    a.x += go;
+    if (MODE != 3) a.x += go;
     a.part += (size_t)blockIdx.y * gm.nsplit * NS * C;
+    if (MODE == 3) { a.dout += go; a.dxhat += go; }
     if (MODE == 1) {
       a.dout += go; a.out += go; a.dxhat += go;
       if (!a.chan_gamma) a.gamma += go;
@@ -73,6 +76,14 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
     if (live) {
       for (long long p = (long long)blockIdx.x * gm.py + ty; p < a.P; p += (long long)gm.nsplit * gm.py) {
         const size_t off = (size_t)p * C + c;
+        if (MODE == 3) {
+          const float4 dv = *reinterpret_cast<const float4*>(a.dout + off);
+          const float sc = a.gamma ? a.gamma[blockIdx.y] : 1.f;
+          *reinterpret_cast<float4*>(a.dxhat + off) = make_float4(elem_round_tf32(dv.x * sc), elem_round_tf32(dv.y * sc),
+                                                                  elem_round_tf32(dv.z * sc), elem_round_tf32(dv.w * sc));
+          s[0].x += dv.x; s[0].y += dv.y; s[0].z += dv.z; s[0].w += dv.w;
+          continue;
+        }
         const float4 xv = *reinterpret_cast<const float4*>(a.x + off);
         if (MODE == 0) {
           s[0].x += xv.x; s[0].y += xv.y; s[0].z += xv.z; s[0].w += xv.w;
@@ -110,6 +121,8 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
           s[2].x += dxh.x; s[2].y += dxh.y; s[2].z += dxh.z; s[2].w += dxh.w;
           s[3].x = fmaf(dxh.x, xh.x, s[3].x); s[3].y = fmaf(dxh.y, xh.y, s[3].y);
           s[3].z = fmaf(dxh.z, xh.z, s[3].z); s[3].w = fmaf(dxh.w, xh.w, s[3].w);
+          s[NS - 1].x = fmaf(dv.x, ov.x, s[NS - 1].x); s[NS - 1].y = fmaf(dv.y, ov.y, s[NS - 1].y);
+          s[NS - 1].z = fmaf(dv.z, ov.z, s[NS - 1].z); s[NS - 1].w = fmaf(dv.w, ov.w, s[NS - 1].w);
         }
       }
     }
@@ -199,7 +212,7 @@ spade_bwd_dx_kernel(const float* __restrict__ x, float* __restrict__ dxhat, cons
                     long long P, int C) {
   const long long n4 = P * (C >> 2);
   x += (size_t)blockIdx.y * P * C; dxhat += (size_t)blockIdx.y * P * C;
-  mean += (size_t)blockIdx.y * C; rstd += (size_t)blockIdx.y * C; sums += (size_t)blockIdx.y * 4 * C;
+  mean += (size_t)blockIdx.y * C; rstd += (size_t)blockIdx.y * C; sums += (size_t)blockIdx.y * 5 * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % (C >> 2)) << 2;
     const float4 xv = reinterpret_cast<const float4*>(x)[i];
@@ -266,6 +279,52 @@ __global__ void unpack_dw_kernel(const float* __restrict__ part, int nsplit, int
     if (two) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
     float* dst = is_b ? dwb : dwa;
     dst[((size_t)co * Ci + ci) * 9 + tap] = acc;
+  }
+}
+
+// Channels-last weights [Co][3][3][Ci] (the convolutions of a channels_last module).
+//   forward : dst[tap][co][ci] = W[co][tap][ci]                     (row copies)
+__global__ void pack_w3x3_cl_fwd_kernel(const float* __restrict__ w, int Co, int Ci, int round_ops, float* __restrict__ dst) {
+  const int Ci4 = Ci >> 2;
+  const long long total = 9LL * Co * Ci4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % Ci4); const int co = (int)((i / Ci4) % Co); const int tap = (int)(i / ((long long)Ci4 * Co));
+    float4 v = *reinterpret_cast<const float4*>(w + ((size_t)co * 9 + tap) * Ci + 4 * c4);
+    if (round_ops) v = make_float4(elem_round_tf32(v.x), elem_round_tf32(v.y), elem_round_tf32(v.z), elem_round_tf32(v.w));
+    *reinterpret_cast<float4*>(dst + ((size_t)tap * Co + co) * Ci + 4 * c4) = v;
+  }
+}
+//   dgrad   : dst[tap][ci][co] = W[co][8 - tap][ci]                  (32x32 tile transposes through smem)
+__global__ void __launch_bounds__(256) pack_w3x3_cl_dgrad_kernel(const float* __restrict__ w, int Co, int Ci, int round_ops,
+                                                                 float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + tx;
+    tile[r][tx] = (co < Co && ci < Ci) ? w[((size_t)co * 9 + (8 - tap)) * Ci + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + tx;
+    if (ci < Ci && co < Co) {
+      const float v = tile[tx][r];
+      dst[((size_t)tap * Ci + ci) * Co + co] = round_ops ? elem_round_tf32(v) : v;
+    }
+  }
+}
+// part[split][tap][co][ci] -> dW[co][tap][ci] (channels-last weight gradient)
+__global__ void unpack_dw_cl_kernel(const float* __restrict__ part, int nsplit, int Co, int Ci, float* __restrict__ dw) {
+  const int Ci4 = Ci >> 2;
+  const long long per4 = 9LL * Co * Ci4, per = 9LL * Co * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % Ci4); const int co = (int)((i / Ci4) % Co); const int tap = (int)(i / ((long long)Ci4 * Co));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < nsplit; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(part + (size_t)s * per + 4 * i);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(dw + ((size_t)co * 9 + tap) * Ci + 4 * c4) = acc;
   }
 }
 
@@ -395,7 +454,7 @@ extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const flo
   a.chan_gamma = chan_gamma;
   chan_partial_kernel<1><<<dim3(g.nsplit, groups), kElemThreads, 0, stream>>>(a, g);
   AG2V_LAUNCH_CHECK();
-  chan_reduce_kernel<<<dim3(ceil_div(4 * C, 32), groups), 256, 0, stream>>>(partial, g.nsplit, 4 * C, sums);
+  chan_reduce_kernel<<<dim3(ceil_div(5 * C, 32), groups), 256, 0, stream>>>(partial, g.nsplit, 5 * C, sums);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
@@ -446,6 +505,48 @@ extern "C" int ag2v_round_tf32(const float* src, float* dst, long long n, cudaSt
   long long n4 = n / 4;
   int blocks = (int)(ceil_div_ll(n4, 256 * 4) > 148 * 16 ? 148 * 16 : ceil_div_ll(n4, 256 * 4));
   round_tf32_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n4);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// Gradient of y = conv(x, W) * scale[group] + bias w.r.t. the convolution output, as the operand of
+// the input / weight gradient GEMMs: dys = tf32(dy * scale[group]) ([groups][P][C] NHWC, scale may
+// be NULL), sums[g][0..C) = sum dy (the bias gradient).  partial: groups * chan_partial_floats(P, C, 1).
+extern "C" int ag2v_scaled_grad_pre(const float* dy, const float* scale, long long P, int C, int groups, float* dys,
+                                    float* partial, double* sums, cudaStream_t stream) {
+  int rc = chan_check(P, C);
+  if (rc) return rc;
+  AG2V_REQUIRE(dy && dys && partial && sums && groups >= 1 && groups <= 65535, "scaled_grad_pre: bad arguments");
+  ChanGeom g = chan_geom(P, C);
+  ChanArgs a{};
+  a.P = P; a.C = C; a.part = partial; a.dout = dy; a.dxhat = dys; a.gamma = scale;
+  chan_partial_kernel<3><<<dim3(g.nsplit, groups), kElemThreads, 0, stream>>>(a, g);
+  AG2V_LAUNCH_CHECK();
+  chan_reduce_kernel<<<dim3(ceil_div(C, 32), groups), 256, 0, stream>>>(partial, g.nsplit, C, sums);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// Channels-last 3x3 weights [Co][3][3][Ci] -> [9][Co][Ci] (dgrad = 0) or [9][Ci][Co] flipped (dgrad = 1)
+extern "C" int ag2v_pack_w3x3_cl(const float* w, int Co, int Ci, int dgrad, int round_ops, float* dst, cudaStream_t stream) {
+  AG2V_REQUIRE(w && dst && Co > 0 && Ci > 0 && Ci % 4 == 0, "pack_w3x3_cl: bad arguments (Ci %% 4 == 0 required)");
+  if (!dgrad) {
+    const long long total = 9LL * Co * (Ci / 4);
+    const int blocks = (int)(ceil_div_ll(total, 256) > 2368 ? 2368 : ceil_div_ll(total, 256));
+    pack_w3x3_cl_fwd_kernel<<<blocks, 256, 0, stream>>>(w, Co, Ci, round_ops, dst);
+  } else {
+    pack_w3x3_cl_dgrad_kernel<<<dim3(ceil_div(Ci, 32), ceil_div(Co, 32), 9), 256, 0, stream>>>(w, Co, Ci, round_ops, dst);
+  }
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// split-K partials [nsplit][9][Co][Ci] -> channels-last weight gradient [Co][3][3][Ci]
+extern "C" int ag2v_unpack_dw3x3_cl(const float* part, int nsplit, int Co, int Ci, float* dw, cudaStream_t stream) {
+  AG2V_REQUIRE(part && dw && nsplit > 0 && Co > 0 && Ci > 0 && Ci % 4 == 0, "unpack_dw3x3_cl: bad arguments");
+  const long long total = 9LL * Co * (Ci / 4);
+  const int blocks = (int)(ceil_div_ll(total, 256) > 2368 ? 2368 : ceil_div_ll(total, 256));
+  unpack_dw_cl_kernel<<<blocks, 256, 0, stream>>>(part, nsplit, Co, Ci, dw);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

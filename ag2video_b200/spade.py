@@ -38,10 +38,13 @@ L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_i, c_p, c_p, c_p
 L.register('ag2v_unpack_dw3x3', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_i, c_ll, c_p, c_p])
 L.register('ag2v_round_tf32', c_i, [c_p, c_p, c_ll, c_p])
+L.register('ag2v_pack_w3x3_cl', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p])
+L.register('ag2v_unpack_dw3x3_cl', c_i, [c_p, c_i, c_i, c_i, c_p, c_p])
+L.register('ag2v_scaled_grad_pre', c_i, [c_p, c_p, c_ll, c_i, c_i, c_p, c_p, c_p, c_p])
 L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 6)
 L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p])
 L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_ll, c_ll, c_ll,
-                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_ll, c_p, c_p, c_sz, c_i, c_p])
+                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_ll, c_p, c_p, c_p, c_p, c_sz, c_i, c_p])
 L.register('ag2v_conv3x3_splitk_floats', c_sz, [c_i] * 5)
 L.register('ag2v_conv3x3_tc_supported', c_i, [c_i] * 6)
 
@@ -109,7 +112,7 @@ class _Timed:
 
 
 def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, epi, round_out=0,
-          x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None, group_pixels=0):
+          x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None, group_pixels=0, scale=None, res=None):
     lib = L.lib()
     nws = lib.ag2v_conv3x3_splitk_floats(B, Hh, Ww, Cin, Nout) if CONV_IMPL in (0, 2) else 0
     ws = torch.empty(nws, device=out.device, dtype=torch.float32) if nws else None
@@ -117,8 +120,8 @@ def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, ep
         L.check(lib.ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
                                  L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
                                  out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
-                                 L.ptr(gamma_out), float(slope), C, group_pixels, L.ptr(gate), L.ptr(ws), nws, CONV_IMPL,
-                                 L.stream()))
+                                 L.ptr(gamma_out), float(slope), C, group_pixels, L.ptr(scale), L.ptr(res), L.ptr(gate),
+                                 L.ptr(ws), nws, CONV_IMPL, L.stream()))
 
 
 def _pack(wa, wb, ba, bb, dgrad):
@@ -189,7 +192,8 @@ class _SharedSegFn(torch.autograd.Function):
 
 class _SpadeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, seg, token, w_sh, b_sh, w_g, b_g, w_b, b_b, mod, shared, slope, groups=1):
+    def forward(ctx, x, seg, token, w_sh, b_sh, w_g, b_g, w_b, b_b, mod, shared, slope, groups=1, next_scale=None,
+                round_out=False):
         L.need_cuda(x, seg, w_sh)
         lib = L.lib()
         dev = x.device
@@ -208,7 +212,7 @@ class _SpadeFn(torch.autograd.Function):
         bn = mod.param_free_norm
         if B % groups:
             raise ValueError('SPADE: batch %d is not a multiple of groups=%d' % (B, groups))
-        G = groups if training else 1              # statistics per group of B/G images (one reference call each)
+        G = groups                                 # statistics per group of B/G images (one reference call each)
         Pg = P // G
         mean = torch.empty(G * C, device=dev, dtype=torch.float32)
         rstd = torch.empty(G * C, device=dev, dtype=torch.float32)
@@ -226,6 +230,9 @@ class _SpadeFn(torch.autograd.Function):
         else:
             L.check(lib.ag2v_bn_eval_stats(L.ptr(bn.running_mean), L.ptr(bn.running_var), C, bn.eps, L.ptr(mean),
                                            L.ptr(rstd), L.stream()))
+            if G > 1:                              # same running estimates for every group
+                mean[C:].view(G - 1, C).copy_(mean[:C])
+                rstd[C:].view(G - 1, C).copy_(rstd[:C])
         pk = mod._packed(w_sh, b_sh, w_g, b_g, w_b, b_b)
         actv = torch.empty(B, r, rw, NHIDDEN, device=dev, dtype=torch.float32)
         _conv(seg, seg_strides, B, r, rw, Lc, pk['w1'], pk['b1'], NHIDDEN, actv, (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN),
@@ -234,17 +241,17 @@ class _SpadeFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         gamma = torch.empty(B, r, rw, C, device=dev, dtype=torch.float32) if need_grad else None
         _conv(actv, (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN), B, r, rw, NHIDDEN, pk['w2'], pk['b2'], 2 * C, out,
-              (r * rw * C, rw * C, C), EPI_SPADE, x=x, mean=mean, rstd=rstd, gamma_out=gamma, slope=slope, C=C,
-              group_pixels=Pg if G > 1 else 0)
+              (r * rw * C, rw * C, C), EPI_SPADE, round_out=int(round_out and not _precise()), x=x, mean=mean, rstd=rstd,
+              gamma_out=gamma, slope=slope, C=C, group_pixels=Pg if G > 1 else 0)
         if need_grad:
-            ctx.save_for_backward(x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b)
+            ctx.save_for_backward(x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b, next_scale)
         ctx.meta = (B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G)
         ctx.mod, ctx.shared = mod, shared
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b = ctx.saved_tensors
+        x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b, next_scale = ctx.saved_tensors
         B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G = ctx.meta
         Pg = P // G
         mod, shared = ctx.mod, ctx.shared
@@ -254,13 +261,17 @@ class _SpadeFn(torch.autograd.Function):
         act = 0 if slope == 1.0 else 1
         dgb = torch.empty(P, 2 * C, device=dev, dtype=torch.float32)
         dx = torch.empty(B, C, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
-        part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 4), device=dev, dtype=torch.float32)
-        sums = torch.empty(G * 4 * C, device=dev, dtype=torch.float64)
+        part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 5), device=dev, dtype=torch.float32)
+        sums = torch.empty(G * 5 * C, device=dev, dtype=torch.float64)
         L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), Pg, C, G,
                                        act, float(slope), int(not _precise()), 0, L.ptr(dgb), L.ptr(dx), L.ptr(part),
                                        L.ptr(sums), L.stream()))
         db = torch.empty(2 * C, device=dev, dtype=torch.float32)     # [sum g | sum g*xhat] = [d bias_beta | d bias_gamma]
-        L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 4 * C, L.ptr(db), L.stream()))
+        L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 5 * C, L.ptr(db), L.stream()))
+        dscale = None
+        if next_scale is not None and ctx.needs_input_grad[13]:
+            # y = conv(out) * scale_g: d scale_g = <dy_g, conv(out)_g> = <dout_g, out_g> / scale_g  (adjoint of the conv)
+            dscale = (sums.view(G, 5, C)[:, 4].sum(dim=1) / next_scale.double()).float()
         if training:
             dist, world = _world()
             if world > 1:              # db (local sums) is already extracted; the BN backward needs global sums
@@ -290,7 +301,97 @@ class _SpadeFn(torch.autograd.Function):
                 dseg = buf
             _conv(dactv, a_strides, B, r, rw, NHIDDEN, pkt['w1t'], None, Lc, buf, seg_strides, EPI_ACCUM)
         dtoken = torch.zeros(1, device=dev) if (shared is not None and ctx.needs_input_grad[2]) else None
-        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None
+        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None, dscale, None
+
+
+def _packed_cl(conv, w, dgrad):
+    """[9][Co][Ci] (or the transposed + flipped dgrad form) of a channels_last 3x3 weight, rounded to
+    TF32; cached on the module until the weight changes."""
+    key = (w.data_ptr(), w._version, _precise())
+    cache = conv.__dict__.setdefault('_ag2v_pk', {})
+    if cache.get('key') != key:
+        cache.clear()
+        cache['key'] = key
+    if dgrad not in cache:
+        Co, Ci = w.shape[0], w.shape[1]
+        dst = torch.empty(9 * Co * Ci, device=w.device, dtype=torch.float32)
+        L.check(L.lib().ag2v_pack_w3x3_cl(L.ptr(w), Co, Ci, int(dgrad), int(not _precise()), L.ptr(dst), L.stream()))
+        cache[dgrad] = dst
+    return cache[dgrad]
+
+
+class _SnConvFn(torch.autograd.Function):
+    """y = conv3x3(x, weight) * scale[group] + bias (+ res): a spectrally normalised 3x3 convolution
+    of SPADEResnetBlock (architecture.py:34-41,56-62) evaluated on weight_orig, 1/sigma applied in
+    the GEMM epilogue together with the bias and the residual sum.  ``scale`` gets its gradient
+    from the SPADE layer that produced ``x`` (SPADE.forward(next_scale=...)), not from here."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, scale, res, conv, groups):
+        L.need_cuda(x, weight)
+        dev = x.device
+        B, Cin, r, rw = x.shape
+        Nout = weight.shape[0]
+        if not x.is_contiguous(memory_format=torch.channels_last) or x.dtype != torch.float32:
+            raise RuntimeError('sn_conv3x3: x must be a float32 channels_last tensor')
+        if res is not None:
+            res = _cl(res.float())
+        out = torch.empty(B, Nout, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
+        Pg = B * r * rw // groups
+        wpk = _packed_cl(conv, weight, False)
+        _conv(x, (r * rw * Cin, rw * Cin, Cin), B, r, rw, Cin, wpk, bias, Nout, out, (r * rw * Nout, rw * Nout, Nout), EPI_BIAS,
+              group_pixels=Pg if groups > 1 else 0, scale=scale, res=res)
+        ctx.save_for_backward(x, weight, scale)
+        ctx.meta = (B, Cin, r, rw, Nout, groups, bias is not None, res is not None)
+        ctx.conv = conv
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, scale = ctx.saved_tensors
+        B, Cin, r, rw, Nout, G, has_bias, has_res = ctx.meta
+        lib = L.lib()
+        dev = x.device
+        dy = _cl(dy.float())
+        Pg = B * r * rw // G
+        dys = torch.empty_like(dy, memory_format=torch.channels_last)
+        part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, Nout, 1), device=dev, dtype=torch.float32)
+        sums = torch.empty(G * Nout, device=dev, dtype=torch.float64)
+        L.check(lib.ag2v_scaled_grad_pre(L.ptr(dy), L.ptr(scale), Pg, Nout, G, L.ptr(dys), L.ptr(part), L.ptr(sums), L.stream()))
+        dbias = None
+        if has_bias:
+            dbias = torch.empty(Nout, device=dev, dtype=torch.float32)
+            L.check(lib.ag2v_double_to_float(L.ptr(sums), Nout, G, Nout, L.ptr(dbias), L.stream()))
+        y_strides = (r * rw * Nout, rw * Nout, Nout)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, Cin, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
+            _conv(dys, y_strides, B, r, rw, Nout, _packed_cl(ctx.conv, weight, True), None, Cin, dx,
+                  (r * rw * Cin, rw * Cin, Cin), EPI_BIAS)
+        nsplit = lib.ag2v_wgrad3x3_nsplit(B, r, rw, Nout, Cin, CONV_IMPL)
+        wpart = torch.empty(nsplit * 9 * Nout * Cin, device=dev, dtype=torch.float32)
+        with _Timed('wgrad3x3', 2.0 * 9 * B * r * rw * Cin * Nout, ('wgrad', r, Cin, Nout)):
+            L.check(lib.ag2v_wgrad3x3(L.ptr(dys), Nout, L.ptr(x), r * rw * Cin, rw * Cin, Cin, Cin, B, r, rw, L.ptr(wpart),
+                                      CONV_IMPL, L.stream()))
+        dw = torch.empty_like(weight, memory_format=torch.channels_last)
+        L.check(lib.ag2v_unpack_dw3x3_cl(L.ptr(wpart), nsplit, Nout, Cin, L.ptr(dw), L.stream()))
+        return dx, dw, dbias, None, (dy if has_res else None), None, None
+
+
+def sn_conv3x3(conv, x, groups=1, res=None):
+    """``conv(x) (+ res)`` for a spectrally normalised 3x3 nn.Conv2d in sigma mode on the tcgen05
+    implicit-GEMM kernel; ``x`` must come from ``SPADE.forward(..., next_scale=scale, round_out=True)``."""
+    entry = conv.__dict__['_ag2v_sn_entry']
+    return _SnConvFn.apply(x, getattr(conv, entry.name + '_orig'), conv.bias, entry.scale_g, res, conv, int(groups))
+
+
+def sn_conv3x3_usable(conv, x):
+    entry = conv.__dict__.get('_ag2v_sn_entry')
+    w = getattr(conv, entry.name + '_orig', None) if entry is not None else None
+    return (entry is not None and entry.scale_g is not None and w is not None and tuple(w.shape[2:]) == (3, 3)
+            and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and w.shape[1] % 4 == 0 and w.shape[0] % 4 == 0
+            and w.is_contiguous(memory_format=torch.channels_last) and x.is_cuda)
 
 
 class _BnActFn(torch.autograd.Function):
@@ -342,13 +443,13 @@ class _BnActFn(torch.autograd.Function):
         dev = x.device
         dout = _cl(dout.float())
         dx = torch.empty_like(x, memory_format=torch.channels_last)
-        part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 4), device=dev, dtype=torch.float32)
-        sums = torch.empty(G * 4 * C, device=dev, dtype=torch.float64)
+        part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 5), device=dev, dtype=torch.float32)
+        sums = torch.empty(G * 5 * C, device=dev, dtype=torch.float64)
         L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(y), L.ptr(x), L.ptr(w), L.ptr(mean), L.ptr(rstd), Pg, C, G,
                                        0 if slope == 1.0 else 1, float(slope), 0, 1, None, L.ptr(dx), L.ptr(part),
                                        L.ptr(sums), L.stream()))
         db = torch.empty(2 * C, device=dev, dtype=torch.float32)           # [d bias | d weight]
-        L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 4 * C, L.ptr(db), L.stream()))
+        L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 5 * C, L.ptr(db), L.stream()))
         if training:
             dist, world = _world()
             if world > 1:
@@ -419,15 +520,18 @@ class SPADE(nn.Module):
             self._pkt = dict(key=key, w1t=w1t, w2t=w2t)
         return self._pkt
 
-    def forward(self, x, segmap, groups=1):
+    def forward(self, x, segmap, groups=1, next_scale=None, round_out=False):
         """``groups`` > 1: the batch holds that many reference calls (group-major); batch statistics
-        and running-stat updates are per group, as if the layer were called once per group."""
+        and running-stat updates are per group, as if the layer were called once per group.
+        ``next_scale`` [groups]: the 1/sigma vector of the scaled convolution (``sn_conv3x3``) that
+        consumes this output; its gradient is produced here, from sums the backward makes anyway.
+        ``round_out``: store the output rounded to TF32 (operand of a tcgen05 convolution)."""
         shared = segmap if isinstance(segmap, SharedSeg) else None
         seg = shared.seg if shared is not None else segmap
         token = shared.token if shared is not None else None
         return _SpadeFn.apply(x, seg, token, self.mlp_shared[0].weight, self.mlp_shared[0].bias,
                               self.mlp_gamma.weight, self.mlp_gamma.bias, self.mlp_beta.weight, self.mlp_beta.bias,
-                              self, shared, float(self.fused_slope), int(groups))
+                              self, shared, float(self.fused_slope), int(groups), next_scale, bool(round_out))
 
 
 class SPADEResnetBlock(nn.Module):
@@ -465,6 +569,13 @@ class SPADEResnetBlock(nn.Module):
         if not isinstance(seg, SharedSeg):
             seg = SharedSeg.wrap(seg)
         x_s = conv_scaled(self.conv_s, self.norm_s(x, seg, groups)) if self.learned_shortcut else x
+        if sn_conv3x3_usable(self.conv_0, x) and sn_conv3x3_usable(self.conv_1, x):
+            # sigma mode: the 3x3 convolutions run on the tcgen05 kernel with 1/sigma, bias and the
+            # residual sum in the epilogue; d(1/sigma) comes out of the SPADE backward
+            sc0 = self.conv_0.__dict__['_ag2v_sn_entry'].scale_g
+            sc1 = self.conv_1.__dict__['_ag2v_sn_entry'].scale_g
+            dx = sn_conv3x3(self.conv_0, self.norm_0(x, seg, groups, next_scale=sc0, round_out=True), groups)
+            return sn_conv3x3(self.conv_1, self.norm_1(dx, seg, groups, next_scale=sc1, round_out=True), groups, res=x_s)
         dx = conv_scaled(self.conv_0, self.norm_0(x, seg, groups))
         dx = conv_scaled(self.conv_1, self.norm_1(dx, seg, groups))
         return x_s + dx

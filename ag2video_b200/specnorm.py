@@ -169,11 +169,12 @@ def spectral_normalize(weights, us, vs, training=True, eps=1e-12):
 
 
 class _Entry:
-    __slots__ = ('module', 'name', 'eps', 'fresh', 'scale')
+    __slots__ = ('module', 'name', 'eps', 'fresh', 'scale', 'scale_g')
 
     def __init__(self, module, name, eps):
         self.module, self.name, self.eps, self.fresh = module, name, eps, False
         self.scale = None          # sigma mode: [N,1,1,1] per-image 1/sigma of the current batched call
+        self.scale_g = None        # sigma mode: [groups] 1/sigma per frame group (contiguous)
 
     def tensors(self):
         m, n = self.module, self.name
@@ -191,7 +192,7 @@ def _compute(entries):
         for e, w in zip(es, outs):
             setattr(e.module, e.name, w)
             e.fresh = True
-            e.scale = None
+            e.scale = e.scale_g = None
 
 
 def _make_hook(entry):
@@ -239,9 +240,12 @@ class SpectralNormGroup:
         (training, eps), = modes
         trip = [e.tensors() for e in self.entries]
         sigma = spectral_sigmas([t[0] for t in trip], [t[1] for t in trip], [t[2] for t in trip], groups, training, eps)
-        inv_img = sigma.reciprocal().repeat_interleave(images_per_group, dim=0)      # [N, n]
+        inv = sigma.reciprocal()                                                     # [G, n]
+        inv_img = inv.repeat_interleave(images_per_group, dim=0)                     # [N, n]
+        inv_t = inv.t().contiguous()                                                 # [n, G]: rows are contiguous
         for i, e in enumerate(self.entries):
             e.scale = inv_img[:, i].view(-1, 1, 1, 1)
+            e.scale_g = inv_t[i]
             e.fresh = False
         return sigma
 
@@ -252,7 +256,7 @@ class SpectralNormGroup:
     def end_sigma(self):
         """Leave sigma mode (the autograd graph of the finished call keeps what it needs)."""
         for e in self.entries:
-            e.scale = None
+            e.scale = e.scale_g = None
 
 
 def conv_scaled(conv, x):

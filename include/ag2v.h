@@ -178,19 +178,24 @@ int ag2v_pack_w3x3(const float* wa, const float* wb, const float* ba, const floa
  * impl 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel, 3 = mma.sync with 3xTF32 products
  * (fp32-class accuracy, validation mode).  round_ops / round_out: round the stored GEMM operands
  * to nearest TF32 (the tcgen05 TF32 path truncates).  group_pixels > 0 (epilogue 2): mean / rstd
- * are [groups][C] and pixel p uses group p / group_pixels. */
+ * are [groups][C] and pixel p uses group p / group_pixels.  Epilogue 0 also takes scale [groups]
+ * (out = acc * scale[group] + bias, the 1/sigma of a spectrally normalised convolution evaluated
+ * on weight_orig, architecture.py:34-41) and res, a dense [P, Nout] tensor added to the result
+ * (the residual sum x_s + dx of SPADEResnetBlock, architecture.py:62); both may be NULL. */
 int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in_sx, int B, int Hh, int Ww, int Cin,
                  const float* wpk, const float* bias, int Nout, float* out, long long out_sb, long long out_sy,
                  long long out_sx, int epilogue, int round_out, const float* x, const float* mean,
-                 const float* rstd, float* gamma_out, float slope, int C, long long group_pixels, const float* gate,
-                 float* splitk_ws, size_t splitk_ws_floats, int impl, ag2v_stream_t stream);
+                 const float* rstd, float* gamma_out, float slope, int C, long long group_pixels, const float* scale,
+                 const float* res, const float* gate, float* splitk_ws, size_t splitk_ws_floats, int impl,
+                 ag2v_stream_t stream);
 /* split-K scratch (floats) that lets low-resolution layers use the whole chip; 0 = none needed */
 size_t ag2v_conv3x3_splitk_floats(int B, int Hh, int Ww, int Cin, int Nout);
 int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue);
 
 /* SPADE backward, element-wise: pass 1 produces d(gamma|beta) [P,2C], dxhat and the
- * per-channel sums [groups][4][C] (sum g, sum g*xhat, sum dxhat, sum dxhat*xhat); pass 2 turns
- * dxhat into dx (batch-norm backward) in place.  chan_gamma = 1: `gamma` is a per-channel scale
+ * per-channel sums [groups][5][C] (sum g, sum g*xhat, sum dxhat, sum dxhat*xhat, sum dout*out);
+ * pass 2 turns dxhat into dx (batch-norm backward) in place.  The fifth sum, added over channels
+ * and divided by the group's scale, is d(scale) of the scaled convolution that consumed `out`.  chan_gamma = 1: `gamma` is a per-channel scale
  * [C] (affine batch norm) and dgb may be NULL. */
 int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma, const float* mean,
                        const float* rstd, long long P, int C, int groups, int act, float slope, int round_ops,
@@ -205,6 +210,13 @@ int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, lon
                   int B, int Hh, int Ww, float* part, int impl, ag2v_stream_t stream);
 int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
                       ag2v_stream_t stream);
+/* Main convolutions of SPADEResnetBlock (architecture.py:34-41,56-62) on the same implicit-GEMM
+ * kernels: channels-last weight (un)packing and the pre-pass over the output gradient. */
+int ag2v_pack_w3x3_cl(const float* w, int Co, int Ci, int dgrad, int round_ops, float* dst, ag2v_stream_t stream);
+int ag2v_unpack_dw3x3_cl(const float* part, int nsplit, int Co, int Ci, float* dw, ag2v_stream_t stream);
+/* dys = tf32(dy * scale[group]) on [groups][P][C]; sums[g][0..C) = sum dy (doubles) */
+int ag2v_scaled_grad_pre(const float* dy, const float* scale, long long P, int C, int groups, float* dys,
+                         float* partial, double* sums, ag2v_stream_t stream);
 /* dst[i] = (float) sum over groups of src[g * group_stride + i] */
 int ag2v_double_to_float(const double* src, int n, int groups, long long group_stride, float* dst,
                          ag2v_stream_t stream);

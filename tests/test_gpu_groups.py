@@ -163,3 +163,46 @@ def test_generator_batched_frames_equal_frame_loop():
             assert max_rel(s1[k], s0[k]) <= 1e-4, (k, max_rel(s1[k], s0[k]))
     finally:
         sp.CONV_IMPL = old
+
+
+@pytest.mark.parametrize('impl,tol', [(3, 2e-4), (0, 2e-2)])
+@pytest.mark.parametrize('fin,fout', [(64, 64), (128, 64)])
+def test_resnet_block_sigma_mode_equals_successive_calls(fin, fout, impl, tol):
+    """SPADEResnetBlock on a group-major batch in sigma mode (3x3 convolutions on the tcgen05
+    kernel with 1/sigma, bias and residual in the epilogue, d sigma out of the SPADE backward)
+    vs G successive calls through the spectral-norm hooks and cuDNN."""
+    import ag2video_b200.spade as sp
+    G, B, r, Hs = 3, 2, 16, 32
+    opt = make_opt(64)
+    old = sp.CONV_IMPL
+    sp.CONV_IMPL = impl
+    try:
+        blocks = []
+        for _ in range(2):
+            blk = sp.SPADEResnetBlock(fin, fout, opt)
+            blk.load_state_dict(det_state(blk.state_dict(), 9))
+            blocks.append(blk.cuda().to(memory_format=torch.channels_last).train())
+        b1, b2 = blocks
+        x = _rand(G * B, fin, r, r, seed=1, cl=True).requires_grad_()
+        seg = _rand(G * B, opt.semantic_nc, Hs, Hs, seed=2, cl=True).requires_grad_()
+        cot = _rand(G * B, fout, r, r, seed=3, cl=True)
+        b1._sn.refresh_sigma(G, B)
+        out = b1(x, seg, groups=G)
+        b1._sn.end_sigma()
+        (out * cot).sum().backward()
+        got = {'out': out.detach(), 'dx': x.grad.clone(), 'dseg': seg.grad.clone()}
+        got.update({k: p.grad.clone() for k, p in b1.named_parameters()})
+        x.grad = seg.grad = None
+        ref = torch.cat([b2(x[g * B:(g + 1) * B], seg[g * B:(g + 1) * B]) for g in range(G)], dim=0)
+        (ref * cot).sum().backward()
+        want = {'out': ref.detach(), 'dx': x.grad, 'dseg': seg.grad}
+        want.update({k: p.grad for k, p in b2.named_parameters()})
+        assert got.keys() == want.keys()
+        for k in want:
+            err = rel_l2(got[k], want[k]) if impl == 0 else max_rel(got[k], want[k])
+            assert err <= tol, (k, err)
+        for (k, a), (_, b) in zip(b1.state_dict().items(), b2.state_dict().items()):
+            if k.endswith(('_u', '_v', 'running_mean', 'running_var')):
+                assert max_rel(a, b) <= 1e-4, (k, max_rel(a, b))
+    finally:
+        sp.CONV_IMPL = old
