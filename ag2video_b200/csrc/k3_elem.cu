@@ -176,32 +176,42 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const float* __restric
 // unbiased for the running estimate (sync_batchnorm/batchnorm.py:63-68,128-145).
 // With G groups the running estimates are updated G times in group order, exactly as G
 // successive calls of the layer would.
+// in_scale (optional, [G]): the layer's input is s_g * x but the statistics were taken on x (a
+// spectrally normalised convolution evaluated on weight_orig, 1/sigma_g not yet applied).
+// BN(s x; eps) == BN(x; eps / s^2), so only eps and the running estimates change and the
+// multiplication by s never touches the activation.
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, int G, float eps, float momentum,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ mean, float* __restrict__ rstd) {
+                                   const float* __restrict__ in_scale, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ mean, float* __restrict__ rstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   for (int g = 0; g < G; ++g) {
+    const double sc = in_scale ? (double)in_scale[g] : 1.0;
     const double m = sums[(size_t)g * 2 * C + c] / count;
     double var = sums[(size_t)g * 2 * C + C + c] / count - m * m;
     if (var < 0.0) var = 0.0;
     mean[(size_t)g * C + c] = (float)m;
-    rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps / (sc * sc)));
     if (running_mean != nullptr) {
       const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
-      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+      running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * sc * m);
+      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * sc * sc * unbiased);
     }
   }
 }
 
 // eval mode: statistics are the running estimates
+// (with in_scale: (s x - rm) / sqrt(rv + eps) == (x - rm / s) * (s / sqrt(rv + eps)), per group)
 __global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
-                                     int C, float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+                                     int C, int G, float eps, const float* __restrict__ in_scale,
+                                     float* __restrict__ mean, float* __restrict__ rstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  mean[c] = running_mean[c];
-  rstd[c] = 1.f / sqrtf(running_var[c] + eps);
+  for (int g = 0; g < G; ++g) {
+    const float sc = in_scale ? in_scale[g] : 1.f;
+    mean[(size_t)g * C + c] = running_mean[c] / sc;
+    rstd[(size_t)g * C + c] = sc / sqrtf(running_var[c] + eps);
+  }
 }
 
 // pass 2 of the SPADE backward: batch-norm input gradient, in place on dxhat.
@@ -417,18 +427,19 @@ extern "C" int ag2v_bn_stats(const float* x, long long P, int C, int groups, flo
 // mean/rstd from (possibly all-reduced) sums; updates running stats when given.
 // sums [groups][2C] -> mean / rstd [groups][C]; count = elements per channel in ONE group.
 extern "C" int ag2v_bn_finalize(const double* sums, double count, int C, int groups, float eps, float momentum,
-                                float* running_mean, float* running_var, float* mean, float* rstd,
-                                cudaStream_t stream) {
+                                const float* in_scale, float* running_mean, float* running_var, float* mean,
+                                float* rstd, cudaStream_t stream) {
   AG2V_REQUIRE(sums && mean && rstd && C > 0 && count > 0 && groups >= 1, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(sums, count, C, groups, eps, momentum, running_mean, running_var, mean, rstd);
+  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(sums, count, C, groups, eps, momentum, in_scale, running_mean,
+                                                          running_var, mean, rstd);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
 
-extern "C" int ag2v_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
-                                  float* mean, float* rstd, cudaStream_t stream) {
-  AG2V_REQUIRE(running_mean && running_var && mean && rstd && C > 0, "bn_eval_stats: bad arguments");
-  bn_eval_stats_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(running_mean, running_var, C, eps, mean, rstd);
+extern "C" int ag2v_bn_eval_stats(const float* running_mean, const float* running_var, int C, int groups, float eps,
+                                  const float* in_scale, float* mean, float* rstd, cudaStream_t stream) {
+  AG2V_REQUIRE(running_mean && running_var && mean && rstd && C > 0 && groups >= 1, "bn_eval_stats: bad arguments");
+  bn_eval_stats_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(running_mean, running_var, C, groups, eps, in_scale, mean, rstd);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

@@ -22,7 +22,7 @@ from torch.nn.utils import spectral_norm
 from .graph import GraphTripleConv
 from .layout import boxes_to_layout_batched, layout_conv3x3, layout_tables
 from .spade import SPADEResnetBlock, SharedSeg, bn_act
-from .specnorm import SpectralNormGroup, conv_scaled
+from .specnorm import SpectralNormGroup, conv_scaled, conv_unscaled
 
 CL = torch.channels_last
 
@@ -121,9 +121,9 @@ class _BN2d(nn.Module):
         self.register_buffer('running_var', torch.ones(c))
         self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
 
-    def forward(self, x, groups=1, slope=1.0):
+    def forward(self, x, groups=1, slope=1.0, in_scale=None):
         return bn_act(x, self.weight, self.bias, self.running_mean, self.running_var, self.training, 0.1, 1e-5,
-                      slope=slope, groups=groups)
+                      slope=slope, groups=groups, in_scale=in_scale)
 
 
 def _sn_conv_bn(cin, cout, stride=1):
@@ -165,12 +165,14 @@ class FlowsGenerator(nn.Module):
     @staticmethod
     def _stage(conv_bn, x, groups, first=None):
         """conv -> BN -> LeakyReLU(0.2); ``first`` = the convolution's output computed elsewhere."""
-        z = conv_scaled(conv_bn[0], x) if first is None else first
-        return conv_bn[1](z, groups, 0.2)
+        if first is not None:
+            return conv_bn[1](first[0], groups, 0.2, in_scale=first[1])
+        z, scale = conv_unscaled(conv_bn[0], x)
+        return conv_bn[1](z, groups, 0.2, in_scale=scale)
 
     def features(self, label, groups=1, first=None):
-        """up_flow(res_flow(down_flow(label))).  ``first``: output of down_flow[0]'s convolution when
-        the caller evaluated it itself (the fused layout convolution)."""
+        """up_flow(res_flow(down_flow(label))).  ``first``: (output of down_flow[0]'s convolution,
+        its pending 1/sigma scale or None) when the caller evaluated it itself (fused layout conv)."""
         x = self._stage(self.down_flow[0], label, groups, first)
         for i in range(2, len(self.down_flow), 2):
             x = self._stage(self.down_flow[i], x, groups)
@@ -284,15 +286,15 @@ class Layout2VidGenerator(nn.Module):
             else:                                        # sigma mode: raw weight, output scaled per image
                 w = conv_bn[0].weight_orig
             base = F.conv2d(img, w[:, 2 * D:], padding=1).contiguous(memory_format=CL)
-            z = layout_conv3x3(w[:, :2 * D], slots, tables, base)
-            return z if entry.scale is None else z * entry.scale
+            return layout_conv3x3(w[:, :2 * D], slots, tables, base), entry.scale_g     # 1/sigma is folded into the BN
 
         feat = fn.features(None, groups, first=layout_conv(flow_cb, prev))
         flow = fn.conv_flow(feat) * fn.flow_multiplier
         warped = flow_warp(prev[:, -3:], flow)
         diff = prev[:, -3:] - warped
         conf = ((diff * diff).sum(dim=1, keepdim=True) < 0.02).float()
-        y = in_cb[1](layout_conv(in_cb, warped.contiguous(memory_format=CL)), groups, 0.2)
+        z, z_scale = layout_conv(in_cb, warped.contiguous(memory_format=CL))
+        y = in_cb[1](z, groups, 0.2, in_scale=z_scale)
         return self.netG(y, groups) + warped, flow, conf
 
     def forward_fused(self, imgs_gt, objs, obj_vecs, layout, test_mode=False):

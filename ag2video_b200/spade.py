@@ -29,9 +29,9 @@ c_d = L.ctypes.c_double
 
 L.register('ag2v_chan_partial_floats', c_sz, [c_ll, c_i, c_i])
 L.register('ag2v_bn_stats', c_i, [c_p, c_ll, c_i, c_i, c_p, c_p, c_p])
-L.register('ag2v_bn_finalize', c_i, [c_p, c_d, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p])
+L.register('ag2v_bn_finalize', c_i, [c_p, c_d, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p])
 L.register('ag2v_bn_act_fwd', c_i, [c_p] * 5 + [c_ll, c_i, c_i, c_f, c_p, c_p])
-L.register('ag2v_bn_eval_stats', c_i, [c_p, c_p, c_i, c_f, c_p, c_p, c_p])
+L.register('ag2v_bn_eval_stats', c_i, [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_p])
 L.register('ag2v_spade_bwd_pre', c_i, [c_p] * 6 + [c_ll, c_i, c_i, c_i, c_f, c_i, c_i] + [c_p] * 4 + [c_p])
 L.register('ag2v_spade_bwd_dx', c_i, [c_p] * 5 + [c_d, c_i, c_ll, c_i, c_i, c_p])
 L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_i, c_p, c_p, c_p])
@@ -225,14 +225,12 @@ class _SpadeFn(torch.autograd.Function):
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
                 count = float(Pg * world)
-            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, G, bn.eps, bn.momentum, L.ptr(bn.running_mean),
+            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, G, bn.eps, bn.momentum, None, L.ptr(bn.running_mean),
                                          L.ptr(bn.running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
-        else:
-            L.check(lib.ag2v_bn_eval_stats(L.ptr(bn.running_mean), L.ptr(bn.running_var), C, bn.eps, L.ptr(mean),
+        else:                                      # same running estimates for every group
+            L.check(lib.ag2v_bn_eval_stats(L.ptr(bn.running_mean), L.ptr(bn.running_var), C, G, bn.eps, None, L.ptr(mean),
                                            L.ptr(rstd), L.stream()))
-            if G > 1:                              # same running estimates for every group
-                mean[C:].view(G - 1, C).copy_(mean[:C])
-                rstd[C:].view(G - 1, C).copy_(rstd[:C])
+        _cache_of(mod).forward_begin()
         pk = mod._packed(w_sh, b_sh, w_g, b_g, w_b, b_b)
         actv = torch.empty(B, r, rw, NHIDDEN, device=dev, dtype=torch.float32)
         _conv(seg, seg_strides, B, r, rw, Lc, pk['w1'], pk['b1'], NHIDDEN, actv, (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN),
@@ -255,6 +253,7 @@ class _SpadeFn(torch.autograd.Function):
         B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G = ctx.meta
         Pg = P // G
         mod, shared = ctx.mod, ctx.shared
+        _cache_of(mod).backward_seen()
         lib = L.lib()
         dev = x.device
         dout = _cl(dout.float())
@@ -304,20 +303,48 @@ class _SpadeFn(torch.autograd.Function):
         return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None, dscale, None
 
 
+class _PackCache:
+    """Packed (GEMM-layout, TF32-rounded) copies of a module's weights.  Keyed on the tensors'
+    (data_ptr, _version) AND on an epoch that advances at the first forward after a backward:
+    fused optimizers (torch.optim.Adam(fused=True)) update parameters without bumping _version,
+    so "a backward has happened" is the signal that the weights may have changed.  Within one
+    epoch (the forward(s) and backward(s) of one step) every pack is built at most once."""
+
+    def __init__(self):
+        self.epoch, self.dirty, self.store = 0, False, {}
+
+    def forward_begin(self):
+        if self.dirty:
+            self.epoch += 1
+            self.dirty = False
+
+    def backward_seen(self):
+        self.dirty = True
+
+    def get(self, name, tensors, build):
+        key = (self.epoch, _precise()) + tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+        hit = self.store.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, build())
+            self.store[name] = hit
+        return hit[1]
+
+
+def _cache_of(module):
+    cache = module.__dict__.get('_ag2v_packs')
+    if cache is None:
+        cache = module.__dict__['_ag2v_packs'] = _PackCache()
+    return cache
+
+
 def _packed_cl(conv, w, dgrad):
-    """[9][Co][Ci] (or the transposed + flipped dgrad form) of a channels_last 3x3 weight, rounded to
-    TF32; cached on the module until the weight changes."""
-    key = (w.data_ptr(), w._version, _precise())
-    cache = conv.__dict__.setdefault('_ag2v_pk', {})
-    if cache.get('key') != key:
-        cache.clear()
-        cache['key'] = key
-    if dgrad not in cache:
+    """[9][Co][Ci] (or the transposed + flipped dgrad form) of a channels_last 3x3 weight, rounded to TF32."""
+    def build():
         Co, Ci = w.shape[0], w.shape[1]
         dst = torch.empty(9 * Co * Ci, device=w.device, dtype=torch.float32)
         L.check(L.lib().ag2v_pack_w3x3_cl(L.ptr(w), Co, Ci, int(dgrad), int(not _precise()), L.ptr(dst), L.stream()))
-        cache[dgrad] = dst
-    return cache[dgrad]
+        return dst
+    return _cache_of(conv).get('dgrad' if dgrad else 'fwd', (w,), build)
 
 
 class _SnConvFn(torch.autograd.Function):
@@ -338,6 +365,7 @@ class _SnConvFn(torch.autograd.Function):
             res = _cl(res.float())
         out = torch.empty(B, Nout, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
         Pg = B * r * rw // groups
+        _cache_of(conv).forward_begin()
         wpk = _packed_cl(conv, weight, False)
         _conv(x, (r * rw * Cin, rw * Cin, Cin), B, r, rw, Cin, wpk, bias, Nout, out, (r * rw * Nout, rw * Nout, Nout), EPI_BIAS,
               group_pixels=Pg if groups > 1 else 0, scale=scale, res=res)
@@ -350,6 +378,7 @@ class _SnConvFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight, scale = ctx.saved_tensors
         B, Cin, r, rw, Nout, G, has_bias, has_res = ctx.meta
+        _cache_of(ctx.conv).backward_seen()
         lib = L.lib()
         dev = x.device
         dy = _cl(dy.float())
@@ -395,12 +424,14 @@ def sn_conv3x3_usable(conv, x):
 
 
 class _BnActFn(torch.autograd.Function):
-    """act(batch_norm(x) * weight + bias) on an NHWC batch of ``groups`` reference calls
+    """act(batch_norm(in_scale_g * x) * weight + bias) on an NHWC batch of ``groups`` reference calls
     (group-major), statistics and running-stat updates per group: the conv -> SyncBN ->
-    LeakyReLU(0.2) stages around the SPADE generator (normalization.py:16-50)."""
+    LeakyReLU(0.2) stages around the SPADE generator (normalization.py:16-50).  ``in_scale``
+    ([groups], optional) is the 1/sigma of the spectrally normalised convolution that produced x
+    on weight_orig; it is folded into eps (BN(s x; eps) == BN(x; eps / s^2)), never multiplied in."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, slope, groups):
+    def forward(ctx, x, weight, bias, in_scale, running_mean, running_var, training, momentum, eps, slope, groups):
         L.need_cuda(x, weight, bias)
         lib = L.lib()
         dev = x.device
@@ -410,8 +441,9 @@ class _BnActFn(torch.autograd.Function):
             raise NotImplementedError('bn_act: channels %% 4 == 0 and batch %% groups == 0 required (got C=%d, B=%d, groups=%d)'
                                       % (C, B, groups))
         P = B * H * W
-        G = groups if training else 1
+        G = groups if (training or in_scale is not None) else 1
         Pg = P // G
+        sc = L.f32c(in_scale.detach()) if in_scale is not None else None
         mean = torch.empty(G * C, device=dev, dtype=torch.float32)
         rstd = torch.empty(G * C, device=dev, dtype=torch.float32)
         count = float(Pg)
@@ -423,22 +455,23 @@ class _BnActFn(torch.autograd.Function):
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
                 count = float(Pg * world)
-            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, G, eps, momentum, L.ptr(running_mean), L.ptr(running_var),
-                                         L.ptr(mean), L.ptr(rstd), L.stream()))
+            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, G, eps, momentum, L.ptr(sc), L.ptr(running_mean),
+                                         L.ptr(running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
         else:
-            L.check(lib.ag2v_bn_eval_stats(L.ptr(running_mean), L.ptr(running_var), C, eps, L.ptr(mean), L.ptr(rstd), L.stream()))
+            L.check(lib.ag2v_bn_eval_stats(L.ptr(running_mean), L.ptr(running_var), C, G, eps, L.ptr(sc), L.ptr(mean),
+                                           L.ptr(rstd), L.stream()))
         w, b = L.f32c(weight), L.f32c(bias)
         y = torch.empty_like(x, memory_format=torch.channels_last)
         L.check(lib.ag2v_bn_act_fwd(L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(w), L.ptr(b), Pg, C, G, float(slope), L.ptr(y),
                                     L.stream()))
-        ctx.save_for_backward(x, y, mean, rstd, w)
-        ctx.meta = (C, Pg, G, count, training, slope)
+        ctx.save_for_backward(x, y, mean, rstd, w, sc)
+        ctx.meta = (C, Pg, G, count, training, slope, eps)
         return y
 
     @staticmethod
     def backward(ctx, dout):
-        x, y, mean, rstd, w = ctx.saved_tensors
-        C, Pg, G, count, training, slope = ctx.meta
+        x, y, mean, rstd, w, sc = ctx.saved_tensors
+        C, Pg, G, count, training, slope, eps = ctx.meta
         lib = L.lib()
         dev = x.device
         dout = _cl(dout.float())
@@ -450,17 +483,27 @@ class _BnActFn(torch.autograd.Function):
                                        L.ptr(sums), L.stream()))
         db = torch.empty(2 * C, device=dev, dtype=torch.float32)           # [d bias | d weight]
         L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 5 * C, L.ptr(db), L.stream()))
+        dscale = None
+        if sc is not None and ctx.needs_input_grad[3]:
+            # sums[g] = [sum g, sum g xhat, sum dxhat, sum dxhat xhat, .] with dxhat = g * weight
+            s = sums.view(G, 5, C)
+            r, m, s_ = rstd.view(G, C).double(), mean.view(G, C).double(), sc.double().view(G, 1)
+            if training:     # y depends on s only through rstd = (var + eps / s^2)^-1/2:  dy/ds = xhat w rstd^2 eps / s^3
+                dscale = (eps * (r * r * s[:, 3]).sum(dim=1) / s_.view(G) ** 3).float()
+            else:            # y = (s x - rm) r0 w + b with r0 = rstd / s:  dy/ds = x r0 w,  x = xhat / rstd + mean
+                dscale = ((r / s_) * (s[:, 3] / r + m * s[:, 2])).sum(dim=1).float()
         if training:
             dist, world = _world()
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
         L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
                                       int(training), Pg, C, G, L.stream()))
-        return dx, db[C:], db[:C], None, None, None, None, None, None, None
+        return dx, db[C:], db[:C], dscale, None, None, None, None, None, None, None
 
 
-def bn_act(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5, slope=1.0, groups=1):
-    return _BnActFn.apply(x, weight, bias, running_mean, running_var, bool(training), float(momentum), float(eps),
+def bn_act(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5, slope=1.0, groups=1,
+           in_scale=None):
+    return _BnActFn.apply(x, weight, bias, in_scale, running_mean, running_var, bool(training), float(momentum), float(eps),
                           float(slope), int(groups))
 
 
@@ -497,28 +540,20 @@ class SPADE(nn.Module):
         self.mlp_gamma = nn.Conv2d(NHIDDEN, norm_nc, kernel_size=3, padding=1)
         self.mlp_beta = nn.Conv2d(NHIDDEN, norm_nc, kernel_size=3, padding=1)
         self.fused_slope = 1.0
-        self._pk = None
-        self._pkt = None
-
-    @staticmethod
-    def _key(*ts):
-        return tuple((t.data_ptr(), t._version) for t in ts)
 
     def _packed(self, w_sh, b_sh, w_g, b_g, w_b, b_b):
-        key = self._key(w_sh, b_sh, w_g, b_g, w_b, b_b) + (_precise(),)
-        if self._pk is None or self._pk['key'] != key:
+        def build():
             w1, b1 = _pack(w_sh.contiguous(), None, b_sh, None, False)
             w2, b2 = _pack(w_g.contiguous(), w_b.contiguous(), b_g, b_b, False)
-            self._pk = dict(key=key, w1=w1, b1=b1, w2=w2, b2=b2)
-        return self._pk
+            return dict(w1=w1, b1=b1, w2=w2, b2=b2)
+        return _cache_of(self).get('fwd', (w_sh, b_sh, w_g, b_g, w_b, b_b), build)
 
     def _packed_t(self, w_sh, w_g, w_b):
-        key = self._key(w_sh, w_g, w_b) + (_precise(),)
-        if self._pkt is None or self._pkt['key'] != key:
+        def build():
             w1t, _ = _pack(w_sh.contiguous(), None, None, None, True)
             w2t, _ = _pack(w_g.contiguous(), w_b.contiguous(), None, None, True)
-            self._pkt = dict(key=key, w1t=w1t, w2t=w2t)
-        return self._pkt
+            return dict(w1t=w1t, w2t=w2t)
+        return _cache_of(self).get('dgrad', (w_sh, w_g, w_b), build)
 
     def forward(self, x, segmap, groups=1, next_scale=None, round_out=False):
         """``groups`` > 1: the batch holds that many reference calls (group-major); batch statistics

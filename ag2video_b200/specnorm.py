@@ -271,3 +271,15 @@ def conv_scaled(conv, x):
     if conv.bias is None:
         return z * entry.scale
     return torch.addcmul(conv.bias.view(1, -1, 1, 1), z, entry.scale)
+
+
+def conv_unscaled(conv, x):
+    """(z, scale): in sigma mode z = conv on weight_orig (no bias allowed) and scale = the pending
+    per-group 1/sigma [groups] for the consumer to fold in (a batch norm absorbs it into eps);
+    otherwise (conv(x), None)."""
+    entry = conv.__dict__.get('_ag2v_sn_entry')
+    if entry is None or entry.scale_g is None or conv.bias is not None:
+        return conv_scaled(conv, x), None
+    z = torch.nn.functional.conv2d(x, getattr(conv, entry.name + '_orig'), None, conv.stride, conv.padding,
+                                   conv.dilation, conv.groups)
+    return z, entry.scale_g

@@ -154,15 +154,20 @@ size_t ag2v_chan_partial_floats(long long P, int C, int NS);
 int ag2v_bn_stats(const float* x, long long P, int C, int groups, float* partial, double* sums, ag2v_stream_t stream);
 /* F.batch_norm(training) statistics (normalization.py:99): mean/rstd [groups][C] + running update
  * (once per group, in group order); count = elements per channel of one group */
+/* in_scale (optional, [groups]): the layer's input is in_scale[g] * x while the sums were taken on x
+ * (a spectrally normalised convolution evaluated on weight_orig): BN(s x; eps) == BN(x; eps / s^2),
+ * so the 1/sigma multiplication never touches the activation. */
 int ag2v_bn_finalize(const double* sums, double count, int C, int groups, float eps, float momentum,
-                     float* running_mean, float* running_var, float* mean, float* rstd, ag2v_stream_t stream);
+                     const float* in_scale, float* running_mean, float* running_var, float* mean, float* rstd,
+                     ag2v_stream_t stream);
 /* y = act((x - mean_g) * rstd_g * weight + bias): the affine SyncBN + LeakyReLU(0.2) stages
  * (normalization.py:16-50); slope 1 = no activation.  Its backward is ag2v_spade_bwd_pre with
  * chan_gamma = 1 (gamma := weight [C], dgb = NULL) followed by ag2v_spade_bwd_dx. */
 int ag2v_bn_act_fwd(const float* x, const float* mean, const float* rstd, const float* weight, const float* bias,
                     long long P, int C, int groups, float slope, float* y, ag2v_stream_t stream);
-int ag2v_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
-                       float* rstd, ag2v_stream_t stream);
+/* eval mode: mean / rstd [groups][C] from the running estimates (in_scale as above) */
+int ag2v_bn_eval_stats(const float* running_mean, const float* running_var, int C, int groups, float eps,
+                       const float* in_scale, float* mean, float* rstd, ag2v_stream_t stream);
 
 /* OIHW 3x3 weights -> [9][Nout][Cin] (dgrad = 1: transposed + flipped for the input
  * gradient).  With wb != NULL, (wa, wb) = (mlp_gamma, mlp_beta) are interleaved in

@@ -165,7 +165,7 @@ def test_generator_batched_frames_equal_frame_loop():
         sp.CONV_IMPL = old
 
 
-@pytest.mark.parametrize('impl,tol', [(3, 2e-4), (0, 2e-2)])
+@pytest.mark.parametrize('impl,tol', [(3, 1e-3), (0, 2e-2)])
 @pytest.mark.parametrize('fin,fout', [(64, 64), (128, 64)])
 def test_resnet_block_sigma_mode_equals_successive_calls(fin, fout, impl, tol):
     """SPADEResnetBlock on a group-major batch in sigma mode (3x3 convolutions on the tcgen05
@@ -199,10 +199,75 @@ def test_resnet_block_sigma_mode_equals_successive_calls(fin, fout, impl, tol):
         want.update({k: p.grad for k, p in b2.named_parameters()})
         assert got.keys() == want.keys()
         for k in want:
-            err = rel_l2(got[k], want[k]) if impl == 0 else max_rel(got[k], want[k])
+            if k == 'conv_0.bias':        # a bias in front of a batch norm: its true gradient is zero, both are noise
+                continue
+            err = max_rel(got[k], want[k]) if k == 'out' else rel_l2(got[k], want[k])   # gradients: LeakyReLU gate flips
             assert err <= tol, (k, err)
         for (k, a), (_, b) in zip(b1.state_dict().items(), b2.state_dict().items()):
             if k.endswith(('_u', '_v', 'running_mean', 'running_var')):
-                assert max_rel(a, b) <= 1e-4, (k, max_rel(a, b))
+                assert max_rel(a, b) <= (1e-4 if impl == 3 else 2e-3), (k, max_rel(a, b))
     finally:
         sp.CONV_IMPL = old
+
+
+@pytest.mark.parametrize('training', [True, False])
+def test_bn_act_folds_an_input_scale_into_eps(training):
+    """bn(in_scale_g * z) computed as BN(z; eps / s^2): outputs, dz, d in_scale, running stats."""
+    from ag2video_b200.networks import _BN2d
+    G, B, C, H, slope = 3, 2, 32, 10, 0.2
+    bn = _BN2d(C).cuda()
+    bn.load_state_dict(det_state(bn.state_dict(), 2))
+    with torch.no_grad():
+        bn.running_var.abs_().add_(0.5)
+    ref = copy.deepcopy(bn)
+    bn.train(training), ref.train(training)
+    # small activations so that eps matters and d in_scale is not pure rounding noise
+    z = (_rand(G * B, C, H, H, seed=4, cl=True) * 0.02).requires_grad_()
+    scale = torch.tensor([0.7, 1.3, 2.1], device='cuda', requires_grad=True)
+    cot = _rand(G * B, C, H, H, seed=5, cl=True)
+    y = bn(z, groups=G, slope=slope, in_scale=scale)
+    (y * cot).sum().backward()
+    got = [y.detach(), z.grad.clone(), scale.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()]
+    z.grad = scale.grad = None
+    parts = []
+    for g in range(G):
+        zz = z[g * B:(g + 1) * B] * scale[g]
+        parts.append(F.leaky_relu(F.batch_norm(zz, ref.running_mean, ref.running_var, ref.weight, ref.bias, training, 0.1, 1e-5), slope))
+    yr = torch.cat(parts, dim=0)
+    (yr * cot).sum().backward()
+    want = [yr.detach(), z.grad, scale.grad, ref.weight.grad, ref.bias.grad]
+    for name, a, b in zip(('y', 'dz', 'dscale', 'dweight', 'dbias'), got, want):
+        assert max_rel(a, b) <= (2e-3 if name == 'dscale' and training else 5e-5), (name, max_rel(a, b), a.flatten()[:4], b.flatten()[:4])
+    assert max_rel(bn.running_mean, ref.running_mean) <= 1e-5
+    assert max_rel(bn.running_var, ref.running_var) <= 1e-5
+
+
+def test_packed_weights_follow_a_fused_optimizer():
+    """torch.optim.Adam(fused=True) updates parameters without bumping Tensor._version; the packed
+    GEMM-layout weight copies must still be rebuilt for the next forward."""
+    import ag2video_b200.spade as sp
+    opt = make_opt(64)
+    G, B = 2, 1
+    blk = sp.SPADEResnetBlock(64, 64, opt)
+    blk.load_state_dict(det_state(blk.state_dict(), 9))
+    blk = blk.cuda().to(memory_format=torch.channels_last).train()
+    x = _rand(G * B, 64, 16, 16, seed=1, cl=True)
+    seg = _rand(G * B, opt.semantic_nc, 32, 32, seed=2, cl=True)
+    optim = torch.optim.Adam(blk.parameters(), lr=1e-2, fused=True)
+
+    def run(block):
+        block._sn.refresh_sigma(G, B)
+        out = block(x, seg, groups=G)
+        block._sn.end_sigma()
+        return out
+    out0 = run(blk)
+    out0.square().mean().backward()
+    optim.step()
+    state = {k: v.clone() for k, v in blk.state_dict().items()}
+    out1 = run(blk).detach()
+    fresh = sp.SPADEResnetBlock(64, 64, opt)
+    fresh.load_state_dict(state)
+    fresh = fresh.cuda().to(memory_format=torch.channels_last).train()
+    out2 = run(fresh).detach()
+    assert max_rel(out1, out0.detach()) > 1e-2, 'the optimizer step did not change the output'
+    assert max_rel(out1, out2) <= 1e-5, max_rel(out1, out2)

@@ -33,4 +33,13 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=90))
+from torch.autograd import DeviceType  # noqa: E402
+rows = [(e.self_device_time_total, e.count, e.key) for e in prof.key_averages() if e.device_type == DeviceType.CUDA]
+rows.sort(reverse=True)
+total = sum(r[0] for r in rows)
+print('GPU kernels of one step: %.3f ms in %d launches' % (total / 1e3, sum(r[1] for r in rows)))
+print('%10s %6s %6s  %s' % ('us', 'share', 'calls', 'kernel'))
+for t, n, k in rows[:150]:
+    print('%10.1f %5.1f%% %6d  %s' % (t, 100.0 * t / total, n, k[:150]))
+print()
+print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=90))
