@@ -20,7 +20,7 @@ extern "C" int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, l
                             int Ww, int Cin, const float* wpk, const float* bias, int Nout, float* out,
                             long long out_sb, long long out_sy, long long out_sx, int epilogue, int round_out,
                             const float* x, const float* mean, const float* rstd, float* gamma_out,
-                            float slope, int C, long long group_pixels, const float* scale, const float* res,
+                            float slope, int C, long long group_pixels, int x_up, const float* scale, const float* res,
                             const float* gate, float* splitk_ws, size_t splitk_ws_floats, int impl,
                             cudaStream_t stream) {
   ConvParams p{};
@@ -29,7 +29,7 @@ extern "C" int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, l
   p.wpk = wpk; p.bias = bias; p.Nout = Nout;
   p.out = out; p.out_sb = out_sb; p.out_sy = out_sy; p.out_sx = out_sx;
   p.x = x; p.mean = mean; p.rstd = rstd; p.gamma_out = gamma_out; p.slope = slope; p.C = C;
-  p.group_pixels = group_pixels; p.scale = scale; p.res = res;
+  p.group_pixels = group_pixels; p.x_up = x_up; p.scale = scale; p.res = res;
   p.gate = gate;
   p.splitk_ws = splitk_ws; p.splitk_ws_floats = splitk_ws_floats;
   int rc = conv3x3_check(p, epilogue);

@@ -35,6 +35,7 @@ struct ConvParams {
   // EPI_SPADE: Nout == 2*C in gb8 order; out is [.., C]
   const float* x; const float* mean; const float* rstd; float* gamma_out; float slope; int C;
   long long group_pixels;    // > 0: mean/rstd are [groups][C], group = pixel index / group_pixels
+  int x_up;                  // EPI_SPADE: x is [B, Hh/2, Ww/2, C] and is read through a nearest 2x up-sampling
   // EPI_BIAS extras (the spectrally normalised convolutions of SPADEResnetBlock run on weight_orig):
   // scale [groups] = 1/sigma per frame group (group = pixel / group_pixels), res = dense [P, Nout] residual
   const float* scale; const float* res;

@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(kConvThreads, PRECISE ? 1 : 2) conv3x3_mma_ker
           float b0 = acc[mt][2 * pr + 1][half * 2 + 0], b1 = acc[mt][2 * pr + 1][half * 2 + 1];
           if (p.bias) { g0 += p.bias[ng]; g1 += p.bias[ng + 1]; b0 += p.bias[ng + 8]; b1 += p.bias[ng + 9]; }
           const size_t off = (size_t)pp * p.C + c;
-          const float2 xv = *reinterpret_cast<const float2*>(p.x + off);
+          const long long xpix = p.x_up ? ((long long)b * (p.Hh >> 1) + (y >> 1)) * (p.Ww >> 1) + (x >> 1) : pp;
+          const float2 xv = *reinterpret_cast<const float2*>(p.x + (size_t)xpix * p.C + c);
           const size_t sc = (p.group_pixels > 0 ? (size_t)(pp / p.group_pixels) * p.C : 0) + c;
           const float2 mu = *reinterpret_cast<const float2*>(p.mean + sc);
           const float2 rs = *reinterpret_cast<const float2*>(p.rstd + sc);
@@ -217,6 +218,7 @@ int conv3x3_check(const ConvParams& p, int epi) {
   AG2V_REQUIRE(p.out_sx % 2 == 0 && p.out_sy % 2 == 0 && p.out_sb % 2 == 0, "conv3x3: output view must be 8-byte aligned");
   if (epi == EPI_SPADE) {
     AG2V_REQUIRE(p.x && p.mean && p.rstd && p.C > 0 && p.Nout == 2 * p.C && p.C % 8 == 0, "conv3x3: SPADE epilogue needs x/mean/rstd and Nout == 2C, C %% 8 == 0");
+    AG2V_REQUIRE(!p.x_up || (p.Hh % 2 == 0 && p.Ww % 2 == 0), "conv3x3: up-sampled x needs even output sizes");
   }
   if (epi == EPI_GATE) AG2V_REQUIRE(p.gate, "conv3x3: gate epilogue needs a gate tensor");
   return AG2V_OK;

@@ -51,15 +51,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // one 32-column chunk of one accumulator row (= one pixel): v[] holds the fp32 sums
 template <int EPI, bool ROUND_OUT>
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float (&v)[32], int n, long long pp, float* orow) {
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float (&v)[32], int n, long long pp, long long xpix,
+                                               float* orow) {
   if (EPI == EPI_SPADE) {
     const int c = n >> 1;                                           // 16 channels: [g8 | b8 | g8 | b8]
     const size_t off = (size_t)pp * p.C + c;
+    const size_t xoff = (size_t)xpix * p.C + c;
     const size_t sc = (p.group_pixels > 0 ? (size_t)(pp / p.group_pixels) * p.C : 0) + c;
     float xs[16], mu[16], rs[16], o[16], gm_[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      *reinterpret_cast<float4*>(xs + 4 * i) = *reinterpret_cast<const float4*>(p.x + off + 4 * i);
+      *reinterpret_cast<float4*>(xs + 4 * i) = *reinterpret_cast<const float4*>(p.x + xoff + 4 * i);
       *reinterpret_cast<float4*>(mu + 4 * i) = *reinterpret_cast<const float4*>(p.mean + sc + 4 * i);
       *reinterpret_cast<float4*>(rs + 4 * i) = *reinterpret_cast<const float4*>(p.rstd + sc + 4 * i);
     }
@@ -248,6 +250,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int x = x0 + xt, y = y0 + yt, b = b0 + bt;
         const bool valid = x < p.Ww && y < p.Hh && b < p.B;
         const long long pp = ((long long)b * p.Hh + y) * p.Ww + x;
+        const long long xpix = p.x_up ? ((long long)b * (p.Hh >> 1) + (y >> 1)) * (p.Ww >> 1) + (x >> 1) : pp;
         float* orow = (EPI == EPI_RAW)
             ? p.splitk_ws + ((size_t)split * p.B * p.Hh * p.Ww + (size_t)pp) * p.Nout        // partial sums [split][pixel][n]
             : p.out + (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
@@ -268,7 +271,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int j = 0; j < 32; j += 4)
                 if (j < ncols) *reinterpret_cast<float4*>(orow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
-              epilogue_chunk<EPI, ROUND_OUT>(p, v, n, pp, orow);
+              epilogue_chunk<EPI, ROUND_OUT>(p, v, n, pp, xpix, orow);
             }
           }
         }
@@ -308,7 +311,8 @@ __global__ void __launch_bounds__(128) conv_finish_kernel(ConvParams p, int kspl
   const int rem = (int)(pp - (long long)b * p.Hh * p.Ww);
   const int y = rem / p.Ww, x = rem - y * p.Ww;
   float* orow = p.out + (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
-  epilogue_chunk<EPI, ROUND_OUT>(p, v, n, pp, orow);
+  const long long xpix = p.x_up ? ((long long)b * (p.Hh >> 1) + (y >> 1)) * (p.Ww >> 1) + (x >> 1) : pp;
+  epilogue_chunk<EPI, ROUND_OUT>(p, v, n, pp, xpix, orow);
 }
 
 // ---- host side -----------------------------------------------------------------

@@ -41,6 +41,7 @@ struct ChanArgs {
   const float* dout; const float* out; const float* gamma; const float* mean; const float* rstd;
   float* dgb; float* dxhat; float slope; int act; int round_ops;
   int chan_gamma;                   // MODE 1: gamma is a per-channel scale w[c] (affine batch norm) instead of per-pixel 1+gamma
+  int up_h, up_w;                   // MODE 1, > 0: x is [.., up_h/2, up_w/2, C], read through a nearest 2x up-sampling
 };
 // Groups: blockIdx.y selects one of G independent pixel ranges of P rows each (the frames of a
 // clip batched into one call keep per-call batch statistics); every per-group array
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
   const int C = a.C, c4n = C >> 2;
   {                                                     // this group's slices
     const size_t go = (size_t)blockIdx.y * a.P * C;
-    if (MODE != 3) a.x += go;
+    if (MODE != 3) a.x += (MODE == 1 && a.up_w > 0) ? go / 4 : go;
     a.part += (size_t)blockIdx.y * gm.nsplit * NS * C;
     if (MODE == 3) { a.dout += go; a.dxhat += go; }
     if (MODE == 1) {
@@ -84,7 +85,15 @@ __global__ void __launch_bounds__(kElemThreads) chan_partial_kernel(ChanArgs a, 
           s[0].x += dv.x; s[0].y += dv.y; s[0].z += dv.z; s[0].w += dv.w;
           continue;
         }
-        const float4 xv = *reinterpret_cast<const float4*>(a.x + off);
+        size_t xoff = off;
+        if (MODE == 1 && a.up_w > 0) {                    // pixel p of this group -> its low-resolution parent
+          const long long per = (long long)a.up_h * a.up_w;
+          const long long b = p / per;
+          const int rem = (int)(p - b * per);
+          const int y = rem / a.up_w, xx = rem - y * a.up_w;
+          xoff = (size_t)((b * (a.up_h >> 1) + (y >> 1)) * (a.up_w >> 1) + (xx >> 1)) * C + c;
+        }
+        const float4 xv = *reinterpret_cast<const float4*>(a.x + xoff);
         if (MODE == 0) {
           s[0].x += xv.x; s[0].y += xv.y; s[0].z += xv.z; s[0].w += xv.w;
           s[1].x = fmaf(xv.x, xv.x, s[1].x); s[1].y = fmaf(xv.y, xv.y, s[1].y);
@@ -180,8 +189,9 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const float* __restric
 // spectrally normalised convolution evaluated on weight_orig, 1/sigma_g not yet applied).
 // BN(s x; eps) == BN(x; eps / s^2), so only eps and the running estimates change and the
 // multiplication by s never touches the activation.
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, int G, float eps, float momentum,
-                                   const float* __restrict__ in_scale, float* __restrict__ running_mean,
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, double unbias_count, int C, int G,
+                                   float eps, float momentum, const float* __restrict__ in_scale,
+                                   float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ mean, float* __restrict__ rstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -193,7 +203,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
     mean[(size_t)g * C + c] = (float)m;
     rstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps / (sc * sc)));
     if (running_mean != nullptr) {
-      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      const double unbiased = unbias_count > 1.0 ? var * unbias_count / (unbias_count - 1.0) : var;
       running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * sc * m);
       running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * sc * sc * unbiased);
     }
@@ -242,6 +252,50 @@ spade_bwd_dx_kernel(const float* __restrict__ x, float* __restrict__ dxhat, cons
       d.x *= rs.x; d.y *= rs.y; d.z *= rs.z; d.w *= rs.w;
     }
     reinterpret_cast<float4*>(dxhat)[i] = d;
+  }
+}
+
+// The same pass when x was up-sampled 2x (nearest) on the fly: dxhat is full resolution
+// [.., H, W, C]; the gradient of the low-resolution x [.., H/2, W/2, C] is the sum over its four
+// children, written to dx_low.  m1 / m2 are means over the FULL-resolution elements (count).
+__global__ void __launch_bounds__(kElemThreads)
+spade_bwd_dx_up_kernel(const float* __restrict__ x, const float* __restrict__ dxhat, const float* __restrict__ mean,
+                       const float* __restrict__ rstd, const double* __restrict__ sums, double count, int training,
+                       long long P_low, int C, int H, int W, float* __restrict__ dx_low) {
+  const long long n4 = P_low * (C >> 2);
+  const int h = H >> 1, w = W >> 1;
+  x += (size_t)blockIdx.y * P_low * C; dx_low += (size_t)blockIdx.y * P_low * C;
+  dxhat += (size_t)blockIdx.y * P_low * 4 * C;
+  mean += (size_t)blockIdx.y * C; rstd += (size_t)blockIdx.y * C; sums += (size_t)blockIdx.y * 5 * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (C >> 2)) << 2;
+    const long long pl = i / (C >> 2);
+    const long long b = pl / ((long long)h * w);
+    const int rem = (int)(pl - b * h * w);
+    const int yl = rem / w, xl = rem - yl * w;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t pf = (size_t)((b * H + 2 * yl + (k >> 1)) * W + 2 * xl + (k & 1));
+      const float4 t = *reinterpret_cast<const float4*>(dxhat + pf * C + c);
+      d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+    }
+    if (training) {     // sum over the 4 children of rstd * (dxhat - m1 - xhat * m2)
+      const float m1x = (float)(sums[2 * C + c] / count), m2x = (float)(sums[3 * C + c] / count);
+      const float m1y = (float)(sums[2 * C + c + 1] / count), m2y = (float)(sums[3 * C + c + 1] / count);
+      const float m1z = (float)(sums[2 * C + c + 2] / count), m2z = (float)(sums[3 * C + c + 2] / count);
+      const float m1w = (float)(sums[2 * C + c + 3] / count), m2w = (float)(sums[3 * C + c + 3] / count);
+      d.x = rs.x * (d.x - 4.f * (m1x + (xv.x - mu.x) * rs.x * m2x));
+      d.y = rs.y * (d.y - 4.f * (m1y + (xv.y - mu.y) * rs.y * m2y));
+      d.z = rs.z * (d.z - 4.f * (m1z + (xv.z - mu.z) * rs.z * m2z));
+      d.w = rs.w * (d.w - 4.f * (m1w + (xv.w - mu.w) * rs.w * m2w));
+    } else {
+      d.x *= rs.x; d.y *= rs.y; d.z *= rs.z; d.w *= rs.w;
+    }
+    reinterpret_cast<float4*>(dx_low)[i] = d;
   }
 }
 
@@ -426,12 +480,12 @@ extern "C" int ag2v_bn_stats(const float* x, long long P, int C, int groups, flo
 
 // mean/rstd from (possibly all-reduced) sums; updates running stats when given.
 // sums [groups][2C] -> mean / rstd [groups][C]; count = elements per channel in ONE group.
-extern "C" int ag2v_bn_finalize(const double* sums, double count, int C, int groups, float eps, float momentum,
-                                const float* in_scale, float* running_mean, float* running_var, float* mean,
-                                float* rstd, cudaStream_t stream) {
+extern "C" int ag2v_bn_finalize(const double* sums, double count, double unbias_count, int C, int groups, float eps,
+                                float momentum, const float* in_scale, float* running_mean, float* running_var,
+                                float* mean, float* rstd, cudaStream_t stream) {
   AG2V_REQUIRE(sums && mean && rstd && C > 0 && count > 0 && groups >= 1, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(sums, count, C, groups, eps, momentum, in_scale, running_mean,
-                                                          running_var, mean, rstd);
+  bn_finalize_kernel<<<ceil_div(C, 256), 256, 0, stream>>>(sums, count, unbias_count > 0 ? unbias_count : count, C, groups,
+                                                          eps, momentum, in_scale, running_mean, running_var, mean, rstd);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
@@ -450,8 +504,8 @@ extern "C" int ag2v_bn_eval_stats(const float* running_mean, const float* runnin
 // per-channel sums (doubles, [4][C]): sum g, sum g*xhat, sum dxhat, sum dxhat*xhat.
 extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma,
                                   const float* mean, const float* rstd, long long P, int C, int groups, int act,
-                                  float slope, int round_ops, int chan_gamma, float* dgb, float* dxhat,
-                                  float* partial, double* sums, cudaStream_t stream) {
+                                  float slope, int round_ops, int chan_gamma, int up_h, int up_w, float* dgb,
+                                  float* dxhat, float* partial, double* sums, cudaStream_t stream) {
   int rc = chan_check(P, C);
   if (rc) return rc;
   AG2V_REQUIRE(dgb == nullptr || C % 8 == 0, "spade_bwd_pre: C %% 8 == 0 required (C=%d)", C);
@@ -463,6 +517,9 @@ extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const flo
   a.x = x; a.P = P; a.C = C; a.part = partial; a.dout = dout; a.out = out; a.gamma = gamma;
   a.mean = mean; a.rstd = rstd; a.dgb = dgb; a.dxhat = dxhat; a.slope = slope; a.act = act; a.round_ops = round_ops;
   a.chan_gamma = chan_gamma;
+  AG2V_REQUIRE((up_h == 0 && up_w == 0) || (up_h > 0 && up_w > 0 && up_h % 2 == 0 && up_w % 2 == 0 && P % ((long long)up_h * up_w) == 0),
+               "spade_bwd_pre: bad up-sampling geometry %dx%d for %lld pixels", up_h, up_w, P);
+  a.up_h = up_h; a.up_w = up_w;
   chan_partial_kernel<1><<<dim3(g.nsplit, groups), kElemThreads, 0, stream>>>(a, g);
   AG2V_LAUNCH_CHECK();
   chan_reduce_kernel<<<dim3(ceil_div(5 * C, 32), groups), 256, 0, stream>>>(partial, g.nsplit, 5 * C, sums);
@@ -474,10 +531,22 @@ extern "C" int ag2v_spade_bwd_pre(const float* dout, const float* out, const flo
 // all-reduced across ranks by the caller under SyncBN; count = global element count).
 extern "C" int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean, const float* rstd,
                                  const double* sums, double count, int training, long long P, int C, int groups,
-                                 cudaStream_t stream) {
+                                 int up_h, int up_w, float* dx_low, cudaStream_t stream) {
   int rc = chan_check(P, C);
   if (rc) return rc;
   AG2V_REQUIRE(x && dxhat && mean && rstd && sums && groups >= 1 && groups <= 65535, "spade_bwd_dx: bad arguments");
+  if (up_w > 0) {      // x is low resolution: P full-resolution pixels per group, P / 4 parents
+    AG2V_REQUIRE(dx_low && up_h > 0 && up_h % 2 == 0 && up_w % 2 == 0 && P % ((long long)up_h * up_w) == 0,
+                 "spade_bwd_dx: bad up-sampling geometry");
+    const long long n4l = (P / 4) * (C / 4);
+    const long long capl = 4 * 148 * 8 / groups + 1;
+    int bl = (int)(ceil_div_ll(n4l, kElemThreads) > capl ? capl : ceil_div_ll(n4l, kElemThreads));
+    if (bl < 1) bl = 1;
+    spade_bwd_dx_up_kernel<<<dim3(bl, groups), kElemThreads, 0, stream>>>(x, dxhat, mean, rstd, sums, count, training, P / 4,
+                                                                         C, up_h, up_w, dx_low);
+    AG2V_LAUNCH_CHECK();
+    return AG2V_OK;
+  }
   long long n4 = P * (C / 4);
   const long long cap = 4 * 148 * 8 / groups + 1;
   int blocks = (int)(ceil_div_ll(n4, kElemThreads * 4) > cap ? cap : ceil_div_ll(n4, kElemThreads * 4));

@@ -214,8 +214,8 @@ class SPADEGenerator(nn.Module):
         x = self.head_0(x, seg, groups)
         x = self.G_middle_0(up(x), seg, groups)
         x = self.G_middle_1(x, seg, groups)
-        for name in ('up_0', 'up_1', 'up_2', 'up_3'):
-            x = getattr(self, name)(up(x), seg, groups)
+        for name in ('up_0', 'up_1', 'up_2', 'up_3'):      # up(x) is read on the fly by the SPADE kernels
+            x = getattr(self, name)(x, seg, groups, upsample=True)
         return torch.tanh(self.conv_img(F.leaky_relu(x, 0.2)))
 
 

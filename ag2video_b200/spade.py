@@ -29,11 +29,11 @@ c_d = L.ctypes.c_double
 
 L.register('ag2v_chan_partial_floats', c_sz, [c_ll, c_i, c_i])
 L.register('ag2v_bn_stats', c_i, [c_p, c_ll, c_i, c_i, c_p, c_p, c_p])
-L.register('ag2v_bn_finalize', c_i, [c_p, c_d, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p])
+L.register('ag2v_bn_finalize', c_i, [c_p, c_d, c_d, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p])
 L.register('ag2v_bn_act_fwd', c_i, [c_p] * 5 + [c_ll, c_i, c_i, c_f, c_p, c_p])
 L.register('ag2v_bn_eval_stats', c_i, [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_p])
-L.register('ag2v_spade_bwd_pre', c_i, [c_p] * 6 + [c_ll, c_i, c_i, c_i, c_f, c_i, c_i] + [c_p] * 4 + [c_p])
-L.register('ag2v_spade_bwd_dx', c_i, [c_p] * 5 + [c_d, c_i, c_ll, c_i, c_i, c_p])
+L.register('ag2v_spade_bwd_pre', c_i, [c_p] * 6 + [c_ll, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_i] + [c_p] * 4 + [c_p])
+L.register('ag2v_spade_bwd_dx', c_i, [c_p] * 5 + [c_d, c_i, c_ll, c_i, c_i, c_i, c_i, c_p, c_p])
 L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_unpack_dw3x3', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_i, c_ll, c_p, c_p])
@@ -44,7 +44,7 @@ L.register('ag2v_scaled_grad_pre', c_i, [c_p, c_p, c_ll, c_i, c_i, c_p, c_p, c_p
 L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 6)
 L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p])
 L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_ll, c_ll, c_ll,
-                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_ll, c_p, c_p, c_p, c_p, c_sz, c_i, c_p])
+                                 c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_ll, c_i, c_p, c_p, c_p, c_p, c_sz, c_i, c_p])
 L.register('ag2v_conv3x3_splitk_floats', c_sz, [c_i] * 5)
 L.register('ag2v_conv3x3_tc_supported', c_i, [c_i] * 6)
 
@@ -112,7 +112,8 @@ class _Timed:
 
 
 def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, epi, round_out=0,
-          x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None, group_pixels=0, scale=None, res=None):
+          x=None, mean=None, rstd=None, gamma_out=None, slope=1.0, C=0, gate=None, group_pixels=0, scale=None, res=None,
+          x_up=0):
     lib = L.lib()
     nws = lib.ag2v_conv3x3_splitk_floats(B, Hh, Ww, Cin, Nout) if CONV_IMPL in (0, 2) else 0
     ws = torch.empty(nws, device=out.device, dtype=torch.float32) if nws else None
@@ -120,7 +121,7 @@ def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, ep
         L.check(lib.ag2v_conv3x3(L.ptr(inp), in_strides[0], in_strides[1], in_strides[2], B, Hh, Ww, Cin,
                                  L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), out_strides[0], out_strides[1],
                                  out_strides[2], epi, round_out, L.ptr(x), L.ptr(mean), L.ptr(rstd),
-                                 L.ptr(gamma_out), float(slope), C, group_pixels, L.ptr(scale), L.ptr(res), L.ptr(gate),
+                                 L.ptr(gamma_out), float(slope), C, group_pixels, int(x_up), L.ptr(scale), L.ptr(res), L.ptr(gate),
                                  L.ptr(ws), nws, CONV_IMPL, L.stream()))
 
 
@@ -193,13 +194,15 @@ class _SharedSegFn(torch.autograd.Function):
 class _SpadeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, seg, token, w_sh, b_sh, w_g, b_g, w_b, b_b, mod, shared, slope, groups=1, next_scale=None,
-                round_out=False):
+                round_out=False, upsample=False):
         L.need_cuda(x, seg, w_sh)
         lib = L.lib()
         dev = x.device
         x = _cl(x.float())
         seg = seg if shared is not None else _seg_operand(seg)
         B, C, r, rw = x.shape
+        if upsample:                               # x is the low-resolution source of a nearest 2x up-sampling
+            r, rw = 2 * r, 2 * rw
         _, Lc, Hs, Ws = seg.shape
         if Hs % r or Ws % rw:
             raise NotImplementedError('SPADE: segmap %dx%d is not an integer multiple of the activation %dx%d' % (Hs, Ws, r, rw))
@@ -218,15 +221,16 @@ class _SpadeFn(torch.autograd.Function):
         rstd = torch.empty(G * C, device=dev, dtype=torch.float32)
         count = float(Pg)
         if training:
-            part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 2), device=dev, dtype=torch.float32)
+            Ps = Pg // 4 if upsample else Pg       # statistics of up(x) are those of x (every element appears 4 times)
+            part = torch.empty(G * lib.ag2v_chan_partial_floats(Ps, C, 2), device=dev, dtype=torch.float32)
             sums = torch.empty(G * 2 * C, device=dev, dtype=torch.float64)
-            L.check(lib.ag2v_bn_stats(L.ptr(x), Pg, C, G, L.ptr(part), L.ptr(sums), L.stream()))
+            L.check(lib.ag2v_bn_stats(L.ptr(x), Ps, C, G, L.ptr(part), L.ptr(sums), L.stream()))
             dist, world = _world()
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
-                count = float(Pg * world)
-            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, G, bn.eps, bn.momentum, None, L.ptr(bn.running_mean),
-                                         L.ptr(bn.running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
+            count = float(Pg * world)
+            L.check(lib.ag2v_bn_finalize(L.ptr(sums), float(Ps * world), count, C, G, bn.eps, bn.momentum, None,
+                                         L.ptr(bn.running_mean), L.ptr(bn.running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
         else:                                      # same running estimates for every group
             L.check(lib.ag2v_bn_eval_stats(L.ptr(bn.running_mean), L.ptr(bn.running_var), C, G, bn.eps, None, L.ptr(mean),
                                            L.ptr(rstd), L.stream()))
@@ -240,18 +244,19 @@ class _SpadeFn(torch.autograd.Function):
         gamma = torch.empty(B, r, rw, C, device=dev, dtype=torch.float32) if need_grad else None
         _conv(actv, (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN), B, r, rw, NHIDDEN, pk['w2'], pk['b2'], 2 * C, out,
               (r * rw * C, rw * C, C), EPI_SPADE, round_out=int(round_out and not _precise()), x=x, mean=mean, rstd=rstd,
-              gamma_out=gamma, slope=slope, C=C, group_pixels=Pg if G > 1 else 0)
+              gamma_out=gamma, slope=slope, C=C, group_pixels=Pg if G > 1 else 0, x_up=int(upsample))
         if need_grad:
             ctx.save_for_backward(x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b, next_scale)
-        ctx.meta = (B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G)
+        ctx.meta = (B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G, bool(upsample))
         ctx.mod, ctx.shared = mod, shared
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, seg, actv, gamma, out, mean, rstd, w_sh, w_g, w_b, next_scale = ctx.saved_tensors
-        B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G = ctx.meta
+        B, C, r, rw, Lc, Hs, Ws, seg_strides, P, count, training, slope, G, upsample = ctx.meta
         Pg = P // G
+        uh, uw = (r, rw) if upsample else (0, 0)
         mod, shared = ctx.mod, ctx.shared
         _cache_of(mod).backward_seen()
         lib = L.lib()
@@ -263,7 +268,7 @@ class _SpadeFn(torch.autograd.Function):
         part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 5), device=dev, dtype=torch.float32)
         sums = torch.empty(G * 5 * C, device=dev, dtype=torch.float64)
         L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), Pg, C, G,
-                                       act, float(slope), int(not _precise()), 0, L.ptr(dgb), L.ptr(dx), L.ptr(part),
+                                       act, float(slope), int(not _precise()), 0, uh, uw, L.ptr(dgb), L.ptr(dx), L.ptr(part),
                                        L.ptr(sums), L.stream()))
         db = torch.empty(2 * C, device=dev, dtype=torch.float32)     # [sum g | sum g*xhat] = [d bias_beta | d bias_gamma]
         L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 5 * C, L.ptr(db), L.stream()))
@@ -275,8 +280,11 @@ class _SpadeFn(torch.autograd.Function):
             dist, world = _world()
             if world > 1:              # db (local sums) is already extracted; the BN backward needs global sums
                 dist.all_reduce(sums, group=_sync_group['group'])
+        dx_low = torch.empty_like(x, memory_format=torch.channels_last) if upsample else None
         L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
-                                      int(training), Pg, C, G, L.stream()))
+                                      int(training), Pg, C, G, uh, uw, L.ptr(dx_low), L.stream()))
+        if upsample:
+            dx = dx_low
         a_strides = (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN)
         # gamma / beta convolutions: weight gradient, then input gradient gated by the ReLU of actv
         dw_g, dw_b = _wgrad(dgb, 2 * C, actv, a_strides, NHIDDEN, B, r, rw, True, w_g, w_b)
@@ -300,7 +308,7 @@ class _SpadeFn(torch.autograd.Function):
                 dseg = buf
             _conv(dactv, a_strides, B, r, rw, NHIDDEN, pkt['w1t'], None, Lc, buf, seg_strides, EPI_ACCUM)
         dtoken = torch.zeros(1, device=dev) if (shared is not None and ctx.needs_input_grad[2]) else None
-        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None, dscale, None
+        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None, dscale, None, None
 
 
 class _PackCache:
@@ -455,7 +463,7 @@ class _BnActFn(torch.autograd.Function):
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
                 count = float(Pg * world)
-            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, C, G, eps, momentum, L.ptr(sc), L.ptr(running_mean),
+            L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, 0.0, C, G, eps, momentum, L.ptr(sc), L.ptr(running_mean),
                                          L.ptr(running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
         else:
             L.check(lib.ag2v_bn_eval_stats(L.ptr(running_mean), L.ptr(running_var), C, G, eps, L.ptr(sc), L.ptr(mean),
@@ -479,7 +487,7 @@ class _BnActFn(torch.autograd.Function):
         part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 5), device=dev, dtype=torch.float32)
         sums = torch.empty(G * 5 * C, device=dev, dtype=torch.float64)
         L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(y), L.ptr(x), L.ptr(w), L.ptr(mean), L.ptr(rstd), Pg, C, G,
-                                       0 if slope == 1.0 else 1, float(slope), 0, 1, None, L.ptr(dx), L.ptr(part),
+                                       0 if slope == 1.0 else 1, float(slope), 0, 1, 0, 0, None, L.ptr(dx), L.ptr(part),
                                        L.ptr(sums), L.stream()))
         db = torch.empty(2 * C, device=dev, dtype=torch.float32)           # [d bias | d weight]
         L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 5 * C, L.ptr(db), L.stream()))
@@ -497,7 +505,7 @@ class _BnActFn(torch.autograd.Function):
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
         L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
-                                      int(training), Pg, C, G, L.stream()))
+                                      int(training), Pg, C, G, 0, 0, None, L.stream()))
         return dx, db[C:], db[:C], dscale, None, None, None, None, None, None, None
 
 
@@ -555,18 +563,20 @@ class SPADE(nn.Module):
             return dict(w1t=w1t, w2t=w2t)
         return _cache_of(self).get('dgrad', (w_sh, w_g, w_b), build)
 
-    def forward(self, x, segmap, groups=1, next_scale=None, round_out=False):
+    def forward(self, x, segmap, groups=1, next_scale=None, round_out=False, upsample=False):
         """``groups`` > 1: the batch holds that many reference calls (group-major); batch statistics
         and running-stat updates are per group, as if the layer were called once per group.
         ``next_scale`` [groups]: the 1/sigma vector of the scaled convolution (``sn_conv3x3``) that
         consumes this output; its gradient is produced here, from sums the backward makes anyway.
-        ``round_out``: store the output rounded to TF32 (operand of a tcgen05 convolution)."""
+        ``round_out``: store the output rounded to TF32 (operand of a tcgen05 convolution).
+        ``upsample``: the layer's input is ``F.interpolate(x, scale_factor=2)`` (nearest), evaluated
+        without materialising it; the output has twice the resolution of ``x``."""
         shared = segmap if isinstance(segmap, SharedSeg) else None
         seg = shared.seg if shared is not None else segmap
         token = shared.token if shared is not None else None
         return _SpadeFn.apply(x, seg, token, self.mlp_shared[0].weight, self.mlp_shared[0].bias,
                               self.mlp_gamma.weight, self.mlp_gamma.bias, self.mlp_beta.weight, self.mlp_beta.bias,
-                              self, shared, float(self.fused_slope), int(groups), next_scale, bool(round_out))
+                              self, shared, float(self.fused_slope), int(groups), next_scale, bool(round_out), bool(upsample))
 
 
 class SPADEResnetBlock(nn.Module):
@@ -596,22 +606,28 @@ class SPADEResnetBlock(nn.Module):
             self.norm_s = SPADE(cfg, fin, opt.semantic_nc)
         self.__dict__['_sn'] = SpectralNormGroup(self)        # spectral norm through csrc/k5_specnorm.cu
 
-    def forward(self, x, seg, groups=1):
+    def forward(self, x, seg, groups=1, upsample=False):
         """``groups`` > 1: the batch holds that many reference calls (see SPADE.forward); the caller
-        has put the spectral norms in sigma mode (SpectralNormGroup.refresh_sigma)."""
+        has put the spectral norms in sigma mode (SpectralNormGroup.refresh_sigma).
+        ``upsample``: evaluate the block on ``F.interpolate(x, scale_factor=2)`` (the ``up(x)`` in
+        front of every block of the generator); with a learned shortcut x only feeds SPADE layers,
+        which read it through the up-sampling, so the 4x larger tensor is never written."""
         if groups == 1:
             self._sn.refresh_stale()                          # no-op when the generator prepared the weights
         if not isinstance(seg, SharedSeg):
             seg = SharedSeg.wrap(seg)
-        x_s = conv_scaled(self.conv_s, self.norm_s(x, seg, groups)) if self.learned_shortcut else x
+        if upsample and not self.learned_shortcut:             # x itself is the residual: materialise it
+            x, upsample = F.interpolate(x, scale_factor=2, mode='nearest'), False
+        up = dict(upsample=True) if upsample else {}
+        x_s = conv_scaled(self.conv_s, self.norm_s(x, seg, groups, **up)) if self.learned_shortcut else x
         if sn_conv3x3_usable(self.conv_0, x) and sn_conv3x3_usable(self.conv_1, x):
             # sigma mode: the 3x3 convolutions run on the tcgen05 kernel with 1/sigma, bias and the
             # residual sum in the epilogue; d(1/sigma) comes out of the SPADE backward
             sc0 = self.conv_0.__dict__['_ag2v_sn_entry'].scale_g
             sc1 = self.conv_1.__dict__['_ag2v_sn_entry'].scale_g
-            dx = sn_conv3x3(self.conv_0, self.norm_0(x, seg, groups, next_scale=sc0, round_out=True), groups)
+            dx = sn_conv3x3(self.conv_0, self.norm_0(x, seg, groups, next_scale=sc0, round_out=True, **up), groups)
             return sn_conv3x3(self.conv_1, self.norm_1(dx, seg, groups, next_scale=sc1, round_out=True), groups, res=x_s)
-        dx = conv_scaled(self.conv_0, self.norm_0(x, seg, groups))
+        dx = conv_scaled(self.conv_0, self.norm_0(x, seg, groups, **up))
         dx = conv_scaled(self.conv_1, self.norm_1(dx, seg, groups))
         return x_s + dx
 

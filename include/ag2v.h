@@ -153,13 +153,15 @@ int ag2v_crop_bbox_bwd(const float* dout, const int* frame, const float* boxes, 
 size_t ag2v_chan_partial_floats(long long P, int C, int NS);
 int ag2v_bn_stats(const float* x, long long P, int C, int groups, float* partial, double* sums, ag2v_stream_t stream);
 /* F.batch_norm(training) statistics (normalization.py:99): mean/rstd [groups][C] + running update
- * (once per group, in group order); count = elements per channel of one group */
+ * (once per group, in group order); count = elements per channel of one group; unbias_count
+ * (0 = count) is the n of the running estimate's n/(n-1) factor: statistics of a nearest-2x
+ * up-sampled tensor are taken on its low-resolution source with unbias_count = 4 * count. */
 /* in_scale (optional, [groups]): the layer's input is in_scale[g] * x while the sums were taken on x
  * (a spectrally normalised convolution evaluated on weight_orig): BN(s x; eps) == BN(x; eps / s^2),
  * so the 1/sigma multiplication never touches the activation. */
-int ag2v_bn_finalize(const double* sums, double count, int C, int groups, float eps, float momentum,
-                     const float* in_scale, float* running_mean, float* running_var, float* mean, float* rstd,
-                     ag2v_stream_t stream);
+int ag2v_bn_finalize(const double* sums, double count, double unbias_count, int C, int groups, float eps,
+                     float momentum, const float* in_scale, float* running_mean, float* running_var, float* mean,
+                     float* rstd, ag2v_stream_t stream);
 /* y = act((x - mean_g) * rstd_g * weight + bias): the affine SyncBN + LeakyReLU(0.2) stages
  * (normalization.py:16-50); slope 1 = no activation.  Its backward is ag2v_spade_bwd_pre with
  * chan_gamma = 1 (gamma := weight [C], dgb = NULL) followed by ag2v_spade_bwd_dx. */
@@ -183,16 +185,19 @@ int ag2v_pack_w3x3(const float* wa, const float* wb, const float* ba, const floa
  * impl 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel, 3 = mma.sync with 3xTF32 products
  * (fp32-class accuracy, validation mode).  round_ops / round_out: round the stored GEMM operands
  * to nearest TF32 (the tcgen05 TF32 path truncates).  group_pixels > 0 (epilogue 2): mean / rstd
- * are [groups][C] and pixel p uses group p / group_pixels.  Epilogue 0 also takes scale [groups]
+ * are [groups][C] and pixel p uses group p / group_pixels.  x_up != 0 (epilogue 2): x is
+ * [B, Hh/2, Ww/2, C] and is read through a nearest 2x up-sampling (the `up(x)` in front of every
+ * SPADEResnetBlock of the generator, spade_models/networks/generator.py) that is never
+ * materialised.  Epilogue 0 also takes scale [groups]
  * (out = acc * scale[group] + bias, the 1/sigma of a spectrally normalised convolution evaluated
  * on weight_orig, architecture.py:34-41) and res, a dense [P, Nout] tensor added to the result
  * (the residual sum x_s + dx of SPADEResnetBlock, architecture.py:62); both may be NULL. */
 int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in_sx, int B, int Hh, int Ww, int Cin,
                  const float* wpk, const float* bias, int Nout, float* out, long long out_sb, long long out_sy,
                  long long out_sx, int epilogue, int round_out, const float* x, const float* mean,
-                 const float* rstd, float* gamma_out, float slope, int C, long long group_pixels, const float* scale,
-                 const float* res, const float* gate, float* splitk_ws, size_t splitk_ws_floats, int impl,
-                 ag2v_stream_t stream);
+                 const float* rstd, float* gamma_out, float slope, int C, long long group_pixels, int x_up,
+                 const float* scale, const float* res, const float* gate, float* splitk_ws, size_t splitk_ws_floats,
+                 int impl, ag2v_stream_t stream);
 /* split-K scratch (floats) that lets low-resolution layers use the whole chip; 0 = none needed */
 size_t ag2v_conv3x3_splitk_floats(int B, int Hh, int Ww, int Cin, int Nout);
 int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue);
@@ -204,9 +209,14 @@ int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epil
  * [C] (affine batch norm) and dgb may be NULL. */
 int ag2v_spade_bwd_pre(const float* dout, const float* out, const float* x, const float* gamma, const float* mean,
                        const float* rstd, long long P, int C, int groups, int act, float slope, int round_ops,
-                       int chan_gamma, float* dgb, float* dxhat, float* partial, double* sums, ag2v_stream_t stream);
+                       int chan_gamma, int up_h, int up_w, float* dgb, float* dxhat, float* partial, double* sums,
+                       ag2v_stream_t stream);
+/* up_h / up_w > 0 (both calls): x is the low-resolution source [.., up_h/2, up_w/2, C] of a nearest
+ * 2x up-sampling; P counts full-resolution pixels per group and pass 2 writes the gradient of the
+ * low-resolution x (sum over the four children) to dx_low instead of working in place. */
 int ag2v_spade_bwd_dx(const float* x, float* dxhat, const float* mean, const float* rstd, const double* sums,
-                      double count, int training, long long P, int C, int groups, ag2v_stream_t stream);
+                      double count, int training, long long P, int C, int groups, int up_h, int up_w, float* dx_low,
+                      ag2v_stream_t stream);
 
 /* weight gradient of a 3x3 conv: split-K partials (tcgen05 MN-major kernel or mma.sync,
  * `impl` as for ag2v_conv3x3), then reduction + scatter to OIHW */

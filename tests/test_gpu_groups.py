@@ -271,3 +271,37 @@ def test_packed_weights_follow_a_fused_optimizer():
     out2 = run(fresh).detach()
     assert max_rel(out1, out0.detach()) > 1e-2, 'the optimizer step did not change the output'
     assert max_rel(out1, out2) <= 1e-5, max_rel(out1, out2)
+
+
+@pytest.mark.parametrize('training', [True, False])
+@pytest.mark.parametrize('impl', [1, 0])
+def test_spade_reads_its_input_through_the_upsampling(training, impl):
+    """SPADE(x, seg, upsample=True) == SPADE(F.interpolate(x, scale_factor=2), seg), forward, backward
+    (gradient of the low-resolution x = sum over its four children) and running statistics."""
+    import ag2video_b200.spade as sp
+    G, B, C, Lc, h, Hs = 2, 2, 64, 32, 8, 32
+    old = sp.CONV_IMPL
+    sp.CONV_IMPL = impl
+    try:
+        m1 = sp.SPADE('spadesyncbatch3x3', C, Lc).cuda()
+        m1.load_state_dict(det_state(m1.state_dict(), 5))
+        m1.fused_slope = 0.2
+        m2 = copy.deepcopy(m1)
+        m1.train(training), m2.train(training)
+        x = _rand(G * B, C, h, h, seed=1, cl=True).requires_grad_()
+        seg = _rand(G * B, Lc, Hs, Hs, seed=2, cl=True).requires_grad_()
+        cot = _rand(G * B, C, 2 * h, 2 * h, seed=3, cl=True)
+        out = m1(x, seg, groups=G, upsample=True)
+        (out * cot).sum().backward()
+        got = [out.detach(), x.grad.clone(), seg.grad.clone()] + [p.grad.clone() for p in m1.parameters()]
+        x.grad = seg.grad = None
+        ref = m2(F.interpolate(x, scale_factor=2, mode='nearest'), seg, groups=G)
+        (ref * cot).sum().backward()
+        want = [ref.detach(), x.grad, seg.grad] + [p.grad for p in m2.parameters()]
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert max_rel(a, b) <= 2e-5, (i, max_rel(a, b))
+        for name in ('running_mean', 'running_var'):
+            a, b = getattr(m1.param_free_norm, name), getattr(m2.param_free_norm, name)
+            assert max_rel(a, b) <= 1e-6, (name, max_rel(a, b))
+    finally:
+        sp.CONV_IMPL = old
