@@ -335,14 +335,16 @@ def run_ours(args):
                 'all_kernels': {k: {'TFLOPs': v[0] / (v[1] / 1e3) / 1e12, 'ms_per_step': v[1] / prof_steps, 'launches': v[2]}
                                 for k, v in agg.items()}}
     def shutdown():
-        # every rank leaves together; a rank that exits while another still tears NCCL down hangs the job
+        # Every rank leaves together and WITHOUT tearing NCCL down: destroying a communicator whose
+        # collectives live inside a captured CUDA graph (and the interpreter's own teardown order
+        # afterwards) hung the job after the result line had been printed.  os._exit skips both.
         if world > 1:
-            try:
-                dist.barrier()
-                torch.cuda.synchronize()
-                dist.destroy_process_group()
-            except Exception:
-                pass
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
     if rank != 0:
         shutdown()
