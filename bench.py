@@ -57,6 +57,15 @@ def peaks():
     return p
 
 
+# DRAM bytes of ONE launch (read + write) from `ncu --set full` captures, keyed like the per-shape
+# breakdown: (kind, epilogue, resolution, Cin, Nout, images).  Source: profiles/r01_ncu_r34_spade_groups.csv
+NCU_DRAM_BYTES = {
+    ('conv3x3', 'epi4', 256, 128, 512, 6): 1.0e9 + 751.5e6,     # algorithmic: 201 MB in + 805 MB read-modify-write
+    ('conv3x3', 'epi3', 256, 256, 128, 6): 0.6e9 + 172.5e6,
+    ('wgrad3x3', 'wgrad', 256, 512, 128, 6): 1.0e9 + 4.6e6,
+}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
@@ -166,6 +175,7 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # keep stdout for the one JSON line
     rank, world, local = agdist.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -322,17 +332,26 @@ def run_ours(args):
                 f.write('kind epi r Cin Nout launches ms_per_step TFLOPs\n')
                 for key, (fl_, ms_, n_) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
                     f.write('%s %d %.3f %.1f\n' % (' '.join(str(k) for k in key), n_, ms_ / prof_steps, fl_ / (ms_ / 1e3) / 1e12))
-        kind = max(agg, key=lambda k: agg[k][1])
-        fl, ms, n = agg[kind]
+        # the dominant kernel = the (kernel, shape) with the largest share of the step
+        key = max(by_shape, key=lambda k: by_shape[k][1])
+        fl, ms, n = by_shape[key]
         achieved = fl / (ms / 1e3) / 1e12
         tf32_peak = pk['bf16_tflops_sustained'] / 2.0
-        roof = {'bound': 'tensor', 'kernel': kind, 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                'frac': achieved / tf32_peak, 'traffic': None,
+        batch_imgs = args.batch * (args.frames - 1)
+        traffic = NCU_DRAM_BYTES.get(key + (batch_imgs,))
+        roof = {'bound': 'tensor', 'kernel': '%s %s r=%d Cin=%d Nout=%d (%d images)' % (key + (batch_imgs,)),
+                'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
+                'traffic': traffic,
+                'traffic_basis': ('dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full '
+                                  '(profiles/r01_ncu_r34_spade_groups.csv)') if traffic else None,
+                'flops_per_launch': fl / n,
                 'peak_basis': 'tf32 operands: half of the %s bf16 sustained peak (%.1f TFLOP/s)' % (pk['source'], pk['bf16_tflops_sustained']),
                 'frac_of_bf16_peak': achieved / pk['bf16_tflops_sustained'],
                 'launches': n, 'avg_launch_us': ms * 1e3 / n, 'share_of_step': (ms / prof_steps) / (ms_dev / args.steps),
                 'measured_in': 'eager pass of %d steps, CUDA events around every launch' % prof_steps,
-                'all_kernels': {k: {'TFLOPs': v[0] / (v[1] / 1e3) / 1e12, 'ms_per_step': v[1] / prof_steps, 'launches': v[2]}
+                'all_kernels': {k: {'TFLOPs': v[0] / (v[1] / 1e3) / 1e12, 'ms_per_step': v[1] / prof_steps, 'launches': v[2],
+                                    'frac': v[0] / (v[1] / 1e3) / 1e12 / tf32_peak,
+                                    'share_of_step': (v[1] / prof_steps) / (ms_dev / args.steps)}
                                 for k, v in agg.items()}}
     def shutdown():
         # Every rank leaves together and WITHOUT tearing NCCL down: destroying a communicator whose

@@ -1,6 +1,6 @@
 """A short run that launches each hot kernel a few times at BASELINE shapes, for ncu:
   ncu --set full --clock-control none --import-source on -k regex:<pattern> -c N -o gpurun_out/prof python tools/ncu_targets.py <what>
-what: spade | layout | gcn"""
+what: spade | layout | gcn | step (one whole train step at 256x256: K4 layout conv, K5 spectral norm, grouped SPADE)"""
 import os
 import sys
 
@@ -42,4 +42,15 @@ elif what == 'gcn':
     for _ in range(reps):
         o, p = m(obj, pred, edges.cuda(), ind.cuda())
         (o.sum() + p.sum()).backward()
+elif what == 'step':
+    from ag2video_b200.config import make_opt, synthetic_batch
+    from ag2video_b200.networks import AG2VideoModel
+    dev = torch.device('cuda', 0)
+    model = AG2VideoModel(make_opt(256, batch_size=2), dev).train()
+    b = synthetic_batch(B=2, F=4, image_size=256, seed=1, device=dev)
+    for _ in range(reps):
+        out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+        loss = (out[0] - b['imgs']).abs().mean() + 10 * (out[1] - b['boxes'])[:, 1:].abs().mean()
+        model.zero_grad(set_to_none=True)
+        loss.backward()
 torch.cuda.synchronize()
