@@ -346,49 +346,70 @@ __global__ void unpack_dw_kernel(const float* __restrict__ part, int nsplit, int
   }
 }
 
-// Channels-last weights [Co][3][3][Ci] (the convolutions of a channels_last module).
-//   forward : dst[tap][co][ci] = W[co][tap][ci]                     (row copies)
-__global__ void pack_w3x3_cl_fwd_kernel(const float* __restrict__ w, int Co, int Ci, int round_ops, float* __restrict__ dst) {
+// Channels-last weights [Co][3][3][Ci] (the convolutions of a channels_last module).  With a second
+// source (gamma, beta) the combined output index n follows gb8_col, as in pack_w3x3_kernel.
+//   forward : dst[tap][n][ci] = W(n)[co(n)][tap][ci]                (row copies)
+__global__ void pack_w3x3_cl_fwd_kernel(const float* __restrict__ wa, const float* __restrict__ wb,
+                                        const float* __restrict__ ba, const float* __restrict__ bb, int Co, int Ci,
+                                        int round_ops, float* __restrict__ dst, float* __restrict__ bias_dst) {
+  const int Ntot = wb ? 2 * Co : Co;
   const int Ci4 = Ci >> 2;
-  const long long total = 9LL * Co * Ci4;
+  const long long total = 9LL * Ntot * Ci4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % Ci4); const int co = (int)((i / Ci4) % Co); const int tap = (int)(i / ((long long)Ci4 * Co));
-    float4 v = *reinterpret_cast<const float4*>(w + ((size_t)co * 9 + tap) * Ci + 4 * c4);
+    const int c4 = (int)(i % Ci4); const int n = (int)((i / Ci4) % Ntot); const int tap = (int)(i / ((long long)Ci4 * Ntot));
+    int co = n, is_b = 0;
+    if (wb) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
+    float4 v = *reinterpret_cast<const float4*>((is_b ? wb : wa) + ((size_t)co * 9 + tap) * Ci + 4 * c4);
     if (round_ops) v = make_float4(elem_round_tf32(v.x), elem_round_tf32(v.y), elem_round_tf32(v.z), elem_round_tf32(v.w));
-    *reinterpret_cast<float4*>(dst + ((size_t)tap * Co + co) * Ci + 4 * c4) = v;
+    *reinterpret_cast<float4*>(dst + ((size_t)tap * Ntot + n) * Ci + 4 * c4) = v;
   }
-}
-//   dgrad   : dst[tap][ci][co] = W[co][8 - tap][ci]                  (32x32 tile transposes through smem)
-__global__ void __launch_bounds__(256) pack_w3x3_cl_dgrad_kernel(const float* __restrict__ w, int Co, int Ci, int round_ops,
-                                                                 float* __restrict__ dst) {
-  __shared__ float tile[32][33];
-  const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int co = co0 + r, ci = ci0 + tx;
-    tile[r][tx] = (co < Co && ci < Ci) ? w[((size_t)co * 9 + (8 - tap)) * Ci + ci] : 0.f;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int ci = ci0 + r, co = co0 + tx;
-    if (ci < Ci && co < Co) {
-      const float v = tile[tx][r];
-      dst[((size_t)tap * Ci + ci) * Co + co] = round_ops ? elem_round_tf32(v) : v;
+  if (bias_dst != nullptr && blockIdx.x == 0) {
+    for (int n = threadIdx.x; n < Ntot; n += blockDim.x) {
+      int co = n, is_b = 0;
+      if (wb) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
+      const float* bsrc = is_b ? bb : ba;
+      bias_dst[n] = bsrc ? bsrc[co] : 0.f;
     }
   }
 }
-// part[split][tap][co][ci] -> dW[co][tap][ci] (channels-last weight gradient)
-__global__ void unpack_dw_cl_kernel(const float* __restrict__ part, int nsplit, int Co, int Ci, float* __restrict__ dw) {
+//   dgrad   : dst[tap][ci][k] = W(k)[co(k)][8 - tap][ci]             (32x32 tile transposes through smem)
+__global__ void __launch_bounds__(256) pack_w3x3_cl_dgrad_kernel(const float* __restrict__ wa, const float* __restrict__ wb,
+                                                                 int Co, int Ci, int round_ops, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int Ntot = wb ? 2 * Co : Co;
+  const int tap = blockIdx.z, k0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, ci = ci0 + tx;
+    int co = k, is_b = 0;
+    if (wb) { is_b = (k >> 3) & 1; co = ((k >> 4) << 3) + (k & 7); }
+    tile[r][tx] = (k < Ntot && ci < Ci) ? (is_b ? wb : wa)[((size_t)co * 9 + (8 - tap)) * Ci + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, k = k0 + tx;
+    if (ci < Ci && k < Ntot) {
+      const float v = tile[tx][r];
+      dst[((size_t)tap * Ci + ci) * Ntot + k] = round_ops ? elem_round_tf32(v) : v;
+    }
+  }
+}
+// part[split][tap][n][ci] -> dW(n)[co(n)][tap][ci] (channels-last weight gradients)
+__global__ void unpack_dw_cl_kernel(const float* __restrict__ part, int nsplit, int Co, int Ci, int two,
+                                    float* __restrict__ dwa, float* __restrict__ dwb) {
+  const int Ntot = two ? 2 * Co : Co;
   const int Ci4 = Ci >> 2;
-  const long long per4 = 9LL * Co * Ci4, per = 9LL * Co * Ci;
+  const long long per4 = 9LL * Ntot * Ci4, per = 9LL * Ntot * Ci;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per4; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % Ci4); const int co = (int)((i / Ci4) % Co); const int tap = (int)(i / ((long long)Ci4 * Co));
+    const int c4 = (int)(i % Ci4); const int n = (int)((i / Ci4) % Ntot); const int tap = (int)(i / ((long long)Ci4 * Ntot));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < nsplit; ++s) {
       const float4 t = *reinterpret_cast<const float4*>(part + (size_t)s * per + 4 * i);
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
-    *reinterpret_cast<float4*>(dw + ((size_t)co * 9 + tap) * Ci + 4 * c4) = acc;
+    int co = n, is_b = 0;
+    if (two) { is_b = (n >> 3) & 1; co = ((n >> 4) << 3) + (n & 7); }
+    *reinterpret_cast<float4*>((is_b ? dwb : dwa) + ((size_t)co * 9 + tap) * Ci + 4 * c4) = acc;
   }
 }
 
@@ -607,26 +628,32 @@ extern "C" int ag2v_scaled_grad_pre(const float* dy, const float* scale, long lo
   return AG2V_OK;
 }
 
-// Channels-last 3x3 weights [Co][3][3][Ci] -> [9][Co][Ci] (dgrad = 0) or [9][Ci][Co] flipped (dgrad = 1)
-extern "C" int ag2v_pack_w3x3_cl(const float* w, int Co, int Ci, int dgrad, int round_ops, float* dst, cudaStream_t stream) {
-  AG2V_REQUIRE(w && dst && Co > 0 && Ci > 0 && Ci % 4 == 0, "pack_w3x3_cl: bad arguments (Ci %% 4 == 0 required)");
+// Channels-last 3x3 weights [Co][3][3][Ci] -> [9][N][Ci] (dgrad = 0) or [9][Ci][N] flipped (dgrad = 1);
+// wb != NULL: (wa, wb) = (mlp_gamma, mlp_beta) interleaved in gb8 order, N = 2 Co; bias_dst (dgrad = 0,
+// optional) receives the biases in the same column order.
+extern "C" int ag2v_pack_w3x3_cl(const float* wa, const float* wb, const float* ba, const float* bb, int Co, int Ci,
+                                 int dgrad, int round_ops, float* dst, float* bias_dst, cudaStream_t stream) {
+  AG2V_REQUIRE(wa && dst && Co > 0 && Ci > 0 && Ci % 4 == 0, "pack_w3x3_cl: bad arguments (Ci %% 4 == 0 required)");
+  AG2V_REQUIRE(!wb || Co % 8 == 0, "pack_w3x3_cl: gamma/beta packing needs Co %% 8 == 0");
+  const int Ntot = wb ? 2 * Co : Co;
   if (!dgrad) {
-    const long long total = 9LL * Co * (Ci / 4);
+    const long long total = 9LL * Ntot * (Ci / 4);
     const int blocks = (int)(ceil_div_ll(total, 256) > 2368 ? 2368 : ceil_div_ll(total, 256));
-    pack_w3x3_cl_fwd_kernel<<<blocks, 256, 0, stream>>>(w, Co, Ci, round_ops, dst);
+    pack_w3x3_cl_fwd_kernel<<<blocks, 256, 0, stream>>>(wa, wb, ba, bb, Co, Ci, round_ops, dst, bias_dst);
   } else {
-    pack_w3x3_cl_dgrad_kernel<<<dim3(ceil_div(Ci, 32), ceil_div(Co, 32), 9), 256, 0, stream>>>(w, Co, Ci, round_ops, dst);
+    pack_w3x3_cl_dgrad_kernel<<<dim3(ceil_div(Ci, 32), ceil_div(Ntot, 32), 9), 256, 0, stream>>>(wa, wb, Co, Ci, round_ops, dst);
   }
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
 
-// split-K partials [nsplit][9][Co][Ci] -> channels-last weight gradient [Co][3][3][Ci]
-extern "C" int ag2v_unpack_dw3x3_cl(const float* part, int nsplit, int Co, int Ci, float* dw, cudaStream_t stream) {
-  AG2V_REQUIRE(part && dw && nsplit > 0 && Co > 0 && Ci > 0 && Ci % 4 == 0, "unpack_dw3x3_cl: bad arguments");
-  const long long total = 9LL * Co * (Ci / 4);
+// split-K partials [nsplit][9][N][Ci] -> channels-last weight gradient(s) [Co][3][3][Ci]
+extern "C" int ag2v_unpack_dw3x3_cl(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
+                                    cudaStream_t stream) {
+  AG2V_REQUIRE(part && dwa && nsplit > 0 && Co > 0 && Ci > 0 && Ci % 4 == 0 && (!two || dwb), "unpack_dw3x3_cl: bad arguments");
+  const long long total = 9LL * (two ? 2 * Co : Co) * (Ci / 4);
   const int blocks = (int)(ceil_div_ll(total, 256) > 2368 ? 2368 : ceil_div_ll(total, 256));
-  unpack_dw_cl_kernel<<<blocks, 256, 0, stream>>>(part, nsplit, Co, Ci, dw);
+  unpack_dw_cl_kernel<<<blocks, 256, 0, stream>>>(part, nsplit, Co, Ci, two, dwa, dwb);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

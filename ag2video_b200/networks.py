@@ -23,6 +23,7 @@ from .graph import GraphTripleConv
 from .layout import boxes_to_layout_batched, layout_conv3x3, layout_tables
 from .spade import SPADEResnetBlock, SharedSeg, bn_act
 from .specnorm import SpectralNormGroup, conv_scaled, conv_unscaled
+from .thinconv import thin_conv3x3
 
 CL = torch.channels_last
 
@@ -210,13 +211,13 @@ class SPADEGenerator(nn.Module):
     def forward(self, layout, groups=1):
         seg = SharedSeg.wrap(layout)                       # one NHWC copy + one gradient buffer for all 18 SPADEs
         up = lambda z: F.interpolate(z, scale_factor=2, mode='nearest')
-        x = self.fc(F.interpolate(layout, size=(self.sh, self.sw)))
+        x = self.fc(seg.nearest(self.sh, self.sw))           # = F.interpolate(layout, size=(sh, sw))
         x = self.head_0(x, seg, groups)
         x = self.G_middle_0(up(x), seg, groups)
         x = self.G_middle_1(x, seg, groups)
         for name in ('up_0', 'up_1', 'up_2', 'up_3'):      # up(x) is read on the fly by the SPADE kernels
             x = getattr(self, name)(x, seg, groups, upsample=True)
-        return torch.tanh(self.conv_img(F.leaky_relu(x, 0.2)))
+        return thin_conv3x3(self.conv_img, x, slope_in=0.2, act_out='tanh')    # tanh(conv_img(leaky_relu(x, 0.2)))
 
 
 _GRID = {}
@@ -289,7 +290,7 @@ class Layout2VidGenerator(nn.Module):
             return layout_conv3x3(w[:, :2 * D], slots, tables, base), entry.scale_g     # 1/sigma is folded into the BN
 
         feat = fn.features(None, groups, first=layout_conv(flow_cb, prev))
-        flow = fn.conv_flow(feat) * fn.flow_multiplier
+        flow = thin_conv3x3(fn.conv_flow[0], feat) * fn.flow_multiplier
         warped = flow_warp(prev[:, -3:], flow)
         diff = prev[:, -3:] - warped
         conf = ((diff * diff).sum(dim=1, keepdim=True) < 0.02).float()

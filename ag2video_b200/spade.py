@@ -38,8 +38,8 @@ L.register('ag2v_pack_w3x3', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_i, c_p, c_p, c_p
 L.register('ag2v_unpack_dw3x3', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_double_to_float', c_i, [c_p, c_i, c_i, c_ll, c_p, c_p])
 L.register('ag2v_round_tf32', c_i, [c_p, c_p, c_ll, c_p])
-L.register('ag2v_pack_w3x3_cl', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p])
-L.register('ag2v_unpack_dw3x3_cl', c_i, [c_p, c_i, c_i, c_i, c_p, c_p])
+L.register('ag2v_pack_w3x3_cl', c_i, [c_p] * 4 + [c_i, c_i, c_i, c_i, c_p, c_p, c_p])
+L.register('ag2v_unpack_dw3x3_cl', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p])
 L.register('ag2v_scaled_grad_pre', c_i, [c_p, c_p, c_ll, c_i, c_i, c_p, c_p, c_p, c_p])
 L.register('ag2v_wgrad3x3_nsplit', c_i, [c_i] * 6)
 L.register('ag2v_wgrad3x3', c_i, [c_p, c_i, c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p])
@@ -125,11 +125,24 @@ def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, ep
                                  L.ptr(ws), nws, CONV_IMPL, L.stream()))
 
 
+def _is_cl(w):
+    """True when a 4-D weight is stored channels_last ([Co][kh][kw][Ci]) and not also contiguous."""
+    return w.dim() == 4 and not w.is_contiguous() and w.is_contiguous(memory_format=torch.channels_last) and w.shape[1] % 4 == 0
+
+
 def _pack(wa, wb, ba, bb, dgrad):
+    """GEMM-layout copy of one (or two interleaved) 3x3 weight(s), straight from the storage order
+    the module keeps them in (OIHW or channels_last)."""
     Co, Ci = wa.shape[0], wa.shape[1]
     Ntot = 2 * Co if wb is not None else Co
     dst = torch.empty(9 * Ntot * Ci, device=wa.device, dtype=torch.float32)
     bias = torch.empty(Ntot, device=wa.device, dtype=torch.float32) if not dgrad else None
+    if _is_cl(wa) and (wb is None or _is_cl(wb)):
+        L.check(L.lib().ag2v_pack_w3x3_cl(L.ptr(wa), L.ptr(wb), L.ptr(ba), L.ptr(bb), Co, Ci, int(dgrad), int(not _precise()),
+                                          L.ptr(dst), L.ptr(bias), L.stream()))
+        return dst, bias
+    wa = wa.contiguous()
+    wb = wb.contiguous() if wb is not None else None
     L.check(L.lib().ag2v_pack_w3x3(L.ptr(wa), L.ptr(wb), L.ptr(ba), L.ptr(bb), Co, Ci, int(dgrad), int(not _precise()),
                                    L.ptr(dst), L.ptr(bias), L.stream()))
     return dst, bias
@@ -142,9 +155,14 @@ def _wgrad(dy, Nout, x, x_strides, Cin, B, Hh, Ww, two, like_a, like_b):
     with _Timed('wgrad3x3', 2.0 * 9 * B * Hh * Ww * Cin * Nout, ('wgrad', Hh, Cin, Nout)):
         L.check(lib.ag2v_wgrad3x3(L.ptr(dy), Nout, L.ptr(x), x_strides[0], x_strides[1], x_strides[2], Cin, B, Hh, Ww,
                                   L.ptr(part), CONV_IMPL, L.stream()))
+    Co = Nout // 2 if two else Nout
+    if _is_cl(like_a) and (not two or _is_cl(like_b)):        # gradients in the parameters' own storage order
+        dwa = torch.empty_like(like_a, memory_format=torch.channels_last)
+        dwb = torch.empty_like(like_b, memory_format=torch.channels_last) if two else None
+        L.check(lib.ag2v_unpack_dw3x3_cl(L.ptr(part), nsplit, Co, Cin, int(two), L.ptr(dwa), L.ptr(dwb), L.stream()))
+        return dwa, dwb
     dwa = torch.empty_like(like_a, memory_format=torch.contiguous_format)
     dwb = torch.empty_like(like_b, memory_format=torch.contiguous_format) if two else None
-    Co = Nout // 2 if two else Nout
     L.check(lib.ag2v_unpack_dw3x3(L.ptr(part), nsplit, Co, Cin, int(two), L.ptr(dwa), L.ptr(dwb), L.stream()))
     return dwa, dwb
 
@@ -174,6 +192,15 @@ class SharedSeg:
             self.grad = torch.zeros_like(self.seg, memory_format=torch.channels_last)
         return self.grad
 
+    def nearest(self, h, w):
+        """``F.interpolate(seg, size=(h, w))`` (nearest, integer ratio) read from the shared copy;
+        its gradient goes straight into the shared buffer instead of a full-resolution tensor of
+        zeros (the generator's ``fc`` input, spade_models/networks/generator.py)."""
+        H, W = self.seg.shape[2:]
+        if H % h or W % w:
+            raise NotImplementedError('nearest resize %dx%d -> %dx%d is not an integer ratio' % (H, W, h, w))
+        return _SegNearestFn.apply(self.token, self, H // h, W // w)
+
 
 class _SharedSegFn(torch.autograd.Function):
     @staticmethod
@@ -189,6 +216,19 @@ class _SharedSegFn(torch.autograd.Function):
         g = ctx.handle.grad
         ctx.handle.grad = None
         return g, None
+
+
+class _SegNearestFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, token, handle, sy, sx):
+        ctx.handle, ctx.step = handle, (sy, sx)
+        return handle.seg[:, :, ::sy, ::sx].contiguous(memory_format=torch.channels_last)
+
+    @staticmethod
+    def backward(ctx, g):
+        sy, sx = ctx.step
+        ctx.handle.grad_buffer()[:, :, ::sy, ::sx] += g
+        return torch.zeros(1, device=g.device), None, None, None
 
 
 class _SpadeFn(torch.autograd.Function):
@@ -350,7 +390,8 @@ def _packed_cl(conv, w, dgrad):
     def build():
         Co, Ci = w.shape[0], w.shape[1]
         dst = torch.empty(9 * Co * Ci, device=w.device, dtype=torch.float32)
-        L.check(L.lib().ag2v_pack_w3x3_cl(L.ptr(w), Co, Ci, int(dgrad), int(not _precise()), L.ptr(dst), L.stream()))
+        L.check(L.lib().ag2v_pack_w3x3_cl(L.ptr(w), None, None, None, Co, Ci, int(dgrad), int(not _precise()), L.ptr(dst), None,
+                                          L.stream()))
         return dst
     return _cache_of(conv).get('dgrad' if dgrad else 'fwd', (w,), build)
 
@@ -411,7 +452,7 @@ class _SnConvFn(torch.autograd.Function):
             L.check(lib.ag2v_wgrad3x3(L.ptr(dys), Nout, L.ptr(x), r * rw * Cin, rw * Cin, Cin, Cin, B, r, rw, L.ptr(wpart),
                                       CONV_IMPL, L.stream()))
         dw = torch.empty_like(weight, memory_format=torch.channels_last)
-        L.check(lib.ag2v_unpack_dw3x3_cl(L.ptr(wpart), nsplit, Nout, Cin, L.ptr(dw), L.stream()))
+        L.check(lib.ag2v_unpack_dw3x3_cl(L.ptr(wpart), nsplit, Nout, Cin, 0, L.ptr(dw), None, L.stream()))
         return dx, dw, dbias, None, (dy if has_res else None), None, None
 
 
@@ -551,15 +592,15 @@ class SPADE(nn.Module):
 
     def _packed(self, w_sh, b_sh, w_g, b_g, w_b, b_b):
         def build():
-            w1, b1 = _pack(w_sh.contiguous(), None, b_sh, None, False)
-            w2, b2 = _pack(w_g.contiguous(), w_b.contiguous(), b_g, b_b, False)
+            w1, b1 = _pack(w_sh, None, b_sh, None, False)
+            w2, b2 = _pack(w_g, w_b, b_g, b_b, False)
             return dict(w1=w1, b1=b1, w2=w2, b2=b2)
         return _cache_of(self).get('fwd', (w_sh, b_sh, w_g, b_g, w_b, b_b), build)
 
     def _packed_t(self, w_sh, w_g, w_b):
         def build():
-            w1t, _ = _pack(w_sh.contiguous(), None, None, None, True)
-            w2t, _ = _pack(w_g.contiguous(), w_b.contiguous(), None, None, True)
+            w1t, _ = _pack(w_sh, None, None, None, True)
+            w2t, _ = _pack(w_g, w_b, None, None, True)
             return dict(w1t=w1t, w2t=w2t)
         return _cache_of(self).get('dgrad', (w_sh, w_g, w_b), build)
 

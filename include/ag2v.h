@@ -117,6 +117,20 @@ int ag2v_spectral_norm_sigma_bwd(int n, const float* dsigma, void* const* grad_w
                                  const int* taps, const int* channels_last, int iters, const float* save,
                                  size_t save_floats, ag2v_stream_t stream);
 
+/* K6 — 3x3 convolutions with 2-3 output channels at full resolution (the generator's conv_img
+ * 64 -> 3 between LeakyReLU(0.2) and tanh, spade_models/networks/generator.py; the flow head
+ * conv_flow 32 -> 2, flows_generator.py): streaming kernels, y = act_out(conv(act_in(x)) + bias).
+ * x [B,H,W,CI], y / dy [B,H,W,CO] NHWC; w [CO][CI][3][3] or channels-last [CO][3][3][CI]
+ * (w_channels_last); slope_in = LeakyReLU slope in front (1 = none); act_out 0 none, 1 tanh.
+ * Instantiated for (CI, CO) = (64, 3) and (32, 2). */
+int ag2v_thin_conv3x3_supported(int CI, int CO);
+size_t ag2v_thin_conv3x3_workspace_floats(int B, int H, int W, int CI, int CO);
+int ag2v_thin_conv3x3_fwd(const float* x, const float* w, const float* bias, int B, int H, int W, int CI, int CO,
+                          int w_channels_last, float slope_in, int act_out, float* y, ag2v_stream_t stream);
+int ag2v_thin_conv3x3_bwd(const float* x, const float* w, const float* dy, const float* y, int B, int H, int W, int CI,
+                          int CO, int w_channels_last, float slope_in, int act_out, float* dx, float* workspace,
+                          float* dw, float* dbias, ag2v_stream_t stream);
+
 /* masks_to_layout (models/layout.py:66-95, _pool_mask_samples :164-202) for one
  * (clip, frame): vecs [O,D], boxes [O,4] xywh, masks [O,M,M]; S [O,H,W] receives the
  * sampled masks (kept for the backward); test_mode != 0 composites objects in
@@ -225,10 +239,14 @@ int ag2v_wgrad3x3(const float* dy, int Nout, const float* x, long long x_sb, lon
                   int B, int Hh, int Ww, float* part, int impl, ag2v_stream_t stream);
 int ag2v_unpack_dw3x3(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
                       ag2v_stream_t stream);
-/* Main convolutions of SPADEResnetBlock (architecture.py:34-41,56-62) on the same implicit-GEMM
- * kernels: channels-last weight (un)packing and the pre-pass over the output gradient. */
-int ag2v_pack_w3x3_cl(const float* w, int Co, int Ci, int dgrad, int round_ops, float* dst, ag2v_stream_t stream);
-int ag2v_unpack_dw3x3_cl(const float* part, int nsplit, int Co, int Ci, float* dw, ag2v_stream_t stream);
+/* Channels-last ([Co][3][3][Ci]) variants of ag2v_pack_w3x3 / ag2v_unpack_dw3x3 (weights of a
+ * channels_last module are packed without a layout copy; the dgrad form is a tiled transpose), and
+ * the pre-pass over the output gradient of the main convolutions of SPADEResnetBlock
+ * (architecture.py:34-41,56-62), which run on the same implicit-GEMM kernels. */
+int ag2v_pack_w3x3_cl(const float* wa, const float* wb, const float* ba, const float* bb, int Co, int Ci, int dgrad,
+                      int round_ops, float* dst, float* bias_dst, ag2v_stream_t stream);
+int ag2v_unpack_dw3x3_cl(const float* part, int nsplit, int Co, int Ci, int two, float* dwa, float* dwb,
+                         ag2v_stream_t stream);
 /* dys = tf32(dy * scale[group]) on [groups][P][C]; sums[g][0..C) = sum dy (doubles) */
 int ag2v_scaled_grad_pre(const float* dy, const float* scale, long long P, int C, int groups, float* dys,
                          float* partial, double* sums, ag2v_stream_t stream);
