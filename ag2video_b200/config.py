@@ -50,6 +50,10 @@ def make_opt(image_size=256, batch_size=2, **overrides):
         n_blocks_F=6, nff=32, n_downsample_F=3, flow_deconv=False, flow_multiplier=20,
         frames_per_action=4, n_frames_G=2, bp_prev=0, learning_rate=1e-4, beta1=0.5,
         crop_size=32, gpu_ids=[],
+        # discriminator / losses (args.py:61-63,105,152-169)
+        num_D=2, n_layers_D=4, ndf=64, norm_D='spectralinstance', use_actions_loss=1, gan_mode='hinge',
+        no_ganFeat_loss=False, no_vgg_loss=True, lambda_feat=10.0, lambda_F_warp=10.0,
+        discriminator_img_loss_weight=1.0, bbox_pred_loss_weight=10, frames_per_action_graph=4,
     )
     for k, v in overrides.items():
         setattr(opt, k, v)

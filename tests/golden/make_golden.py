@@ -267,8 +267,64 @@ def generator_case():
                                 grad_picks={k: grads[k].flatten()[:4096].clone() for k in picks}))
 
 
+def losses_case():
+    """One training iteration's three losses at BASELINE config 1 (64x64, batch 2, 4 frames):
+    the reference's MultiscaleActionDiscriminator + LossModel (--no_vgg_loss) on the reference
+    generator's output, in the order of scripts/train.py:446-493."""
+    from models.spade_models.networks.discriminator import MultiscaleActionDiscriminator
+    from models.spade_models.loss_model import LossModel
+    opt = ref_opt(['--image_size', '64,64', '--batch_size', '2'])
+    m = AG2VideoModel(opt, torch.device('cpu'))
+    load_det(m, 61)
+    m.train()
+    netD = MultiscaleActionDiscriminator(opt)
+    load_det(netD, 71)
+    netD.train()
+    holder = types.SimpleNamespace(img_discriminator=netD)
+    lm = LossModel(opt, holder)
+    b = synthetic_batch(B=2, F=4, image_size=64, seed=99)
+    batch = (b['imgs'], b['objs'], b['boxes'], b['triplets'], b['actions'], None)
+    out = m(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], test_mode=False, use_gt=True)
+    # discriminator forward on the real frames: outputs of both scales, every level
+    n = opt.n_frames_G - 1
+    with torch.no_grad():
+        d_real = netD(b['imgs'][:, n:], b['objs'], b['boxes'][:, n:], [a[:, n:] for a in out[4]])
+    G = lm(batch, out, mode='compute_generator_loss')
+    G = {k: v.mean() for k, v in G.items()}
+    m.zero_grad(); netD.zero_grad()
+    G['total_loss'].backward()
+    g_grads = grads_of(m)
+    netD.zero_grad()
+    D = lm(batch, out, mode='compute_discriminator_loss')
+    D = {k: v.mean() for k, v in D.items()}
+    D['total_img_loss'].backward()
+    d_grads = {k: p.grad.clone() for k, p in netD.named_parameters() if p.grad is not None}
+    bg = synthetic_batch(B=2, F=16, image_size=64, seed=101, with_images=False)
+    boxes_pred = m(None, bg['objs'], bg['triplets'], bg['actions'], boxes_gt=bg['boxes'], test_mode=False, graph_only=True)
+    GG = lm((None, bg['objs'], bg['boxes'], bg['triplets'], bg['actions'], None), boxes_pred, mode='compute_graph_loss')
+    m.zero_grad()
+    GG['total_loss'].backward()
+    gg_grads = grads_of(m)
+    picks = ['layout_to_video.netG.up_3.norm_1.mlp_gamma.weight', 'layout_to_video.netG.fc.bias',
+             'acts_to_objs.gconvs.0.net1.0.weight', 'layout_to_video.flows_network.conv_flow.0.weight']
+    save('losses64.pt', dict(
+        seed_g=61, seed_d=71, batch_seed=99, graph_batch_seed=101,
+        d_real_last=[scale[-1].clone() for scale in d_real],
+        d_real_norms=[[float(o.norm()) for o in scale] for scale in d_real],
+        d_real_picks=[[o.flatten()[:1024].clone() for o in scale] for scale in d_real],
+        G={k: v.detach().clone() for k, v in G.items()}, D={k: v.detach().clone() for k, v in D.items()},
+        graph={k: v.detach().clone() for k, v in GG.items()},
+        g_grad_norms={k: float(v.norm()) for k, v in g_grads.items()},
+        g_grad_picks={k: g_grads[k].flatten()[:4096].clone() for k in picks if k in g_grads},
+        d_grad_norms={k: float(v.norm()) for k, v in d_grads.items()},
+        d_grad_picks={k: d_grads[k].flatten()[:2048].clone() for k in
+                      ['discriminator_0.model0.0.weight', 'discriminator_1.model3.0.0.weight_orig',
+                       'gconvs.0.net1.0.weight', 'fc_objs_vecs.weight', 'acts_embeddings.weight']},
+        graph_grad_norms={k: float(v.norm()) for k, v in gg_grads.items() if k.startswith('acts_to_boxes')}))
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['gconv', 'gconv_net', 'layout', 'masks', 'crop', 'spade', 'block',
-                             'acts2layout', 'generator']
+                             'acts2layout', 'generator', 'losses']
     for w in which:
         globals()['%s_case' % w]()

@@ -158,3 +158,65 @@ def test_generator64_matches_reference():
     bad = [k for k, n in c['grad_norms'].items()
            if abs(float(grads[k].norm()) - n) > 2e-3 * max(n, 1e-6)]
     assert not bad, bad[:5]
+
+
+def test_losses64_match_reference():
+    """One training iteration's losses (scripts/train.py:446-493) at BASELINE config 1: the oracle
+    discriminator + LossModel against the reference's, on the oracle generator's output."""
+    from oracle import losses as oloss
+    c = golden('losses64.pt')
+    opt = make_opt(64, batch_size=2)
+    m = onet.AG2VideoModel(opt)
+    m.load_state_dict(det_state(m.state_dict(), c['seed_g']), strict=True)
+    m.train()
+    netD = oloss.MultiscaleActionDiscriminator(opt)
+    netD.load_state_dict(det_state(netD.state_dict(), c['seed_d']), strict=True)
+    netD.train()
+    lm = oloss.LossModel(opt, netD)
+    b = synthetic_batch(B=2, F=4, image_size=64, seed=c['batch_seed'])
+    out = m(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+    n = opt.n_frames_G - 1
+    with torch.no_grad():
+        d_real = netD(b['imgs'][:, n:], b['objs'], b['boxes'][:, n:], [a[:, n:] for a in out[4]])
+    for s, scale in enumerate(d_real):
+        assert max_rel(scale[-1], c['d_real_last'][s]) <= 2e-5
+        for j, o in enumerate(scale):
+            assert max_rel(o.flatten()[:1024], c['d_real_picks'][s][j]) <= 2e-5, (s, j)
+            assert abs(float(o.norm()) - c['d_real_norms'][s][j]) <= 1e-5 * c['d_real_norms'][s][j]
+    G = lm.compute_generator_loss(b, out)
+    # the warp loss bilinearly samples WHITE-NOISE frames at flow-displaced positions: the 2e-4
+    # summation-order noise of the flow network (see test_generator64) moves it by ~1e-3, so it is
+    # checked strictly on the reference's own flows and loosely on the oracle generator's
+    strict = lm.compute_generator_loss(b, (out[0], out[1], golden('generator64.pt')['flows'], out[3], out[4]))
+    assert abs(float(strict['loss_F_Warp']) - float(c['G']['loss_F_Warp'])) <= 2e-5 * abs(float(c['G']['loss_F_Warp']))
+    for k, v in c['G'].items():
+        tol = 5e-3 if k in ('loss_F_Warp', 'total_loss') else 2e-5
+        assert abs(float(G[k]) - float(v)) <= tol * abs(float(v)), k
+    m.zero_grad(); netD.zero_grad()
+    G['total_loss'].backward()
+    grads = _grads(m)
+    for k, v in c['g_grad_picks'].items():
+        assert max_rel(grads[k].flatten()[:4096], v) <= 1e-3, k
+    bad = [k for k, nrm in c['g_grad_norms'].items() if abs(float(grads[k].norm()) - nrm) > 5e-3 * max(nrm, 1e-6)]
+    assert not bad, bad[:5]
+    netD.zero_grad()
+    D = lm.compute_discriminator_loss(b, out)
+    for k, v in c['D'].items():
+        assert abs(float(D[k]) - float(v)) <= 2e-5 * abs(float(v)), k
+    D['total_img_loss'].backward()
+    dg = _grads(netD)
+    for k, v in c['d_grad_picks'].items():
+        # hinge gates of the D loss flip for the few logits within 2e-5 of +-1 (the fake frames carry
+        # the generator's summation-order noise): gradients move by O(flipped share), not O(eps)
+        assert max_rel(dg[k].flatten()[:2048], v) <= 1e-2, k
+    bad = [k for k, nrm in c['d_grad_norms'].items() if abs(float(dg[k].norm()) - nrm) > 5e-3 * max(nrm, 1e-6)]
+    assert not bad, bad[:5]
+    bg = synthetic_batch(B=2, F=16, image_size=64, seed=c['graph_batch_seed'], with_images=False)
+    boxes_pred = m(None, bg['objs'], bg['triplets'], bg['actions'], boxes_gt=bg['boxes'], graph_only=True)
+    GG = lm.compute_graph_loss(bg, boxes_pred)
+    assert abs(float(GG['total_loss']) - float(c['graph']['total_loss'])) <= 1e-5 * abs(float(c['graph']['total_loss']))
+    m.zero_grad()
+    GG['total_loss'].backward()
+    gg = _grads(m)
+    bad = [k for k, nrm in c['graph_grad_norms'].items() if abs(float(gg[k].norm()) - nrm) > 1e-3 * max(nrm, 1e-6)]
+    assert not bad, bad[:5]
