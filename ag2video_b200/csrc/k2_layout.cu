@@ -94,7 +94,7 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256)
 layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ wx_g,
                   const float* __restrict__ wy_g, const float* __restrict__ scale, int O, int D, int H,
-                  int W, float* __restrict__ out) {
+                  int W, size_t out_nstride, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   float* wx_s = smem;
   float* wy_s = wx_s + (size_t)O * W;
@@ -143,7 +143,7 @@ layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ wx_g
         }
       }
       for (int c = 0; c < chans; ++c) {
-        float* dst = out + (((size_t)n * D + d0 + c) * H + y0 + r) * W;
+        float* dst = out + (size_t)n * out_nstride + (((size_t)d0 + c) * H + y0 + r) * W;
         float coef[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) coef[a] = v_s[oa[a] * kDC + c] * wya[a];
@@ -164,7 +164,7 @@ layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ wx_g
       continue;
     }
     for (int c = 0; c < chans; ++c) {
-      float* dst = out + (((size_t)n * D + d0 + c) * H + y0 + r) * W;
+      float* dst = out + (size_t)n * out_nstride + (((size_t)d0 + c) * H + y0 + r) * W;
       if (VEC4) {
         for (int x4 = lane; x4 < (W >> 2); x4 += 32) {
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256)
 layout_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ wx_g,
                   const float* __restrict__ wy_g, const int4* __restrict__ range,
                   const float* __restrict__ scale, int N, int O, int D, int H, int W,
-                  float* __restrict__ dvecs) {
+                  size_t dout_nstride, float* __restrict__ dvecs) {
   const int lane = threadIdx.x & 31;
   const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (task >= (long long)N * O * D) return;
@@ -215,7 +215,7 @@ layout_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ wx_g
   if (rg.y > rg.x && rg.w > rg.z) {
     const float* wx = wx_g + (size_t)no * W;
     const float* wy = wy_g + (size_t)no * H;
-    const float* src = dout + ((size_t)n * D + d) * H * W;
+    const float* src = dout + (size_t)n * dout_nstride + (size_t)d * H * W;
     const int xa = rg.x & ~31;
     for (int x = xa + lane; x < rg.y; x += 32) {
       const float wxx = (x >= rg.x) ? wx[x] : 0.f;
@@ -288,16 +288,20 @@ extern "C" int ag2v_boxes_to_layout_tables(const float* boxes, const uint8_t* va
   return AG2V_OK;
 }
 
-extern "C" int ag2v_boxes_to_layout_fwd(const float* vecs, const float* boxes, const uint8_t* valid,
-                                        const float* lin_x, const float* lin_y, int N, int O, int D,
-                                        int H, int W, int avg, void* workspace, float* out,
-                                        cudaStream_t stream) {
+// out[n] starts at out + n * out_nstride floats and holds [D,H,W]: out_nstride = D*H*W is the plain
+// [N,D,H,W] tensor, a larger stride writes the layout straight into a channel slice of a wider
+// NCHW buffer (the discriminator's cat[img, seg], discriminator.py:338-342).
+static int layout_fwd_impl(const float* vecs, const float* boxes, const uint8_t* valid,
+                           const float* lin_x, const float* lin_y, int N, int O, int D,
+                           int H, int W, int avg, void* workspace, float* out, size_t out_nstride,
+                           cudaStream_t stream) {
   int rc = layout_check(N, O, D, H, W);
   if (rc) return rc;
   if (N == 0 || D == 0) return AG2V_OK;
   AG2V_REQUIRE(out && workspace && lin_x && lin_y, "boxes_to_layout_fwd: null pointer");
+  AG2V_REQUIRE(out_nstride >= (size_t)D * H * W, "boxes_to_layout_fwd: batch stride %zu smaller than D*H*W", out_nstride);
   if (O == 0) {
-    AG2V_CUDA(cudaMemsetAsync(out, 0, (size_t)N * D * H * W * sizeof(float), stream));
+    AG2V_CUDA(cudaMemset2DAsync(out, out_nstride * sizeof(float), 0, (size_t)D * H * W * sizeof(float), N, stream));
     return AG2V_OK;
   }
   AG2V_REQUIRE(vecs && boxes, "boxes_to_layout_fwd: null pointer");
@@ -307,24 +311,39 @@ extern "C" int ag2v_boxes_to_layout_fwd(const float* vecs, const float* boxes, c
   AG2V_LAUNCH_CHECK();
   size_t smem = ((size_t)O * W + (size_t)O * (kRB + kDC)) * sizeof(float);
   dim3 grid(ceil_div(H, kRB), ceil_div(D, kDC), N);
-  bool vec4 = (W % 4 == 0) && (((uintptr_t)out & 15) == 0);
+  bool vec4 = (W % 4 == 0) && (((uintptr_t)out & 15) == 0) && (out_nstride % 4 == 0);
   if (vec4) {
     AG2V_CUDA(cudaFuncSetAttribute(layout_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layout_fwd_kernel<true><<<grid, 256, smem, stream>>>(vecs, ws.wx, ws.wy, ws.scale, O, D, H, W, out);
+    layout_fwd_kernel<true><<<grid, 256, smem, stream>>>(vecs, ws.wx, ws.wy, ws.scale, O, D, H, W, out_nstride, out);
   } else {
     AG2V_CUDA(cudaFuncSetAttribute(layout_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layout_fwd_kernel<false><<<grid, 256, smem, stream>>>(vecs, ws.wx, ws.wy, ws.scale, O, D, H, W, out);
+    layout_fwd_kernel<false><<<grid, 256, smem, stream>>>(vecs, ws.wx, ws.wy, ws.scale, O, D, H, W, out_nstride, out);
   }
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }
 
+extern "C" int ag2v_boxes_to_layout_fwd(const float* vecs, const float* boxes, const uint8_t* valid,
+                                        const float* lin_x, const float* lin_y, int N, int O, int D,
+                                        int H, int W, int avg, void* workspace, float* out,
+                                        cudaStream_t stream) {
+  return layout_fwd_impl(vecs, boxes, valid, lin_x, lin_y, N, O, D, H, W, avg, workspace, out, (size_t)D * H * W, stream);
+}
+
+extern "C" int ag2v_boxes_to_layout_fwd_strided(const float* vecs, const float* boxes, const uint8_t* valid,
+                                                const float* lin_x, const float* lin_y, int N, int O, int D,
+                                                int H, int W, int avg, void* workspace, float* out,
+                                                long long out_batch_stride, cudaStream_t stream) {
+  AG2V_REQUIRE(out_batch_stride >= 0, "boxes_to_layout_fwd_strided: negative batch stride");
+  return layout_fwd_impl(vecs, boxes, valid, lin_x, lin_y, N, O, D, H, W, avg, workspace, out, (size_t)out_batch_stride, stream);
+}
+
 // `workspace` must be the buffer a forward call with the same boxes filled
 // (the tables are reused); pass recompute=1 to rebuild them from boxes.
-extern "C" int ag2v_boxes_to_layout_bwd(const float* dout, const float* boxes, const uint8_t* valid,
-                                        const float* lin_x, const float* lin_y, int N, int O, int D,
-                                        int H, int W, int avg, int recompute, void* workspace,
-                                        float* dvecs, cudaStream_t stream) {
+static int layout_bwd_impl(const float* dout, size_t dout_nstride, const float* boxes, const uint8_t* valid,
+                           const float* lin_x, const float* lin_y, int N, int O, int D,
+                           int H, int W, int avg, int recompute, void* workspace,
+                           float* dvecs, cudaStream_t stream) {
   int rc = layout_check(N, O, D, H, W);
   if (rc) return rc;
   if (N == 0 || D == 0 || O == 0) return AG2V_OK;
@@ -338,7 +357,22 @@ extern "C" int ag2v_boxes_to_layout_bwd(const float* dout, const float* boxes, c
   }
   long long tasks = (long long)N * O * D;
   layout_bwd_kernel<<<(unsigned)ceil_div_ll(tasks, 8), 256, 0, stream>>>(dout, ws.wx, ws.wy, ws.range,
-                                                                         ws.scale, N, O, D, H, W, dvecs);
+                                                                         ws.scale, N, O, D, H, W, dout_nstride, dvecs);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
+}
+
+extern "C" int ag2v_boxes_to_layout_bwd(const float* dout, const float* boxes, const uint8_t* valid,
+                                        const float* lin_x, const float* lin_y, int N, int O, int D,
+                                        int H, int W, int avg, int recompute, void* workspace,
+                                        float* dvecs, cudaStream_t stream) {
+  return layout_bwd_impl(dout, (size_t)D * H * W, boxes, valid, lin_x, lin_y, N, O, D, H, W, avg, recompute, workspace, dvecs, stream);
+}
+
+extern "C" int ag2v_boxes_to_layout_bwd_strided(const float* dout, long long dout_batch_stride, const float* boxes,
+                                                const uint8_t* valid, const float* lin_x, const float* lin_y, int N,
+                                                int O, int D, int H, int W, int avg, int recompute, void* workspace,
+                                                float* dvecs, cudaStream_t stream) {
+  AG2V_REQUIRE(dout_batch_stride >= (long long)D * H * W, "boxes_to_layout_bwd_strided: batch stride smaller than D*H*W");
+  return layout_bwd_impl(dout, (size_t)dout_batch_stride, boxes, valid, lin_x, lin_y, N, O, D, H, W, avg, recompute, workspace, dvecs, stream);
 }

@@ -5,6 +5,8 @@
 launch and takes the callers' object masks (models/utils.py:95-102) as a device
 tensor instead of boolean-index compaction, so there is no host sync.
 """
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -77,6 +79,61 @@ def boxes_to_layout(vecs, boxes, H, W=None, pooling='sum'):
     avg = _pooling_flag(pooling)
     W = H if W is None else W
     return _BoxesToLayoutFn.apply(vecs.unsqueeze(0), boxes.unsqueeze(0), None, int(H), int(W), avg)
+
+
+L.register('ag2v_boxes_to_layout_fwd_strided', L.c_i, [L.c_p] * 5 + [L.c_i] * 6 + [L.c_p] * 2 + [ctypes.c_longlong, L.c_p])
+L.register('ag2v_boxes_to_layout_bwd_strided', L.c_i, [L.c_p, ctypes.c_longlong] + [L.c_p] * 4 + [L.c_i] * 7 + [L.c_p] * 2 + [L.c_p])
+
+
+class _LayoutCatFn(torch.autograd.Function):
+    """x = cat([img, boxes_to_layout(vecs, boxes)], dim=1) in ONE pass: the layout kernel writes
+    channels [C, C+D) of the NCHW result directly (batch-strided output), the image is copied
+    into channels [0, C).  Backward: dimg = dx[:, :C]; dvecs read from dx[:, C:] in place."""
+
+    @staticmethod
+    def forward(ctx, img, vecs, boxes, valid, H, W):
+        L.need_cuda(img, vecs, boxes, valid)
+        vecs, boxes = L.f32c(vecs), L.f32c(boxes)
+        N, O, D = vecs.shape
+        C = img.shape[1]
+        if tuple(img.shape) != (N, C, H, W):
+            raise RuntimeError('layout_cat: img %s does not match N=%d H=%d W=%d' % (tuple(img.shape), N, H, W))
+        lib = L.lib()
+        dev = vecs.device
+        if valid is not None:
+            valid = valid.contiguous()
+            valid = valid.view(torch.uint8) if valid.dtype == torch.bool else (valid != 0).view(torch.uint8)
+        ws = torch.empty(max(lib.ag2v_boxes_to_layout_workspace_bytes(N, O, H, W), 16), device=dev, dtype=torch.uint8)
+        x = torch.empty(N, C + D, H, W, device=dev, dtype=torch.float32)
+        x[:, :C].copy_(img)
+        L.check(lib.ag2v_boxes_to_layout_fwd_strided(L.ptr(vecs), L.ptr(boxes), L.ptr(valid), L.ptr(_linspace(W, dev)),
+                                                     L.ptr(_linspace(H, dev)), N, O, D, H, W, 0, L.ptr(ws),
+                                                     ctypes.c_void_p(x.data_ptr() + 4 * C * H * W), (C + D) * H * W, L.stream()))
+        ctx.save_for_backward(ws)
+        ctx.dims = (N, O, D, H, W, C)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        (ws,) = ctx.saved_tensors
+        N, O, D, H, W, C = ctx.dims
+        dx = L.f32c(dx)
+        dimg = dx[:, :C] if ctx.needs_input_grad[0] else None
+        dvecs = None
+        if ctx.needs_input_grad[1]:
+            dvecs = torch.zeros(N, O, D, device=dx.device, dtype=torch.float32)
+            L.check(L.lib().ag2v_boxes_to_layout_bwd_strided(ctypes.c_void_p(dx.data_ptr() + 4 * C * H * W), (C + D) * H * W,
+                                                             None, None, None, None, N, O, D, H, W, 0, 0, L.ptr(ws),
+                                                             L.ptr(dvecs), L.stream()))
+        return dimg, dvecs, None, None, None, None
+
+
+def layout_cat(img, vecs, boxes, valid, H, W=None):
+    """cat([img, boxes_to_layout_batched(vecs, boxes, valid, H, W)], dim=1) without building
+    the layout or the copy of it: img [N,C,H,W], vecs [N,O,D], boxes [N,O,4] -> [N,C+D,H,W]
+    (the discriminator input of discriminator.py:317-342)."""
+    W = H if W is None else W
+    return _LayoutCatFn.apply(img, vecs, boxes, valid, int(H), int(W))
 
 
 L.register('ag2v_masks_to_layout_fwd', L.c_i, [L.c_p] * 5 + [L.c_i] * 6 + [L.c_p] * 3 + [L.c_p])

@@ -68,6 +68,18 @@ int ag2v_boxes_to_layout_fwd(const float* vecs, const float* boxes, const uint8_
 int ag2v_boxes_to_layout_bwd(const float* dout, const float* boxes, const uint8_t* valid, const float* lin_x,
                              const float* lin_y, int N, int O, int D, int H, int W, int avg, int recompute,
                              void* workspace, float* dvecs, ag2v_stream_t stream);
+/* Same kernels with a batch stride (in floats, >= D*H*W) on the image side: sample n lives at
+ * out + n*out_batch_stride as [D,H,W].  Writes the layout straight into a channel slice of a
+ * wider NCHW buffer - the discriminator's cat([img, seg], dim=channels)
+ * (spade_models/networks/discriminator.py:338-342) - and reads its gradient from the same
+ * slice, so neither the 256-channel layout nor the concatenation copy exists. */
+int ag2v_boxes_to_layout_fwd_strided(const float* vecs, const float* boxes, const uint8_t* valid, const float* lin_x,
+                                     const float* lin_y, int N, int O, int D, int H, int W, int avg, void* workspace,
+                                     float* out, long long out_batch_stride, ag2v_stream_t stream);
+int ag2v_boxes_to_layout_bwd_strided(const float* dout, long long dout_batch_stride, const float* boxes,
+                                     const uint8_t* valid, const float* lin_x, const float* lin_y, int N, int O, int D,
+                                     int H, int W, int avg, int recompute, void* workspace, float* dvecs,
+                                     ag2v_stream_t stream);
 
 /* ---- K4: layout fused into its consumer convolution ----------
  * conv3x3(layout)[co,p] = sum_o sum_k U[o,k,co] * m_o(p+k) with U[o,k,:] = W[:,:,k] v[o,:]: the
