@@ -4,13 +4,15 @@
     python bench.py --gpus N --steps K --warmup W             (ours, B200)
     python bench.py --impl reference --steps K --warmup W     (CPU arm: the oracle port)
 
-One "step" = one pass of the hot path over one batch of synthetic CATER-shaped
-clips: both action-graph models (K1), all B*F layouts (K2), flow warp +
-conv_dim_in (cuDNN, out of scope) and the SPADE generator for the F-1 generated
-frames (K3), forward + backward + Adam.  Workload = BASELINE.json configs[2]:
-256x256, batch 2 clips per GPU, frames_per_action 4 (8 frames per GPU step).
-The loss is an L1 image + box surrogate: the reference's GAN / feature-matching
-losses need the discriminator, which is outside the path.
+One "step" = one training iteration of the reference (scripts/train.py:440-493) on one batch of
+synthetic CATER-shaped clips: generator step (both action-graph models K1, all layouts K2 fused
+into their consumer convolutions, flow warp, SPADE generator K3 for the F-1 generated frames,
+GAN + feature-matching + flow-warp loss through the action discriminator, backward, Adam),
+discriminator step (hinge loss on fake / real, backward, Adam) and graph step (acts_to_boxes on a
+16-frame graph batch, masked smooth-L1, backward, Adam).  The VGG perceptual loss is off
+(--no_vgg_loss: its weights are a download).  Workload = BASELINE.json configs[2]: 256x256,
+batch 2 clips per GPU, frames_per_action 4 (8 frames per GPU step).  --generator-only times
+the generator step alone with an L1 surrogate loss (the round-1 bench line).
 
 Prints ONE JSON line (rank 0).  value = frames/s with inputs resident in HBM;
 e2e = the same through the public API with the pinned-host -> device copy of
@@ -42,6 +44,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--conv-impl', type=int, default=0, help='0 auto, 1 mma.sync, 2 tcgen05')
     ap.add_argument('--no-cudnn-benchmark', action='store_true', help='keep cuDNN heuristics for the out-of-path convolutions')
+    ap.add_argument('--generator-only', action='store_true', help='generator fwd+bwd+Adam with an L1 surrogate loss (no discriminator / graph step)')
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -106,27 +109,67 @@ def surrogate_loss(out, batch):
 
 
 # ------------------------------------------------------------------ CPU arm ---
-def cpu_sample(size, seconds_budget, steps, warmup, threads=None):
-    """The oracle (CPU port of the reference's algorithm, oracle/) on a bounded
-    sample of the workload: ONE clip, TWO frames (one generated frame) at the full
-    resolution, generator forward + backward + Adam.  Returns frames/s and details."""
+def workload_text(args):
+    if args.generator_only:
+        return ('AG2Vid CATER %dx%d generator train step (GCN -> layout -> SPADE, fwd+bwd+Adam), batch %d clips/GPU x %d frames'
+                % (args.size, args.size, args.batch, args.frames))
+    return ('AG2Vid CATER %dx%d train iteration (generator step + discriminator step + graph step, scripts/train.py:440-493, '
+            '--no_vgg_loss), batch %d clips/GPU x %d frames + graph batch %d clips x %d frames'
+            % (args.size, args.size, args.batch, args.frames, args.batch, 4 * args.frames))
+
+
+def cpu_sample(size, seconds_budget, steps, warmup, threads=None, generator_only=False, frames=4):
+    """The oracle (CPU port of the reference's algorithm, oracle/) on a bounded sample of the
+    workload: ONE clip, TWO frames (one generated frame) at the full resolution - the whole
+    iteration (generator, discriminator and graph step; the graph batch is one 4*frames-frame
+    clip), or the generator step alone.  Returns frames/s and details."""
     from ag2video_b200.config import make_opt, synthetic_batch
+    from oracle import losses as oloss
     from oracle import networks as onet
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     opt = make_opt(size, batch_size=1)
     model = onet.AG2VideoModel(opt).train()
-    optim = torch.optim.Adam(model.parameters(), lr=opt.learning_rate, betas=(opt.beta1, 0.999))
+    kw = dict(lr=opt.learning_rate, betas=(opt.beta1, 0.999))
     b = synthetic_batch(B=1, F=2, image_size=size, seed=1234)
+    if generator_only:
+        optim = torch.optim.Adam(model.parameters(), **kw)
 
-    def step():
-        out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
-        loss = surrogate_loss(out, b)
-        optim.zero_grad(set_to_none=True)
-        loss.backward()
-        optim.step()
-        return float(loss.detach())
+        def step():
+            out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+            loss = surrogate_loss(out, b)
+            optim.zero_grad(set_to_none=True)
+            loss.backward()
+            optim.step()
+            return float(loss.detach())
+        what = 'generator fwd+bwd+Adam'
+    else:
+        netD = oloss.MultiscaleActionDiscriminator(opt).train()
+        lm = oloss.LossModel(opt, netD)
+        graph_ids = {id(p) for p in model.acts_to_boxes.parameters()}
+        o_graph = torch.optim.Adam(model.acts_to_boxes.parameters(), **kw)
+        o_gen = torch.optim.Adam([p for p in model.parameters() if id(p) not in graph_ids], **kw)
+        o_d = torch.optim.Adam(netD.parameters(), **kw)
+        bg = synthetic_batch(B=1, F=4 * frames, image_size=size, seed=4321, with_images=False)
+
+        def step():
+            out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+            G = lm.compute_generator_loss(b, out)
+            o_gen.zero_grad(set_to_none=True)
+            G['total_loss'].backward()
+            o_gen.step()
+            D = lm.compute_discriminator_loss(b, out)
+            o_d.zero_grad(set_to_none=True)
+            D['total_img_loss'].backward()
+            o_d.step()
+            boxes_pred = model(None, bg['objs'], bg['triplets'], bg['actions'], boxes_gt=bg['boxes'], graph_only=True)
+            GG = lm.compute_graph_loss(bg, boxes_pred)
+            o_graph.zero_grad(set_to_none=True)
+            GG['total_loss'].backward()
+            o_graph.step()
+            return float(G['total_loss'].detach())
+        what = 'full iteration (G + D + graph step on a 1 clip x %d frames graph batch)' % (4 * frames)
 
     t0 = time.perf_counter()
     step()                                   # first step also serves as warm-up / cost probe
@@ -140,23 +183,21 @@ def cpu_sample(size, seconds_budget, steps, warmup, threads=None):
         step()
     dt = (time.perf_counter() - t0) / n
     return {'value': 2.0 / dt, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-            'sample': '1 clip x 2 frames (1 generated) at %dx%d, generator fwd+bwd+Adam, oracle/ torch CPU fp32, '
-                      '%d timed step(s) of %.1f s' % (size, size, n, dt), 's_per_step': dt, 'steps': n}
+            'sample': '1 clip x 2 frames (1 generated) at %dx%d, %s, oracle/ torch CPU fp32, '
+                      '%d timed step(s) of %.1f s' % (size, size, what, n, dt), 's_per_step': dt, 'steps': n}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    res = cpu_sample(args.size, 150.0, args.steps, args.warmup)
+    res = cpu_sample(args.size, 150.0, args.steps, args.warmup, generator_only=args.generator_only, frames=args.frames)
     line = {
         'impl': 'reference', 'metric': 'train-step frames/sec at CATER 256x256', 'value': res['value'],
         'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': res['steps'], 'warmup': min(args.warmup, 1),
         'ms_per_step': res['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'AG2Vid CATER %dx%d generator train step (GCN -> layout -> SPADE, fwd+bwd+Adam), '
-                               'batch %d clips/GPU x %d frames' % (args.size, args.size, args.batch, args.frames),
-                   'sample': res['sample']},
+        'config': {'workload': workload_text(args), 'sample': res['sample']},
         'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': res['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -192,28 +233,46 @@ def run_ours(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_sample(args.size, 25.0, 1, 0)
+        cpu_base = cpu_sample(args.size, 25.0, 1, 0, generator_only=args.generator_only, frames=args.frames)
 
     torch.manual_seed(0)
     opt = make_opt(args.size, batch_size=args.batch, frames_per_action=args.frames)
     model = AG2VideoModel(opt, dev).train()
-    graph_params = list(model.acts_to_boxes.parameters())
-    gen_params = list(model.acts_to_objs.parameters()) + list(model.layout_to_video.parameters())
-    opt_graph = torch.optim.Adam(graph_params, lr=opt.learning_rate, betas=(opt.beta1, 0.999), fused=True, capturable=True)
-    opt_gen = torch.optim.Adam(gen_params, lr=opt.learning_rate, betas=(opt.beta1, 0.999), fused=True, capturable=True)
-    buckets = agdist.GradBuckets(graph_params + gen_params) if world > 1 else None
+    trainer = None
+    if args.generator_only:
+        graph_params = list(model.acts_to_boxes.parameters())
+        gen_params = list(model.acts_to_objs.parameters()) + list(model.layout_to_video.parameters())
+        opt_graph = torch.optim.Adam(graph_params, lr=opt.learning_rate, betas=(opt.beta1, 0.999), fused=True, capturable=True)
+        opt_gen = torch.optim.Adam(gen_params, lr=opt.learning_rate, betas=(opt.beta1, 0.999), fused=True, capturable=True)
+        buckets = agdist.GradBuckets(graph_params + gen_params) if world > 1 else None
+    else:
+        from ag2video_b200.discriminator import MetaDiscriminatorModel
+        from ag2video_b200.losses import LossModel
+        from ag2video_b200.trainer import Trainer
+        discriminator = MetaDiscriminatorModel(opt, dev)
+        trainer = Trainer(opt, model, discriminator, LossModel(opt, discriminator), world=world)
 
-    # a small pool of distinct clips per rank in pinned host memory (disjoint seeds per rank = sharding by clip)
+    # a small pool of distinct clips per rank in pinned host memory (disjoint seeds per rank = sharding by clip);
+    # keys g_* = the long graph batch of the graph step (no images)
     pool_host = []
     for i in range(4):
         b = synthetic_batch(B=args.batch, F=args.frames, image_size=args.size, seed=1234 + 1000 * rank + i,
                             pad_to=(11, 6))          # CATER maxima: 10 objects + dummy, 6 actions -> static shapes
+        if trainer is not None:
+            g = synthetic_batch(B=args.batch, F=4 * args.frames, image_size=args.size, seed=4321 + 1000 * rank + i,
+                                pad_to=(11, 6), with_images=False)
+            b.update({'g_' + k: v for k, v in g.items() if v is not None})
         pool_host.append({k: v.pin_memory() for k, v in b.items()})
     pool_dev = [{k: v.to(dev) for k, v in b.items()} for b in pool_host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
     loss_host = torch.zeros(1).pin_memory()
 
     def train_step(batch):
+        if trainer is not None:
+            clip = {k: v for k, v in batch.items() if not k.startswith('g_')}
+            graph = {k[2:]: v for k, v in batch.items() if k.startswith('g_')}
+            G, D, GG = trainer.iteration(clip, graph)
+            return G['total_loss'].detach() + D['total_img_loss'].detach() + GG['total_loss'].detach()
         out = model(batch['imgs'], batch['objs'], batch['triplets'], batch['actions'], boxes_gt=batch['boxes'], use_gt=True)
         loss = surrogate_loss(out, batch)
         opt_graph.zero_grad(set_to_none=True)
@@ -372,11 +431,11 @@ def run_ours(args):
         'metric': 'train-step frames/sec at CATER 256x256', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 GEMMs / f32 elsewhere', 'data': 'synthetic',
-        'config': {'workload': 'AG2Vid CATER %dx%d generator train step (GCN -> layout -> SPADE, fwd+bwd+Adam), '
-                               'batch %d clips/GPU x %d frames' % (args.size, args.size, args.batch, args.frames),
-                   'loss': 'L1 image + box surrogate (discriminator is outside the path)',
+        'config': {'workload': workload_text(args),
+                   'loss': ('L1 image + box surrogate (generator step only)' if args.generator_only else
+                            'reference losses: GAN hinge + feature matching + flow warp (G), hinge (D), masked smooth-L1 (graph); no VGG'),
                    'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush',
-                   'parallelism': 'dp%d (clips sharded per rank, gradient all-reduce, SyncBN stats for SPADE)' % world,
+                   'parallelism': 'dp%d (clips sharded per rank, gradient all-reduce per optimiser, SyncBN stats for SPADE)' % world,
                    'conv_impl': args.conv_impl, 'step_execution': mode},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},

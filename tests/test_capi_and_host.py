@@ -77,3 +77,29 @@ def test_synthetic_batch_contract():
         assert torch.equal(b['boxes'][i, 0, n], torch.tensor([0., 0., 1., 1.]))      # the __image__ dummy
         assert (b['boxes'][i, :, n + 1:] == -1).all()                                 # padding rows
         assert (b['triplets'][i, 0, :n, 2] == n).all()
+
+
+def test_discriminator_state_dict_matches_reference_layout():
+    """Same keys and shapes as the reference's MultiscaleActionDiscriminator (the oracle's tree loads
+    the reference's state names, tests/test_oracle_golden.py::test_losses64_match_reference)."""
+    from ag2video_b200.discriminator import MultiscaleActionDiscriminator
+    from oracle import losses as oloss
+    opt = make_opt(64)
+    ours, ref = MultiscaleActionDiscriminator(opt).state_dict(), oloss.MultiscaleActionDiscriminator(opt).state_dict()
+    assert list(ours.keys()) == list(ref.keys())
+    assert all(ours[k].shape == ref[k].shape for k in ref)
+
+
+def test_trainer_partitions_parameters_like_the_reference():
+    """optimizer_graph owns acts_to_boxes, optimizer_generator everything else (train.py:365-368)."""
+    from ag2video_b200.discriminator import MetaDiscriminatorModel
+    from ag2video_b200.losses import LossModel
+    from ag2video_b200.networks import AG2VideoModel
+    from ag2video_b200.trainer import Trainer
+    opt = make_opt(64)
+    m, meta = AG2VideoModel(opt), MetaDiscriminatorModel(opt, fused=False)
+    tr = Trainer(opt, m, meta, LossModel(opt, meta), fused=False)
+    n_graph = sum(p.numel() for p in m.acts_to_boxes.parameters())
+    assert sum(p.numel() for p in tr.graph_params) == n_graph
+    assert sum(p.numel() for p in tr.gen_params) == sum(p.numel() for p in m.parameters()) - n_graph
+    assert len({id(p) for p in tr.gen_params} & {id(p) for p in tr.graph_params}) == 0

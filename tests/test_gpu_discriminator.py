@@ -1,0 +1,121 @@
+"""Discriminator-side callers and the three losses of one iteration (SURVEY.md section 8, rows
+ctx / f4) on the sm_100a path, against the CPU oracle and the reference's golden losses."""
+import pytest
+import torch
+
+from _util import det_state, golden, max_rel
+from ag2video_b200.config import make_opt, synthetic_batch
+
+gpu = pytest.mark.gpu
+
+
+def _to(b, dev):
+    return {k: (v.to(dev) if v is not None else None) for k, v in b.items()}
+
+
+@gpu
+@pytest.mark.parametrize('N,O,D,C,H,W', [(4, 6, 16, 3, 32, 32), (3, 11, 256, 3, 64, 64), (2, 5, 10, 2, 24, 36)])
+def test_layout_cat_is_cat_of_layout(N, O, D, C, H, W):
+    """layout_cat == cat([img, boxes_to_layout_batched]) bit for bit, forward and backward."""
+    from ag2video_b200.layout import boxes_to_layout_batched, layout_cat
+    g = torch.Generator().manual_seed(N * 100 + O)
+    xy = torch.rand(N, O, 2, generator=g) * 0.7
+    wh = torch.rand(N, O, 2, generator=g) * 0.3 + 0.05
+    boxes = torch.cat([xy, wh], dim=-1).cuda()
+    boxes[0, 0] = 0.0                                        # an all-zero box is dropped
+    valid = (torch.rand(N, O, generator=g) > 0.2).cuda()
+    img = torch.randn(N, C, H, W, generator=g).cuda()
+    vecs = torch.randn(N, O, D, generator=g).cuda()
+    cot = torch.randn(N, C + D, H, W, generator=g).cuda()
+    i1, v1 = img.clone().requires_grad_(), vecs.clone().requires_grad_()
+    got = layout_cat(i1, v1, boxes, valid, H, W)
+    (got * cot).sum().backward()
+    i2, v2 = img.clone().requires_grad_(), vecs.clone().requires_grad_()
+    want = torch.cat([i2, boxes_to_layout_batched(v2, boxes, valid, H, W)], dim=1)
+    (want * cot).sum().backward()
+    assert torch.equal(got, want)
+    assert torch.equal(i1.grad, i2.grad)
+    assert torch.equal(v1.grad, v2.grad)
+
+
+def _models(size, seed_g, seed_d, dev):
+    from ag2video_b200.discriminator import MetaDiscriminatorModel
+    from ag2video_b200.losses import LossModel
+    from ag2video_b200.networks import AG2VideoModel
+    opt = make_opt(size, batch_size=2)
+    m = AG2VideoModel(opt)
+    m.load_state_dict(det_state(m.state_dict(), seed_g), strict=True)
+    m = m.to(dev).to(memory_format=torch.channels_last).train()
+    meta = MetaDiscriminatorModel(opt, device=dev)
+    meta.img_discriminator.load_state_dict(det_state(meta.img_discriminator.state_dict(), seed_d), strict=True)
+    return opt, m, meta, LossModel(opt, meta)
+
+
+@gpu
+def test_discriminator_forward_backward_matches_oracle():
+    """Our discriminator (K1 graph layers, K2 layouts into the cat buffer, cuDNN PatchGAN in fp32)
+    against the CPU oracle on the same weights: every level of both scales, and parameter gradients."""
+    from oracle import losses as oloss
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device('cuda', 0)
+    opt, m, meta, lm = _models(64, 61, 71, dev)
+    ref = oloss.MultiscaleActionDiscriminator(opt)
+    ref.load_state_dict(det_state(ref.state_dict(), 71), strict=True)
+    ref.train()
+    b = synthetic_batch(B=2, F=4, image_size=64, seed=99)
+    bc = _to(b, dev)
+    with torch.no_grad():
+        _, _, actions_data = m.acts_to_objs(bc['objs'], bc['triplets'], bc['actions'], bc['boxes'])
+    ad_c = [a[:, 1:] for a in actions_data]
+    ad_r = [a[:, 1:].cpu() for a in actions_data]
+    got = meta.img_discriminator(bc['imgs'][:, 1:], bc['objs'], bc['boxes'][:, 1:], ad_c)
+    want = ref(b['imgs'][:, 1:], b['objs'], b['boxes'][:, 1:], ad_r)
+    errs = {}
+    for s in range(len(want)):
+        for j in range(len(want[s])):
+            errs['out%d.%d' % (s, j)] = max_rel(got[s][j], want[s][j])
+    sum(o[-1].mean() + 0.1 * o[1].abs().mean() for o in got).backward()
+    sum(o[-1].mean() + 0.1 * o[1].abs().mean() for o in want).backward()
+    gr = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+    for k, p in meta.img_discriminator.named_parameters():
+        if k in gr:
+            errs['grad ' + k] = max_rel(p.grad, gr[k])
+        else:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+    print({k: '%.2e' % v for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if v > 1e-3}
+    assert not bad, bad
+
+
+@gpu
+def test_iteration_losses_match_reference_golden():
+    """One training iteration (train.py:440-493) at BASELINE config 1 through Trainer.iteration:
+    the losses against the reference's own values (tests/golden/losses64.pt)."""
+    from ag2video_b200.trainer import Trainer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    c = golden('losses64.pt')
+    dev = torch.device('cuda', 0)
+    opt, m, meta, lm = _models(64, c['seed_g'], c['seed_d'], dev)
+    tr = Trainer(opt, m, meta, lm)
+    b = _to(synthetic_batch(B=2, F=4, image_size=64, seed=c['batch_seed']), dev)
+    bg = _to(synthetic_batch(B=2, F=16, image_size=64, seed=c['graph_batch_seed'], with_images=False), dev)
+    before = {k: v.detach().clone() for k, v in meta.img_discriminator.state_dict().items()}
+    G, D, GG = tr.iteration(b, bg)
+    torch.cuda.synchronize()
+    errs = {}
+    for name, got, want in (('G', G, c['G']), ('D', D, c['D']), ('graph', GG, c['graph'])):
+        for k, v in want.items():
+            errs['%s.%s' % (name, k)] = abs(float(got[k]) - float(v)) / abs(float(v))
+    print({k: '%.2e' % v for k, v in errs.items()})
+    # the graph loss and the real-image hinge do not pass through the TF32 SPADE stack: tight
+    assert errs['graph.total_loss'] <= 1e-4 and errs['D.D_img_real'] <= 1e-3, errs
+    # everything computed from the generated frames (18 TF32 SPADE layers deep, see test_gpu_generator)
+    assert max(errs.values()) <= 1e-2, errs
+    # all three optimisers stepped; the discriminator did not move before its own step's backward
+    after = meta.img_discriminator.state_dict()
+    moved = [k for k in before if before[k].is_floating_point() and not torch.equal(before[k], after[k])]
+    assert any('discriminator_0.model0.0.weight' in k for k in moved) and any('gconvs.0' in k for k in moved)
+    for p in tr.graph_params + tr.gen_params:
+        assert p.grad is None or torch.isfinite(p.grad).all()

@@ -1,5 +1,6 @@
 """Reduce an `ncu --metrics gpu__time_duration.sum --csv` log of a bench.py run to the launches of
-its LAST train step (steps are delimited by layout_conv_fwd_kernel, launched once per step), plus
+its LAST full train step (steps are delimited by a kernel launched once per step, default
+specnorm_fwd_kernel), plus
 a per-kernel summary with each kernel's share of the step.
     python tools/launch_list.py gpurun_out/x/launches_raw.csv > profiles/rNN_launches_bench.csv"""
 import csv
@@ -18,7 +19,8 @@ for r in rd:
     u = r[iu]
     us = v / 1e3 if u in ('ns', 'nsecond') else v if u in ('us', 'usecond') else v * 1e3 if u in ('ms', 'msecond') else v / 1e3
     rows.append((r[ik], us))
-marks = [i for i, (k, _) in enumerate(rows) if 'layout_conv_fwd_kernel' in k]
+DELIM = sys.argv[2] if len(sys.argv) > 2 else 'specnorm_fwd_kernel'      # launched once per train step
+marks = [i for i, (k, _) in enumerate(rows) if DELIM in k]
 if len(marks) >= 2:
     step = rows[marks[-2]:marks[-1]]
 else:
@@ -31,7 +33,7 @@ for k, us in step:
     a[0] += us
     a[1] += 1
 w = csv.writer(sys.stdout)
-w.writerow(['# one train step (between two layout_conv_fwd_kernel launches): %d launches, %.1f us serialised (ncu, cold cache, --clock-control none)' % (len(step), total)])
+w.writerow(['# one train step (between two %s launches): %d launches, %.1f us serialised (ncu, cold cache, --clock-control none)' % (DELIM, len(step), total)])
 w.writerow(['kernel', 'launches', 'us_total', 'share_of_step'])
 for name, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     w.writerow([name, n, '%.1f' % us, '%.4f' % (us / total)])

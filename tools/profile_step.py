@@ -1,5 +1,5 @@
 """Kernel-time breakdown of one bench step (torch.profiler / CUPTI), top kernels by GPU time.
-Usage on the GPU box: python tools/profile_step.py [size] [batch] > gpurun_out/step_profile.txt"""
+Usage on the GPU box: python tools/profile_step.py [size] [batch] [iteration|generator] > gpurun_out/step_profile.txt"""
 import os
 import sys
 
@@ -11,19 +11,31 @@ from ag2video_b200.networks import AG2VideoModel  # noqa: E402
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+what = sys.argv[3] if len(sys.argv) > 3 else 'iteration'          # iteration | generator
 dev = torch.device('cuda', 0)
 opt = make_opt(size, batch_size=B)
 model = AG2VideoModel(opt, dev).train()
-optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.5, 0.999), fused=True)
-b = synthetic_batch(B=B, F=4, image_size=size, seed=1, device=dev)
+b = synthetic_batch(B=B, F=4, image_size=size, seed=1, device=dev, pad_to=(11, 6))
+if what == 'generator':
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.5, 0.999), fused=True)
 
+    def step():
+        out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+        loss = (out[0] - b['imgs']).abs().mean() + 10 * (out[1] - b['boxes'])[:, 1:].abs().mean()
+        optim.zero_grad(set_to_none=True)
+        loss.backward()
+        optim.step()
+else:
+    from ag2video_b200.discriminator import MetaDiscriminatorModel
+    from ag2video_b200.losses import LossModel
+    from ag2video_b200.trainer import Trainer
+    meta = MetaDiscriminatorModel(opt, dev)
+    trainer = Trainer(opt, model, meta, LossModel(opt, meta))
+    bg = synthetic_batch(B=B, F=16, image_size=size, seed=2, device=dev, pad_to=(11, 6), with_images=False)
+    bg = {k: v for k, v in bg.items() if v is not None}
 
-def step():
-    out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
-    loss = (out[0] - b['imgs']).abs().mean() + 10 * (out[1] - b['boxes'])[:, 1:].abs().mean()
-    optim.zero_grad(set_to_none=True)
-    loss.backward()
-    optim.step()
+    def step():
+        trainer.iteration(b, bg)
 
 
 for _ in range(2):
