@@ -220,3 +220,24 @@ def test_losses64_match_reference():
     gg = _grads(m)
     bad = [k for k, nrm in c['graph_grad_norms'].items() if abs(float(gg[k].norm()) - nrm) > 1e-3 * max(nrm, 1e-6)]
     assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize('name', ['mixed32', 'demo64', 'rect', 'avg', 'cater128'])
+def test_closed_form_layout_matches_reference(name):
+    """The numpy closed form (no grid_sample) against the reference's boxes_to_layout: identical
+    pixel support, values to fp32 summation noise - an independent pin of K2's contract."""
+    import numpy as np
+    from oracle import closed_form
+    c = golden('layout.pt')[name]
+    out, support = closed_form.boxes_to_layout(c['vecs'], c['boxes'], c['H'], c['W'], pooling=c['pooling'])
+    ref = c['out'].numpy()
+    assert out.shape == ref.shape
+    # support of the whole layout: a pixel is touched iff some object covers it (generic vecs: no cancellation)
+    assert np.array_equal(support.any(axis=0), (ref[0] != 0).any(axis=0))
+    assert max_rel(torch.from_numpy(out), c['out']) <= 2e-6
+    # per-object support against the restated torch path on single-object layouts
+    for o in range(c['boxes'].shape[0]):
+        if not bool(c['boxes'][o].any()):
+            continue
+        one = oops.boxes_to_layout(torch.ones(1, 1), c['boxes'][o:o + 1], c['H'], c['W'])
+        assert np.array_equal(support[o], (one[0, 0] != 0).numpy()), o
