@@ -42,7 +42,7 @@ def hinge_loss(preds, target_is_real, for_discriminator):
 
 def _unpack(batch):
     if isinstance(batch, dict):
-        return batch['imgs'], batch['objs'], batch['boxes']
+        return batch.get('imgs'), batch['objs'], batch['boxes']
     return batch[0], batch[1], batch[2]
 
 
