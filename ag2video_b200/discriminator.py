@@ -5,8 +5,11 @@
 sm_100a kernels:
 
 * its 2-layer action-graph network (``GraphTripleConv``, K1) per frame,
-* its 256-channel layouts (K2) for all (clip, frame) pairs in ONE launch, written
-  straight into the channel slice of the ``cat([img, seg])`` input buffer
+* its 256-channel layouts are never built: the first PatchGAN convolution of every scale
+  (4x4, stride 2, 259 -> 64) is evaluated through the layout's rank-1 structure
+  (``layout.layout_sconv``, K7), the coarser scales from the average-pooled separable masks.
+  ``rank1_stem = False`` keeps the dense form: K2 writes all (clip, frame) layouts in ONE
+  launch straight into the channel slice of the ``cat([img, seg])`` buffer
   (``layout.layout_cat``) - the reference materialises the layout, then copies it.
 
 The conditioning (graph vectors -> fc -> per-object layout vectors) depends only on
@@ -22,7 +25,7 @@ import torch.nn.functional as F
 from torch.nn.utils import spectral_norm
 
 from .graph import GraphTripleConv
-from .layout import layout_cat
+from .layout import layout_cat, layout_sconv, layout_tables, layout_tables_avgpool, pooled_size
 from .networks import AttributeEmbeddings, real_object_mask
 
 
@@ -53,6 +56,14 @@ class NLayerActionDiscriminator(nn.Module):
             outs.append(x)
         return outs
 
+    def from_stem(self, y):
+        """Levels 1.. given the output of model0 (the stem evaluated elsewhere)."""
+        outs = [y]
+        for sub in list(self.children())[1:]:
+            y = sub(y)
+            outs.append(y)
+        return outs
+
 
 class MultiscaleActionDiscriminator(nn.Module):
     def __init__(self, opt):
@@ -64,6 +75,10 @@ class MultiscaleActionDiscriminator(nn.Module):
         n_attr = len(v['attributes'])
         obj_in = n_attr * emb
         self.pad_act = v['action_name_to_idx']['__padding__']
+        self.num_D = opt.num_D
+        # evaluate the PatchGAN stems through the layout's rank-1 structure (K7); False = materialise the
+        # layout inside the cat([img, seg]) buffer (K2) and run the dense library convolution
+        self.rank1_stem = bool(getattr(opt, 'rank1_stem', True)) and opt.ndf == 64
         for i in range(opt.num_D):
             self.add_module('discriminator_%d' % i, NLayerActionDiscriminator(opt))
         self.attribute_embedding = AttributeEmbeddings(v['attributes'], emb)
@@ -101,30 +116,59 @@ class MultiscaleActionDiscriminator(nn.Module):
         return torch.stack(per_t, dim=1)
 
     def condition(self, objs, layout_boxes, actions_data):
-        """Per-object layout vectors for every (clip, frame): (vecs [B*T,O,2*gconv_dim], boxes
-        [B*T,O,4], valid [B*T,O]) - discriminator.py:317-331 without the boolean-index
-        compaction (the object mask travels to the kernel instead)."""
+        """Everything the PatchGAN stems need from the graph side, for every (clip, frame):
+        (vecs [B*T,O,2*gconv_dim], boxes [B*T,O,4], valid [B*T,O], tables per scale) -
+        discriminator.py:317-331 without the boolean-index compaction (the object mask travels to the
+        kernel instead).  ``tables`` = the separable mask tables at every scale (K2 tables, then their
+        3x3/stride-2 average pools): data only, shared by all passes."""
         B, T, O = layout_boxes.shape[:3]
         obj_vecs = self.get_obj_vecs(objs, layout_boxes, actions_data)
         att = self.attribute_embedding(objs)
         vecs = self.fc_objs_vecs(torch.cat([att.unsqueeze(1).expand(B, T, O, att.shape[-1]), obj_vecs], dim=-1))
         valid = real_object_mask(objs, self.vocab).unsqueeze(1).expand(B, T, O)
-        return vecs.reshape(B * T, O, -1), layout_boxes.reshape(B * T, O, 4), valid.reshape(B * T, O)
+        vecs, boxes, valid = vecs.reshape(B * T, O, -1), layout_boxes.reshape(B * T, O, 4), valid.reshape(B * T, O)
+        tables = None
+        if self.rank1_stem:
+            H = self.image_size
+            tables = [layout_tables(boxes, valid, H, H)]
+            for _ in range(1, self.num_D):
+                tables.append(layout_tables_avgpool(tables[-1], B * T, O, H, H))
+                H = pooled_size(H)
+        return vecs, boxes, valid, tables
+
+    @staticmethod
+    def _pool(x):
+        return F.avg_pool2d(x, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)
 
     def forward(self, img, objs, layout_boxes, actions_data, cond=None):
         """List (scale) of lists (level) of PatchGAN outputs, discriminator.py:317-353.
         ``cond`` = a ``condition(...)`` result to reuse (same objs / boxes / actions)."""
         if cond is None:
             cond = self.condition(objs, layout_boxes, actions_data)
-        vecs, boxes, valid = cond
+        vecs, boxes, valid, tables = cond
         H = self.image_size
-        x = layout_cat(img.reshape(-1, *img.shape[2:]), vecs, boxes, valid, H, H)
+        img = img.reshape(-1, *img.shape[2:])
         nets = [D for name, D in self.named_children() if name.startswith('discriminator')]
         result = []
+        if not self.rank1_stem:
+            # the layout is written straight into the channel slice of cat([img, seg]) (K2, batch-strided)
+            x = layout_cat(img, vecs, boxes, valid, H, H)
+            for i, D in enumerate(nets):
+                result.append(D(x))
+                if i + 1 < len(nets):       # (the reference also pools after the last scale and drops it)
+                    x = self._pool(x)
+            return result
+        # rank-1 stem (csrc/k7_layoutconv_strided.cu): conv(cat[img, seg]) = conv(img; W[:, :3]) + b + the
+        # layout part evaluated from its separable masks; the pooled scales use pooled images / pooled masks
         for i, D in enumerate(nets):
-            result.append(D(x))
-            if i + 1 < len(nets):           # (the reference also pools after the last scale and drops it)
-                x = F.avg_pool2d(x, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)
+            conv = D.model0[0]
+            w = conv.weight
+            base = F.conv2d(img, w[:, :3], conv.bias, stride=conv.stride, padding=conv.padding)
+            base = base.contiguous(memory_format=torch.channels_last)
+            y = layout_sconv(w[:, 3:], vecs, tables[i], base, H, H, stride=conv.stride[0], pad=conv.padding[0])
+            result.append(D.from_stem(D.model0[1](y)))
+            if i + 1 < len(nets):
+                img, H = self._pool(img), pooled_size(H)
         return result
 
 

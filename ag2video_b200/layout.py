@@ -248,3 +248,71 @@ def layout_conv3x3(weight, vec_slots, tables, base):
         us.append((v.reshape(N * O, D) @ wj.t()).view(N, O, 9, Co))
     U = torch.cat(us, dim=1)                                                              # [N, slots*O, 9, Co]
     return _LayoutConvFn.apply(base, U, tables, U.shape[1])
+
+
+# ---- K7: the PatchGAN stem through the rank-1 layout ---------------
+L.register('ag2v_layout_tables_avgpool', L.c_i, [L.c_p] + [L.c_i] * 4 + [L.c_p] + [L.c_p])
+L.register('ag2v_layout_sconv_bwd_workspace_floats', L.c_sz, [L.c_i] * 5)
+L.register('ag2v_layout_sconv_fwd', L.c_i, [L.c_p, L.c_p] + [L.c_i] * 8 + [L.c_p] + [L.c_p])
+L.register('ag2v_layout_sconv_bwd', L.c_i, [L.c_p, L.c_p] + [L.c_i] * 8 + [L.c_p, L.c_p] + [L.c_p])
+
+
+def pooled_size(n):
+    """Output size of avg_pool2d(kernel 3, stride 2, padding 1)."""
+    return (n - 1) // 2 + 1
+
+
+def layout_tables_avgpool(tables, N, S, H, W):
+    """Tables of the 3x3 / stride-2 / pad-1 average pool (count_include_pad=False) of the masks in
+    ``tables`` (boxes [N,S,4] at H x W): the pooled masks stay separable, so every consumer of the
+    tables works unchanged at the coarser scale (discriminator.py:271)."""
+    H2, W2 = pooled_size(H), pooled_size(W)
+    out = torch.empty(max(L.lib().ag2v_boxes_to_layout_workspace_bytes(N, S, H2, W2), 16), device=tables.device, dtype=torch.uint8)
+    L.check(L.lib().ag2v_layout_tables_avgpool(L.ptr(tables), N, S, H, W, L.ptr(out), L.stream()))
+    return out
+
+
+class _LayoutSConvFn(torch.autograd.Function):
+    """base [N,Co,Ho,Wo] (channels_last, modified IN PLACE) += sum_s sum_k U[n,s,k,:] * m_s(stride*p + k - pad)."""
+
+    @staticmethod
+    def forward(ctx, base, U, tables, H, W, kernel, stride, pad):
+        L.need_cuda(base, U, tables)
+        N, Co, Ho, Wo = base.shape
+        S = U.shape[1]
+        if not base.is_contiguous(memory_format=torch.channels_last) or base.dtype != torch.float32:
+            raise RuntimeError('layout_sconv: base must be a float32 channels_last tensor')
+        if (Ho, Wo) != ((H + 2 * pad - kernel) // stride + 1, (W + 2 * pad - kernel) // stride + 1):
+            raise RuntimeError('layout_sconv: base %s does not match input %dx%d' % (tuple(base.shape), H, W))
+        U = L.f32c(U)
+        L.check(L.lib().ag2v_layout_sconv_fwd(L.ptr(U), L.ptr(tables), N, S, Co, H, W, kernel, stride, pad, L.ptr(base), L.stream()))
+        ctx.mark_dirty(base)
+        ctx.save_for_backward(tables)
+        ctx.dims = (N, S, Co, H, W, Ho, kernel, stride, pad)
+        return base
+
+    @staticmethod
+    def backward(ctx, dout):
+        (tables,) = ctx.saved_tensors
+        N, S, Co, H, W, Ho, kernel, stride, pad = ctx.dims
+        dout = dout.float().contiguous(memory_format=torch.channels_last)
+        dU = None
+        if ctx.needs_input_grad[1]:
+            lib = L.lib()
+            KK = kernel * kernel
+            part = torch.empty(lib.ag2v_layout_sconv_bwd_workspace_floats(N, S, Co, Ho, KK), device=dout.device, dtype=torch.float32)
+            dU = torch.empty(N, S, KK, Co, device=dout.device, dtype=torch.float32)
+            L.check(lib.ag2v_layout_sconv_bwd(L.ptr(dout), L.ptr(tables), N, S, Co, H, W, kernel, stride, pad, L.ptr(part),
+                                              L.ptr(dU), L.stream()))
+        return dout, dU, None, None, None, None, None, None
+
+
+def layout_sconv(weight, vecs, tables, base, H, W, stride=2, pad=2):
+    """conv2d(layout(vecs), weight, stride, pad) added in place to ``base`` without building the layout:
+    weight [Co, D, k, k] (the layout channels of the consumer convolution), vecs [N,O,D], tables for the
+    boxes [N,O,4] at the convolution's input resolution H x W, base [N,Co,Ho,Wo] channels_last."""
+    Co, D, k, _ = weight.shape
+    N, O = vecs.shape[:2]
+    wk = weight.permute(2, 3, 0, 1).reshape(k * k * Co, D)                     # [(ky, kx, co), ci]
+    U = (vecs.reshape(N * O, D) @ wk.t()).view(N, O, k * k, Co)
+    return _LayoutSConvFn.apply(base, U, tables, int(H), int(W), int(k), int(stride), int(pad))

@@ -96,6 +96,23 @@ int ag2v_layout_conv_fwd(const float* U, const void* tables, int N, int S, int C
 int ag2v_layout_conv_bwd(const float* dout, const void* tables, int N, int S, int Co, int H, int W, float* part,
                          float* dU, ag2v_stream_t stream);
 
+/* ---- K7: the discriminator's PatchGAN stem through the rank-1 layout ----
+ * Replaces boxes_to_layout + torch.cat([img, seg]) + the dense 4x4 stride-2 convolution 259 -> 64 of
+ * NLayerActionDiscriminator.model0 (spade_models/networks/discriminator.py:317-342, :326-372) and, for
+ * the coarser scales, the avg_pool2d(3, stride 2, padding 1, count_include_pad=False) of the
+ * concatenation (:271, :350):
+ *   conv(seg)[co,p] = sum_o sum_k U[o,k,co] * m_o(stride*p + k - pad),  U[o,k,:] = W[:,3:,k] v[o,:]
+ * tables / tables_out: workspaces of ag2v_boxes_to_layout_workspace_bytes at (H,W) / ((H-1)/2+1,(W-1)/2+1);
+ * U, dU [N,S,kernel*kernel,Co]; out/dout NHWC [N,Ho,Wo,Co], Ho = (H + 2*pad - kernel)/stride + 1, updated
+ * in place (the caller puts the convolution of the image channels + bias there first).
+ * Built for kernel 4, stride 2, pad 2, Co = 64; anything else returns an argument error. */
+int ag2v_layout_tables_avgpool(const void* tables, int N, int O, int H, int W, void* tables_out, ag2v_stream_t stream);
+size_t ag2v_layout_sconv_bwd_workspace_floats(int N, int S, int Co, int Ho, int KK);
+int ag2v_layout_sconv_fwd(const float* U, const void* tables, int N, int S, int Co, int H, int W, int kernel,
+                          int stride, int pad, float* out, ag2v_stream_t stream);
+int ag2v_layout_sconv_bwd(const float* dout, const void* tables, int N, int S, int Co, int H, int W, int kernel,
+                          int stride, int pad, float* part, float* dU, ag2v_stream_t stream);
+
 /* K5 — spectral normalisation of up to 48 convolution weights in ONE launch (the spectral_norm
  * wrappers of SPADEResnetBlock, architecture.py:34-41, and of get_nonspade_norm_layer,
  * normalization.py:16-50; arithmetic of torch/nn/utils/spectral_norm.py compute_weight).

@@ -38,11 +38,11 @@ def test_layout_cat_is_cat_of_layout(N, O, D, C, H, W):
     assert torch.equal(v1.grad, v2.grad)
 
 
-def _models(size, seed_g, seed_d, dev):
+def _models(size, seed_g, seed_d, dev, **over):
     from ag2video_b200.discriminator import MetaDiscriminatorModel
     from ag2video_b200.losses import LossModel
     from ag2video_b200.networks import AG2VideoModel
-    opt = make_opt(size, batch_size=2)
+    opt = make_opt(size, batch_size=2, **over)
     m = AG2VideoModel(opt)
     m.load_state_dict(det_state(m.state_dict(), seed_g), strict=True)
     m = m.to(dev).to(memory_format=torch.channels_last).train()
@@ -52,14 +52,17 @@ def _models(size, seed_g, seed_d, dev):
 
 
 @gpu
-def test_discriminator_forward_backward_matches_oracle():
-    """Our discriminator (K1 graph layers, K2 layouts into the cat buffer, cuDNN PatchGAN in fp32)
-    against the CPU oracle on the same weights: every level of both scales, and parameter gradients."""
+@pytest.mark.parametrize('rank1', [True, False])
+def test_discriminator_forward_backward_matches_oracle(rank1):
+    """Our discriminator (K1 graph layers; PatchGAN stems through the rank-1 layout, K7 - or K2 layouts
+    written into the cat buffer + dense stem; cuDNN PatchGAN trunk in fp32) against the CPU oracle on
+    the same weights: every level of both scales, and parameter gradients."""
     from oracle import losses as oloss
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device('cuda', 0)
-    opt, m, meta, lm = _models(64, 61, 71, dev)
+    opt, m, meta, lm = _models(64, 61, 71, dev, rank1_stem=rank1)
+    assert meta.img_discriminator.rank1_stem == rank1
     ref = oloss.MultiscaleActionDiscriminator(opt)
     ref.load_state_dict(det_state(ref.state_dict(), 71), strict=True)
     ref.train()
@@ -119,3 +122,48 @@ def test_iteration_losses_match_reference_golden():
     assert any('discriminator_0.model0.0.weight' in k for k in moved) and any('gconvs.0' in k for k in moved)
     for p in tr.graph_params + tr.gen_params:
         assert p.grad is None or torch.isfinite(p.grad).all()
+
+
+@gpu
+@pytest.mark.parametrize('H', [32, 50, 128])
+def test_rank1_stem_matches_dense_convolution(H):
+    """K7 against the dense library form on the same numbers: conv4x4/s2(cat[img, layout]) at full
+    resolution and on the 3x3/s2 average pool (count_include_pad=False) of the concatenation -
+    forward, and gradients for the image, the object vectors and the convolution weight."""
+    import torch.nn.functional as F
+    from ag2video_b200.layout import (boxes_to_layout_batched, layout_sconv, layout_tables, layout_tables_avgpool,
+                                      pooled_size)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, O, D, Co = 3, 7, 24, 64
+    g = torch.Generator().manual_seed(H)
+    xy = torch.rand(N, O, 2, generator=g) * 0.8 - 0.05
+    wh = torch.rand(N, O, 2, generator=g) * 0.35 + 0.03
+    boxes = torch.cat([xy, wh], dim=-1).cuda()
+    boxes[0, 1] = 0.0
+    boxes[1, 2] = torch.tensor([0.0, 0.0, 1.0, 1.0])          # a full-frame object
+    valid = (torch.rand(N, O, generator=g) > 0.15).cuda()
+    img0 = torch.randn(N, 3, H, H, generator=g).cuda()
+    vecs0 = torch.randn(N, O, D, generator=g).cuda()
+    w0 = (torch.randn(Co, 3 + D, 4, 4, generator=g) * 0.05).cuda()
+    bias = torch.randn(Co, generator=g).cuda()
+    pool = lambda x: F.avg_pool2d(x, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)
+    for scale in (0, 1):
+        img, vecs, w = img0.clone().requires_grad_(), vecs0.clone().requires_grad_(), w0.clone().requires_grad_()
+        x = torch.cat([img, boxes_to_layout_batched(vecs, boxes, valid, H, H)], dim=1)
+        if scale:
+            x = pool(x)
+        want = F.conv2d(x, w, bias, stride=2, padding=2)
+        cot = torch.randn(want.shape, generator=g).cuda()
+        (want * cot).sum().backward()
+        img2, vecs2, w2 = img0.clone().requires_grad_(), vecs0.clone().requires_grad_(), w0.clone().requires_grad_()
+        tables, Hs, im = layout_tables(boxes, valid, H, H), H, img2
+        if scale:
+            tables, Hs, im = layout_tables_avgpool(tables, N, O, H, H), pooled_size(H), pool(img2)
+        base = F.conv2d(im, w2[:, :3], bias, stride=2, padding=2).contiguous(memory_format=torch.channels_last)
+        got = layout_sconv(w2[:, 3:], vecs2, tables, base, Hs, Hs)
+        (got * cot).sum().backward()
+        errs = dict(out=max_rel(got, want), dimg=max_rel(img2.grad, img.grad), dvecs=max_rel(vecs2.grad, vecs.grad),
+                    dw=max_rel(w2.grad, w.grad))
+        print(H, scale, {k: '%.2e' % v for k, v in errs.items()})
+        assert max(errs.values()) <= 2e-5, (scale, errs)
