@@ -1,6 +1,6 @@
 """A short run that launches each hot kernel a few times at BASELINE shapes, for ncu:
   ncu --set full --clock-control none --import-source on -k regex:<pattern> -c N -o gpurun_out/prof python tools/ncu_targets.py <what>
-what: spade | layout | gcn | step (one whole train step at 256x256: K4 layout conv, K5 spectral norm, grouped SPADE)"""
+what: spade | layout | gcn | disc | step (one whole train step at 256x256: K4 layout conv, K5 spectral norm, grouped SPADE)"""
 import os
 import sys
 
@@ -42,6 +42,23 @@ elif what == 'gcn':
     for _ in range(reps):
         o, p = m(obj, pred, edges.cuda(), ind.cuda())
         (o.sum() + p.sum()).backward()
+elif what == 'disc':
+    # the discriminator's conditioning + PatchGAN stems at 256x256 (K1, K7 with pooled tables) and the dense form (K2 strided)
+    from ag2video_b200.config import make_opt, synthetic_batch
+    from ag2video_b200.discriminator import MultiscaleActionDiscriminator
+    from ag2video_b200.networks import AG2VideoModel
+    dev = torch.device('cuda', 0)
+    for rank1 in (True, False):
+        opt = make_opt(256, batch_size=2, rank1_stem=rank1)
+        model = AG2VideoModel(opt, dev).train()
+        netD = MultiscaleActionDiscriminator(opt).to(dev).train()
+        b = synthetic_batch(B=2, F=4, image_size=256, seed=1, device=dev, pad_to=(11, 6))
+        with torch.no_grad():
+            _, _, ad = model.acts_to_objs(b['objs'], b['triplets'], b['actions'], b['boxes'])
+        for _ in range(reps):
+            out = netD(b['imgs'][:, 1:], b['objs'], b['boxes'][:, 1:], [a[:, 1:] for a in ad])
+            netD.zero_grad(set_to_none=True)
+            sum(o[-1].mean() for o in out).backward()
 elif what == 'step':
     from ag2video_b200.config import make_opt, synthetic_batch
     from ag2video_b200.networks import AG2VideoModel
