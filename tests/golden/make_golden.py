@@ -90,6 +90,33 @@ def gconv_case():
                           c1=c1, c2=c2, dobj=obj.grad, dpred=pred.grad, dparams=grads_of(layer)))
 
 
+def gconv_edge_case():
+    """Edge cases of GraphTripleConv.forward run on the reference: no live edge at all (every node pools
+    nothing, graph.py:93-99), a single node with self loops, and one live edge among masked ones."""
+    dims = dict(obj_input_dim=24, object_output_dim=16, predicate_input_dim=16,
+                predicate_output_dim=16, hidden_dim=32, num_attributes=4)
+    layer = GraphTripleConv(**dims)
+    load_det(layer, 13)
+    cases = {}
+    specs = {'all_masked': (2, 5, 6, lambda B, E: torch.zeros(B, E, dtype=torch.bool)),
+             'single_node': (2, 1, 3, lambda B, E: torch.ones(B, E, dtype=torch.bool)),
+             'one_live_edge': (1, 4, 5, lambda B, E: torch.tensor([[0, 0, 1, 0, 0]], dtype=torch.bool))}
+    for name, (B, O, E, mk) in specs.items():
+        g = torch.Generator().manual_seed(17)
+        obj = det_tensor('gedge.obj.' + name, (B, O, 24), 1).requires_grad_()
+        pred = det_tensor('gedge.pred.' + name, (B, E, 16), 1).requires_grad_()
+        edges = torch.randint(0, O, (B, E, 2), generator=g)
+        ind = mk(B, E)
+        layer.zero_grad()
+        new_obj, new_p = layer(obj, pred, edges, ind)
+        c1, c2 = det_tensor('gedge.c1.' + name, new_obj.shape, 1), det_tensor('gedge.c2.' + name, new_p.shape, 1)
+        ((new_obj * c1).sum() + (new_p * c2).sum()).backward()
+        cases[name] = dict(obj=obj.detach(), pred=pred.detach(), edges=edges, ind=ind, new_obj=new_obj.detach(),
+                           new_p=new_p.detach(), c1=c1, c2=c2, dobj=obj.grad.clone(), dpred=pred.grad.clone(),
+                           dparams=grads_of(layer))
+    save('gconv_edge.pt', dict(dims=dims, state=layer.state_dict(), cases=cases))
+
+
 def gconv_net_case():
     first = dict(obj_input_dim=64, object_output_dim=16, predicate_input_dim=16,
                  predicate_output_dim=16, hidden_dim=32, num_attributes=4)
@@ -324,7 +351,7 @@ def losses_case():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['gconv', 'gconv_net', 'layout', 'masks', 'crop', 'spade', 'block',
+    which = sys.argv[1:] or ['gconv', 'gconv_edge', 'gconv_net', 'layout', 'masks', 'crop', 'spade', 'block',
                              'acts2layout', 'generator', 'losses']
     for w in which:
         globals()['%s_case' % w]()

@@ -103,3 +103,45 @@ def test_trainer_partitions_parameters_like_the_reference():
     assert sum(p.numel() for p in tr.graph_params) == n_graph
     assert sum(p.numel() for p in tr.gen_params) == sum(p.numel() for p in m.parameters()) - n_graph
     assert len({id(p) for p in tr.gen_params} & {id(p) for p in tr.graph_params}) == 0
+
+
+def test_trainer_gradient_buckets_follow_the_optimisers():
+    """With more than one rank every backward is followed by the all-reduce of exactly the gradients its
+    optimiser consumes: three disjoint bucket sets covering generator, discriminator and graph parameters."""
+    from ag2video_b200.discriminator import MetaDiscriminatorModel
+    from ag2video_b200.losses import LossModel
+    from ag2video_b200.networks import AG2VideoModel
+    from ag2video_b200.trainer import Trainer
+    opt = make_opt(64)
+    m, meta = AG2VideoModel(opt), MetaDiscriminatorModel(opt, fused=False)
+    tr = Trainer(opt, m, meta, LossModel(opt, meta), world=2, fused=False)
+    assert set(tr.buckets) == {'gen', 'd', 'graph'}
+    ids = {k: {id(p) for bucket in b.buckets for p in bucket} for k, b in tr.buckets.items()}
+    assert ids['gen'] == {id(p) for p in tr.gen_params if p.requires_grad}
+    assert ids['graph'] == {id(p) for p in tr.graph_params}
+    assert ids['d'] == {id(p) for p in meta.img_discriminator.parameters()}
+    assert not (ids['gen'] & ids['d']) and not (ids['gen'] & ids['graph']) and not (ids['d'] & ids['graph'])
+    for opt_, key in ((tr.optimizer_generator, 'gen'), (tr.optimizer_graph, 'graph'), (tr.optimizer_d_img, 'd')):
+        owned = {id(p) for grp in opt_.param_groups for p in grp['params'] if p.requires_grad}
+        assert owned == ids[key], key
+
+
+def test_loss_model_modes_and_errors():
+    """Same dispatch strings as the reference's LossModel.forward (loss_model.py:140-149); the CPU has no
+    kernels, so only the graph loss (pure torch) is evaluated here - against the oracle."""
+    from ag2video_b200.discriminator import MetaDiscriminatorModel
+    from ag2video_b200.losses import LossModel
+    from oracle import losses as oloss
+    opt = make_opt(64)
+    meta = MetaDiscriminatorModel(opt, fused=False)
+    lm = LossModel(opt, meta)
+    with pytest.raises(ValueError):
+        lm({}, None, mode='compute_everything')
+    b = synthetic_batch(B=2, F=16, image_size=64, seed=3, with_images=False)
+    boxes_pred = b['boxes'] + 0.05 * torch.randn(b['boxes'].shape, generator=torch.Generator().manual_seed(1))
+    got = lm(b, boxes_pred, mode='compute_graph_loss')
+    want = oloss.LossModel(opt, None).compute_graph_loss(b, boxes_pred)
+    assert set(got) == {'bbox_pred', 'total_loss'}
+    assert abs(float(got['total_loss']) - float(want['total_loss'])) <= 1e-6 * abs(float(want['total_loss']))
+    tup = (None, b['objs'], b['boxes'], b['triplets'], b['actions'], None)       # the reference's batch tuple
+    assert torch.equal(lm(tup, boxes_pred, mode='compute_graph_loss')['total_loss'], got['total_loss'])

@@ -50,7 +50,25 @@ def test_gconv_net_golden():
         assert max_rel(_grads(m)[k], v) <= TOL, k
 
 
-@pytest.mark.parametrize('case', ['layer0_c3', 'layer1_c3', 'layer0_c4', 'ragged', 'return_pred'])
+@pytest.mark.parametrize('name', ['all_masked', 'single_node', 'one_live_edge'])
+def test_gconv_edge_cases_golden(name):
+    """Edge cases pinned on the reference itself (tests/golden/gconv_edge.pt)."""
+    from ag2video_b200.graph import GraphTripleConv
+    g = golden('gconv_edge.pt')
+    c = g['cases'][name]
+    m = _to(GraphTripleConv, g['dims'], g['state'], 'cuda')
+    obj, pred = c['obj'].cuda().requires_grad_(), c['pred'].cuda().requires_grad_()
+    o, p = m(obj, pred, c['edges'].cuda(), c['ind'].cuda())
+    assert max_rel(o, c['new_obj']) <= TOL and max_rel(p, c['new_p']) <= TOL
+    ((o * c['c1'].cuda()).sum() + (p * c['c2'].cuda()).sum()).backward()
+    assert max_rel(obj.grad, c['dobj']) <= TOL and max_rel(pred.grad, c['dpred']) <= TOL
+    got = _grads(m)
+    for k, v in c['dparams'].items():
+        assert max_rel(got[k], v) <= TOL, k
+
+
+@pytest.mark.parametrize('case', ['layer0_c3', 'layer1_c3', 'layer0_c4', 'ragged', 'return_pred',
+                                  'all_masked', 'disc_e6', 'single_obj', 'batch8'])
 def test_gconv_vs_oracle_full_size(case):
     """BASELINE configs 3 and 4 shapes: Din 512/128, hidden 512, E = 16 or 40."""
     from ag2video_b200.graph import GraphTripleConv
@@ -65,10 +83,13 @@ def test_gconv_vs_oracle_full_size(case):
         edges, ind = microbench_graph(B=B, O=10)
         E = edges.shape[1]
     else:
-        B, O, E = (2, 11, 16) if case != 'ragged' else (3, 7, 13)
+        # ragged: most edges masked; all_masked: no live edge at all (every node keeps a zero pooled vector);
+        # disc_e6: the discriminator's action-only graph (discriminator.py:296-309); single_obj: one node,
+        # self loops only; batch8: BASELINE config 2's batch (128 edge rows)
+        B, O, E = {'ragged': (3, 7, 13), 'disc_e6': (2, 11, 6), 'single_obj': (2, 1, 3), 'batch8': (8, 11, 16)}.get(case, (2, 11, 16))
         g = torch.Generator().manual_seed(3)
         edges = torch.randint(0, O, (B, E, 2), generator=g)
-        ind = torch.rand(B, E, generator=g) > (0.2 if case != 'ragged' else 0.6)
+        ind = torch.rand(B, E, generator=g) > {'ragged': 0.6, 'all_masked': 2.0}.get(case, 0.2)
     ref = load_det(oops.GraphTripleConv(**kw), 5)
     m = GraphTripleConv(**kw)
     m.load_state_dict(ref.state_dict(), strict=True)
@@ -108,6 +129,15 @@ def test_gconv_is_deterministic():
         outs.append([o, p, obj.grad, pred.grad] + [q.grad.clone() for q in m.parameters()])
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_gconv_empty_graph_is_an_error():
+    """E = 0 never happens on the path (E = objects + actions >= 1); the kernel refuses it loudly."""
+    from ag2video_b200.graph import GraphTripleConv
+    m = GraphTripleConv(8, 8, 8, 8, 8).cuda()
+    with pytest.raises(RuntimeError, match='empty graph'):
+        m(torch.zeros(1, 2, 8).cuda(), torch.zeros(1, 0, 8).cuda(), torch.zeros(1, 0, 2, dtype=torch.long).cuda(),
+          torch.ones(1, 0, dtype=torch.bool).cuda())
 
 
 def test_gconv_rejects_cpu_tensors():

@@ -241,3 +241,17 @@ def test_closed_form_layout_matches_reference(name):
             continue
         one = oops.boxes_to_layout(torch.ones(1, 1), c['boxes'][o:o + 1], c['H'], c['W'])
         assert np.array_equal(support[o], (one[0, 0] != 0).numpy()), o
+
+
+@pytest.mark.parametrize('name', ['all_masked', 'single_node', 'one_live_edge'])
+def test_gconv_edge_cases_match_reference(name):
+    g = golden('gconv_edge.pt')
+    c = g['cases'][name]
+    layer = oops.GraphTripleConv(**g['dims'])
+    layer.load_state_dict(g['state'], strict=True)
+    obj, pred = c['obj'].clone().requires_grad_(), c['pred'].clone().requires_grad_()
+    new_obj, new_p = layer(obj, pred, c['edges'], c['ind'])
+    assert max_rel(new_obj, c['new_obj']) <= TOL and max_rel(new_p, c['new_p']) <= TOL
+    ((new_obj * c['c1']).sum() + (new_p * c['c2']).sum()).backward()
+    assert max_rel(obj.grad, c['dobj']) <= TOL and max_rel(pred.grad, c['dpred']) <= TOL
+    _check_grads(_grads(layer), c['dparams'])
