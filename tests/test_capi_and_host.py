@@ -145,3 +145,14 @@ def test_loss_model_modes_and_errors():
     assert abs(float(got['total_loss']) - float(want['total_loss'])) <= 1e-6 * abs(float(want['total_loss']))
     tup = (None, b['objs'], b['boxes'], b['triplets'], b['actions'], None)       # the reference's batch tuple
     assert torch.equal(lm(tup, boxes_pred, mode='compute_graph_loss')['total_loss'], got['total_loss'])
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """Without the built .so every operator raises (no CPU / PyTorch fallback)."""
+    from ag2video_b200 import _lib as L
+    monkeypatch.setattr(L, '_lib', None)
+    monkeypatch.setattr(L, 'LIB_PATH', os.path.join(ROOT, 'ag2video_b200', 'no_such_library.so'))
+    with pytest.raises(RuntimeError, match='There is no CPU/PyTorch fallback'):
+        L.lib()
+    with pytest.raises(RuntimeError):
+        L.launch_count()
