@@ -103,15 +103,18 @@ class MultiscaleActionDiscriminator(nn.Module):
         a = temporal_triplets[..., 1].long()
         act_vecs = self.acts_embeddings(a)
         act_vecs = torch.cat([act_vecs[..., :-3], locs[..., 0:1], locs[..., 1:2], rel_t.unsqueeze(-1)], dim=-1)
-        edges = torch.stack([temporal_triplets[..., 0], temporal_triplets[..., 2]], dim=-1).long().contiguous()
-        ind = (a != self.pad_act).contiguous()
+        edges = torch.stack([temporal_triplets[..., 0], temporal_triplets[..., 2]], dim=-1).long()
+        # time-major, unbound once: contiguous per-frame views, one stack in the backward (see Acts2LayoutModel)
+        edges_t = edges.transpose(0, 1).contiguous().unbind(0)
+        ind_t = (a != self.pad_act).transpose(0, 1).contiguous().unbind(0)
+        acts_t = act_vecs.transpose(0, 1).contiguous().unbind(0)
         obj_vecs = self.pre_obj_vecs_net(self.attribute_embedding(objs))
         per_t = []
         for t in range(T):
             obj_vecs = self.obj_vecs_net(torch.cat([obj_vecs, layout_boxes[:, t]], dim=-1))
-            p_vecs = act_vecs[:, t]
+            p_vecs = acts_t[t]
             for layer in self.gconvs:
-                obj_vecs, p_vecs = layer(obj_vecs, p_vecs, edges[:, t], ind[:, t])
+                obj_vecs, p_vecs = layer(obj_vecs, p_vecs, edges_t[t], ind_t[t])
             per_t.append(obj_vecs)
         return torch.stack(per_t, dim=1)
 

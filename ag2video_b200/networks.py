@@ -94,15 +94,19 @@ class Acts2LayoutModel(nn.Module):
             edges = torch.cat([torch.stack([triplets[..., 0], triplets[..., 2]], dim=-1), edges], dim=2)
             ind = torch.cat([triplets[..., 1] != self.pad_pred, ind], dim=2)
             pred_vecs = torch.cat([self.pred_embeddings(triplets[..., 1]), act_vecs], dim=2)
-        edges, ind = edges.contiguous(), ind.contiguous()
+        # time-major and unbound once: every per-timestep operand is then a contiguous view (no copy per
+        # layer call) and the backward of the T slices is ONE stack instead of T zero-filled select_backwards
+        edges_t = edges.transpose(0, 1).contiguous().unbind(0)
+        ind_t = ind.transpose(0, 1).contiguous().unbind(0)
+        preds_t = pred_vecs.transpose(0, 1).contiguous().unbind(0)
         emb = self.attribute_embedding(objs)
         boxes = [boxes_gt[:, 0]]
         per_t = [emb.new_zeros(objs.shape[0], objs.shape[1], self.embedding_dim)]
         for t in range(1, T):
             obj_vecs = self.obj_vecs_net(torch.cat([emb, boxes[-1]], dim=-1))
-            p_vecs = pred_vecs[:, t]
+            p_vecs = preds_t[t]
             for layer in self.gconvs:
-                obj_vecs, p_vecs = layer(obj_vecs, p_vecs, edges[:, t], ind[:, t])
+                obj_vecs, p_vecs = layer(obj_vecs, p_vecs, edges_t[t], ind_t[t])
             per_t.append(obj_vecs)
             boxes.append(boxes[-1] + self.box_net(obj_vecs))                           # model.py:168
         locs = torch.stack([x_end, y_end], dim=-1)
