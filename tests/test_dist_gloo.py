@@ -61,3 +61,90 @@ def test_shard_clips_ragged():
     parts = [shard_clips(7, r, 4) for r in range(4)]
     assert sorted(sum(parts, [])) == list(range(7))
     assert shard_clips(2, 3, 4) == []
+
+
+# ---- Trainer.iteration over two gloo ranks (host logic of the N>1 path, CPU stand-in networks) ----------
+class _TinyModel(torch.nn.Module):
+    """Same interface as AG2VideoModel as far as Trainer uses it (acts_to_boxes + the rest; graph_only)."""
+
+    def __init__(self):
+        super().__init__()
+        self.acts_to_boxes = torch.nn.Linear(4, 4)
+        self.acts_to_objs = torch.nn.Linear(4, 4)
+        self.layout_to_video = torch.nn.Linear(4, 3)
+
+    def forward(self, imgs, objs, triplets, actions, boxes_gt=None, test_mode=False, use_gt=False, graph_only=False):
+        boxes_pred = boxes_gt + self.acts_to_boxes(boxes_gt)
+        if graph_only:
+            return boxes_pred
+        imgs_pred = self.layout_to_video(self.acts_to_objs(boxes_gt)).mean(dim=2)        # [B, F, 3]
+        return imgs_pred, boxes_pred, None, None, None
+
+
+class _TinyD(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.img_discriminator = torch.nn.Linear(3, 1)
+        self.optimizer_d_img = torch.optim.Adam(self.img_discriminator.parameters(), lr=1e-2, betas=(0.5, 0.999))
+
+
+class _TinyLosses(torch.nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.d = d
+
+    def forward(self, batch, out, mode):
+        D = self.d.img_discriminator
+        if mode == 'compute_generator_loss':
+            return {'total_loss': -D(out[0]).mean() + (out[0] - batch['imgs']).abs().mean()}
+        if mode == 'compute_discriminator_loss':
+            return {'total_img_loss': torch.relu(1 + D(out[0].detach())).mean() + torch.relu(1 - D(batch['imgs'])).mean()}
+        return {'total_loss': torch.nn.functional.smooth_l1_loss(out, batch['boxes'])}
+
+
+def _tiny_batches(seed, B):
+    g = torch.Generator().manual_seed(seed)
+    clip = dict(imgs=torch.randn(B, 4, 3, generator=g), objs=None, triplets=None, actions=None, boxes=torch.rand(B, 4, 5, 4, generator=g))
+    graph = dict(objs=None, triplets=None, actions=None, boxes=torch.rand(B, 16, 5, 4, generator=g))
+    return clip, graph
+
+
+def _tiny_trainer(world):
+    from types import SimpleNamespace
+    from ag2video_b200.trainer import Trainer
+    torch.manual_seed(0)
+    model, d = _TinyModel(), _TinyD()
+    opt = SimpleNamespace(learning_rate=1e-2, beta1=0.5)
+    return Trainer(opt, model, d, _TinyLosses(d), world=world, fused=False), model, d
+
+
+def _trainer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        tr, model, d = _tiny_trainer(world)
+        clip, graph = _tiny_batches(7, 4)                      # 4 clips; every rank owns 2 of them
+        mine = shard_clips(4, rank, world)
+        take = lambda b: {k: (v[mine] if v is not None else None) for k, v in b.items()}
+        for _ in range(2):
+            tr.iteration(take(clip), take(graph))
+        out[rank] = torch.cat([p.detach().flatten() for p in list(model.parameters()) + list(d.parameters())])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_iteration_two_ranks_equals_one_rank_on_all_clips():
+    """Clips sharded over two ranks + the three per-optimiser gradient all-reduces give the same parameters
+    (on every rank) as one process stepping on all clips: losses are batch means, shards are equal-sized."""
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_trainer_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    tr, model, d = _tiny_trainer(1)
+    clip, graph = _tiny_batches(7, 4)
+    for _ in range(2):
+        tr.iteration(clip, graph)
+    want = torch.cat([p.detach().flatten() for p in list(model.parameters()) + list(d.parameters())])
+    assert torch.equal(res[0], res[1])
+    assert (res[0] - want).abs().max() <= 1e-5 * want.abs().max()
