@@ -89,3 +89,28 @@ def f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
     return t if t.is_contiguous() else t.contiguous()
+
+
+# ---- per-launch timing (bench.py / tools): CUDA events around a launch on the current stream ----------
+PROFILE = None          # set to a list to record (kind, work, start_event, end_event, tag) for every timed launch
+
+
+class timed:
+    """``with timed(kind, work, tag):`` around one kernel launch (or one operator call).  ``work`` =
+    algorithmic FLOPs (GEMM-shaped kernels) or algorithmic bytes (HBM-bound kernels) of the launch.
+    A no-op unless ``PROFILE`` is a list (events cannot be recorded inside a replayed CUDA graph, so the
+    bench measures them in a separate eager pass over the same steps)."""
+
+    def __init__(self, kind, work, tag=None):
+        self.kind, self.work, self.tag = kind, work, tag
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.append((self.kind, self.work, self.s, self.e, self.tag))

@@ -35,10 +35,21 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
-def shard_clips(n_clips, rank, world):
-    """Contiguous, disjoint clip indices per rank (DistributedSampler-style, no padding)."""
+def shard_clips(n_clips, rank, world, drop_last=True):
+    """Disjoint clip indices for ``rank`` with the SAME count on every rank (DistributedSampler semantics):
+    the gradient average is an unweighted 1/world and SyncBN scales the local pixel count by ``world``
+    (spade.py), and a rank without work would skip its collectives and hang the others - so shards are
+    never ragged.  ``drop_last`` drops the ``n_clips % world`` tail clips; otherwise the tail is padded by
+    wrapping around to the first clips (those are then seen twice in the epoch)."""
+    if n_clips < world and drop_last:
+        raise ValueError('shard_clips: %d clips cannot be sharded over %d ranks without padding' % (n_clips, world))
+    if drop_last:
+        per = n_clips // world
+        return list(range(rank * per, (rank + 1) * per))
+    if n_clips <= 0:
+        raise ValueError('shard_clips: no clips')
     per = (n_clips + world - 1) // world
-    return list(range(min(rank * per, n_clips), min((rank + 1) * per, n_clips)))
+    return [i % n_clips for i in range(rank * per, (rank + 1) * per)]
 
 
 class GradBuckets:

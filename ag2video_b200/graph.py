@@ -12,6 +12,12 @@ import torch.nn as nn
 from . import _lib as L
 
 
+def gcn_layer_bytes(B, O, E, Din, Dp, H, Dout, Dpo):
+    """Algorithmic bytes of one forward layer call: parameters + inputs + outputs, fp32."""
+    params = (2 * Din + Dp) * H + H + H * (2 * H + Dpo) + (2 * H + Dpo) + H * H + H + H * Dout + Dout
+    return 4.0 * (params + B * O * Din + B * E * Dp + 2 * B * E + B * O * Dout + B * E * Dpo)
+
+
 class _GcnLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, obj, pred, edges, ind, W1a, b1a, W1b, b1b, W2a, b2a, W2b, b2b, want_p):
@@ -32,9 +38,10 @@ class _GcnLayerFn(torch.autograd.Function):
         new_obj = torch.empty(B, O, Dout, device=obj.device, dtype=torch.float32)
         new_p = torch.empty(B, E, Dpo, device=obj.device, dtype=torch.float32)
         saved = torch.empty(lib.ag2v_gcn_layer_saved_floats(B, O, E, H, Dpo), device=obj.device, dtype=torch.float32)
-        L.check(lib.ag2v_gcn_layer_fwd(L.ptr(obj), L.ptr(pred), L.ptr(edges), L.ptr(ind), *[L.ptr(w) for w in W],
-                                       B, O, E, Din, Dp, H, Dout, Dpo, L.ptr(new_obj), L.ptr(new_p), L.ptr(saved),
-                                       L.stream()))
+        with L.timed('k1_gcn_fwd', gcn_layer_bytes(B, O, E, Din, Dp, H, Dout, Dpo), (B * E, Din)):
+            L.check(lib.ag2v_gcn_layer_fwd(L.ptr(obj), L.ptr(pred), L.ptr(edges), L.ptr(ind), *[L.ptr(w) for w in W],
+                                           B, O, E, Din, Dp, H, Dout, Dpo, L.ptr(new_obj), L.ptr(new_p), L.ptr(saved),
+                                           L.stream()))
         ctx.dims = (B, O, E, Din, Dp, H, Dout, Dpo)
         ctx.want_p = want_p
         ctx.save_for_backward(obj, pred, edges, ind, W[0], W[2], W[4], W[6], new_obj, saved)
@@ -52,10 +59,11 @@ class _GcnLayerFn(torch.autograd.Function):
         g_obj, g_pred = torch.empty_like(obj), torch.empty_like(pred)
         gW = [torch.empty_like(W1a), torch.empty(H, device=dev), torch.empty_like(W1b), torch.empty(2 * H + Dpo, device=dev),
               torch.empty_like(W2a), torch.empty(H, device=dev), torch.empty_like(W2b), torch.empty(Dout, device=dev)]
-        L.check(lib.ag2v_gcn_layer_bwd(L.ptr(obj), L.ptr(pred), L.ptr(edges), L.ptr(ind), L.ptr(W1a), L.ptr(W1b),
-                                       L.ptr(W2a), L.ptr(W2b), L.ptr(new_obj), L.ptr(saved), L.ptr(d_obj), L.ptr(d_p),
-                                       B, O, E, Din, Dp, H, Dout, Dpo, L.ptr(ws), L.ptr(g_obj), L.ptr(g_pred),
-                                       *[L.ptr(g) for g in gW], L.stream()))
+        with L.timed('k1_gcn_bwd', 2.0 * gcn_layer_bytes(B, O, E, Din, Dp, H, Dout, Dpo), (B * E, Din)):
+            L.check(lib.ag2v_gcn_layer_bwd(L.ptr(obj), L.ptr(pred), L.ptr(edges), L.ptr(ind), L.ptr(W1a), L.ptr(W1b),
+                                           L.ptr(W2a), L.ptr(W2b), L.ptr(new_obj), L.ptr(saved), L.ptr(d_obj), L.ptr(d_p),
+                                           B, O, E, Din, Dp, H, Dout, Dpo, L.ptr(ws), L.ptr(g_obj), L.ptr(g_pred),
+                                           *[L.ptr(g) for g in gW], L.stream()))
         return (g_obj, g_pred, None, None, *gW, None)
 
 

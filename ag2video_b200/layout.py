@@ -40,8 +40,9 @@ class _BoxesToLayoutFn(torch.autograd.Function):
         lin_x, lin_y = _linspace(W, dev), _linspace(H, dev)
         ws = torch.empty(max(lib.ag2v_boxes_to_layout_workspace_bytes(N, O, H, W), 16), device=dev, dtype=torch.uint8)
         out = torch.empty(N, D, H, W, device=dev, dtype=torch.float32)
-        L.check(lib.ag2v_boxes_to_layout_fwd(L.ptr(vecs), L.ptr(boxes), L.ptr(valid), L.ptr(lin_x), L.ptr(lin_y),
-                                             N, O, D, H, W, int(avg), L.ptr(ws), L.ptr(out), L.stream()))
+        with L.timed('k2_layout_fwd', 4.0 * N * D * H * W, (N, D, H)):
+            L.check(lib.ag2v_boxes_to_layout_fwd(L.ptr(vecs), L.ptr(boxes), L.ptr(valid), L.ptr(lin_x), L.ptr(lin_y),
+                                                 N, O, D, H, W, int(avg), L.ptr(ws), L.ptr(out), L.stream()))
         ctx.save_for_backward(ws)
         ctx.dims = (N, O, D, H, W, int(avg))
         return out
@@ -52,8 +53,9 @@ class _BoxesToLayoutFn(torch.autograd.Function):
         N, O, D, H, W, avg = ctx.dims
         dout = L.f32c(dout)
         dvecs = torch.zeros(N, O, D, device=dout.device, dtype=torch.float32)
-        L.check(L.lib().ag2v_boxes_to_layout_bwd(L.ptr(dout), None, None, None, None, N, O, D, H, W, avg, 0,
-                                                 L.ptr(ws), L.ptr(dvecs), L.stream()))
+        with L.timed('k2_layout_bwd', 4.0 * N * D * H * W, (N, D, H)):
+            L.check(L.lib().ag2v_boxes_to_layout_bwd(L.ptr(dout), None, None, None, None, N, O, D, H, W, avg, 0,
+                                                     L.ptr(ws), L.ptr(dvecs), L.stream()))
         # boxes are data on the training path (meta_models.py:53 passes ground truth
         # or detached predictions), so no gradient is produced for them.
         return dvecs, None, None, None, None, None
@@ -216,7 +218,8 @@ class _LayoutConvFn(torch.autograd.Function):
         if not base.is_contiguous(memory_format=torch.channels_last) or base.dtype != torch.float32:
             raise RuntimeError('layout_conv: base must be a float32 channels_last tensor')
         U = L.f32c(U)
-        L.check(L.lib().ag2v_layout_conv_fwd(L.ptr(U), L.ptr(tables), N, S, Co, H, W, L.ptr(base), L.stream()))
+        with L.timed('k4_layout_conv_fwd', 8.0 * N * H * W * Co, (N, Co, H)):      # output tile read-modify-write
+            L.check(L.lib().ag2v_layout_conv_fwd(L.ptr(U), L.ptr(tables), N, S, Co, H, W, L.ptr(base), L.stream()))
         ctx.mark_dirty(base)
         ctx.save_for_backward(tables)
         ctx.dims = (N, S, Co, H, W)
@@ -230,7 +233,8 @@ class _LayoutConvFn(torch.autograd.Function):
         lib = L.lib()
         part = torch.empty(lib.ag2v_layout_conv_bwd_workspace_floats(N, S, Co, H), device=dout.device, dtype=torch.float32)
         dU = torch.empty(N, S, 9, Co, device=dout.device, dtype=torch.float32)
-        L.check(lib.ag2v_layout_conv_bwd(L.ptr(dout), L.ptr(tables), N, S, Co, H, W, L.ptr(part), L.ptr(dU), L.stream()))
+        with L.timed('k4_layout_conv_bwd', 4.0 * N * H * W * Co, (N, Co, H)):
+            L.check(lib.ag2v_layout_conv_bwd(L.ptr(dout), L.ptr(tables), N, S, Co, H, W, L.ptr(part), L.ptr(dU), L.stream()))
         return dout, dU, None, None
 
 
@@ -285,7 +289,8 @@ class _LayoutSConvFn(torch.autograd.Function):
         if (Ho, Wo) != ((H + 2 * pad - kernel) // stride + 1, (W + 2 * pad - kernel) // stride + 1):
             raise RuntimeError('layout_sconv: base %s does not match input %dx%d' % (tuple(base.shape), H, W))
         U = L.f32c(U)
-        L.check(L.lib().ag2v_layout_sconv_fwd(L.ptr(U), L.ptr(tables), N, S, Co, H, W, kernel, stride, pad, L.ptr(base), L.stream()))
+        with L.timed('k7_layout_sconv_fwd', 8.0 * N * Ho * Wo * Co, (N, Co, Ho)):
+            L.check(L.lib().ag2v_layout_sconv_fwd(L.ptr(U), L.ptr(tables), N, S, Co, H, W, kernel, stride, pad, L.ptr(base), L.stream()))
         ctx.mark_dirty(base)
         ctx.save_for_backward(tables)
         ctx.dims = (N, S, Co, H, W, Ho, kernel, stride, pad)
@@ -302,8 +307,9 @@ class _LayoutSConvFn(torch.autograd.Function):
             KK = kernel * kernel
             part = torch.empty(lib.ag2v_layout_sconv_bwd_workspace_floats(N, S, Co, Ho, KK), device=dout.device, dtype=torch.float32)
             dU = torch.empty(N, S, KK, Co, device=dout.device, dtype=torch.float32)
-            L.check(lib.ag2v_layout_sconv_bwd(L.ptr(dout), L.ptr(tables), N, S, Co, H, W, kernel, stride, pad, L.ptr(part),
-                                              L.ptr(dU), L.stream()))
+            with L.timed('k7_layout_sconv_bwd', 4.0 * N * Ho * Ho * Co, (N, Co, Ho)):
+                L.check(lib.ag2v_layout_sconv_bwd(L.ptr(dout), L.ptr(tables), N, S, Co, H, W, kernel, stride, pad, L.ptr(part),
+                                                  L.ptr(dU), L.stream()))
         return dout, dU, None, None, None, None, None, None
 
 

@@ -51,6 +51,11 @@ class LossModel(nn.Module):
         super().__init__()
         if getattr(opt, 'gan_mode', 'hinge') != 'hinge':
             raise NotImplementedError('gan_mode=%r: only the reference default "hinge" is built' % opt.gan_mode)
+        if not getattr(opt, 'no_vgg_loss', False):
+            # the reference's default (--no_vgg_loss is store_true, data/args.py) adds G_losses['VGG'] from a
+            # downloaded VGG19 (networks/architecture.py:96); training without it would silently change the objective
+            raise NotImplementedError('the VGG perceptual loss needs downloaded VGG19 weights and is not built: '
+                                      'pass --no_vgg_loss (opt.no_vgg_loss = True)')
         self.opt = opt
         self.discriminator = discriminator
         self.netD_img = discriminator.img_discriminator

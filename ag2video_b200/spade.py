@@ -90,25 +90,7 @@ def _seg_operand(seg):
     return dst
 
 
-PROFILE = None                     # bench.py sets this to a list to time every GEMM-shaped launch with CUDA events
-
-
-class _Timed:
-    """Records (kind, flops, start, end) around one launch on the current stream."""
-
-    def __init__(self, kind, flops, tag=None):
-        self.kind, self.flops, self.tag = kind, flops, tag
-
-    def __enter__(self):
-        if PROFILE is not None:
-            self.s = torch.cuda.Event(enable_timing=True)
-            self.e = torch.cuda.Event(enable_timing=True)
-            self.s.record()
-
-    def __exit__(self, *a):
-        if PROFILE is not None:
-            self.e.record()
-            PROFILE.append((self.kind, self.flops, self.s, self.e, self.tag))
+_Timed = L.timed                   # per-launch CUDA-event timing, active while _lib.PROFILE is a list
 
 
 def _conv(inp, in_strides, B, Hh, Ww, Cin, wpk, bias, Nout, out, out_strides, epi, round_out=0,
@@ -264,7 +246,8 @@ class _SpadeFn(torch.autograd.Function):
             Ps = Pg // 4 if upsample else Pg       # statistics of up(x) are those of x (every element appears 4 times)
             part = torch.empty(G * lib.ag2v_chan_partial_floats(Ps, C, 2), device=dev, dtype=torch.float32)
             sums = torch.empty(G * 2 * C, device=dev, dtype=torch.float64)
-            L.check(lib.ag2v_bn_stats(L.ptr(x), Ps, C, G, L.ptr(part), L.ptr(sums), L.stream()))
+            with _Timed('k3_bn_stats', 4.0 * G * Ps * C, (r, C)):
+                L.check(lib.ag2v_bn_stats(L.ptr(x), Ps, C, G, L.ptr(part), L.ptr(sums), L.stream()))
             dist, world = _world()
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
@@ -307,9 +290,10 @@ class _SpadeFn(torch.autograd.Function):
         dx = torch.empty(B, C, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
         part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 5), device=dev, dtype=torch.float32)
         sums = torch.empty(G * 5 * C, device=dev, dtype=torch.float64)
-        L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), Pg, C, G,
-                                       act, float(slope), int(not _precise()), 0, uh, uw, L.ptr(dgb), L.ptr(dx), L.ptr(part),
-                                       L.ptr(sums), L.stream()))
+        with _Timed('k3_spade_bwd_pre', 4.0 * P * C * 7, (r, C)):       # reads dout, out, x, gamma; writes dgamma|dbeta, dxhat
+            L.check(lib.ag2v_spade_bwd_pre(L.ptr(dout), L.ptr(out), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), Pg, C, G,
+                                           act, float(slope), int(not _precise()), 0, uh, uw, L.ptr(dgb), L.ptr(dx), L.ptr(part),
+                                           L.ptr(sums), L.stream()))
         db = torch.empty(2 * C, device=dev, dtype=torch.float32)     # [sum g | sum g*xhat] = [d bias_beta | d bias_gamma]
         L.check(lib.ag2v_double_to_float(L.ptr(sums), 2 * C, G, 5 * C, L.ptr(db), L.stream()))
         dscale = None
@@ -321,8 +305,9 @@ class _SpadeFn(torch.autograd.Function):
             if world > 1:              # db (local sums) is already extracted; the BN backward needs global sums
                 dist.all_reduce(sums, group=_sync_group['group'])
         dx_low = torch.empty_like(x, memory_format=torch.channels_last) if upsample else None
-        L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
-                                      int(training), Pg, C, G, uh, uw, L.ptr(dx_low), L.stream()))
+        with _Timed('k3_spade_bwd_dx', 4.0 * P * C * (2.5 if upsample else 3), (r, C)):
+            L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
+                                          int(training), Pg, C, G, uh, uw, L.ptr(dx_low), L.stream()))
         if upsample:
             dx = dx_low
         a_strides = (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN)
@@ -351,12 +336,23 @@ class _SpadeFn(torch.autograd.Function):
         return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None, dscale, None, None
 
 
+_PACK_EPOCH = [0]
+
+
+def invalidate_packs():
+    """Declare every packed (GEMM-layout, TF32-rounded) weight copy stale.  ``Trainer`` calls this from a
+    post-step hook on each of its optimisers; call it yourself after any in-place weight update that
+    neither bumps ``Tensor._version`` (fused optimisers do not) nor follows a backward through the module."""
+    _PACK_EPOCH[0] += 1
+
+
 class _PackCache:
-    """Packed (GEMM-layout, TF32-rounded) copies of a module's weights.  Keyed on the tensors'
-    (data_ptr, _version) AND on an epoch that advances at the first forward after a backward:
-    fused optimizers (torch.optim.Adam(fused=True)) update parameters without bumping _version,
-    so "a backward has happened" is the signal that the weights may have changed.  Within one
-    epoch (the forward(s) and backward(s) of one step) every pack is built at most once."""
+    """Packed (GEMM-layout, TF32-rounded) copies of a module's weights.  A pack is reused only while ALL
+    of these are unchanged: the tensors' (data_ptr, _version); the global epoch advanced by
+    ``invalidate_packs()`` (optimiser post-step hooks); and a per-module epoch that advances at the first
+    forward after a backward (fused optimisers update parameters without bumping _version, so for callers
+    that step an optimiser of their own without the hook "a backward has happened" is the remaining signal
+    that the weights may have changed).  Within one step every pack is built at most once."""
 
     def __init__(self):
         self.epoch, self.dirty, self.store = 0, False, {}
@@ -370,7 +366,7 @@ class _PackCache:
         self.dirty = True
 
     def get(self, name, tensors, build):
-        key = (self.epoch, _precise()) + tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+        key = (self.epoch, _PACK_EPOCH[0], _precise()) + tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
         hit = self.store.get(name)
         if hit is None or hit[0] != key:
             hit = (key, build())

@@ -2,7 +2,7 @@
 generator's ``conv_img`` (spade_models/networks/generator.py: ``tanh(conv_img(leaky_relu(x, 0.2)))``)
 and the flow head ``conv_flow`` (flows_generator.py).  ``thin_conv3x3(conv, x, slope_in, act_out)``
 evaluates ``act_out(conv(leaky_relu(x, slope_in)))`` for a plain ``nn.Conv2d`` in one streaming
-kernel per direction; shapes the kernels are not instantiated for go through the module itself."""
+kernel per direction; shapes the kernels are not instantiated for raise (no silent library path)."""
 import torch
 import torch.nn.functional as F
 
@@ -60,13 +60,30 @@ class _ThinConvFn(torch.autograd.Function):
         return dx, dw, (db if has_bias else None), None, None
 
 
-def thin_conv3x3(conv, x, slope_in=1.0, act_out=None):
-    """``act_out(conv(leaky_relu(x, slope_in)))`` for a 3x3, stride-1, padding-1 ``nn.Conv2d``."""
+def thin_conv3x3(conv, x, slope_in=1.0, act_out=None, allow_library=False):
+    """``act_out(conv(leaky_relu(x, slope_in)))`` for a 3x3, stride-1, padding-1 ``nn.Conv2d``.
+    The kernels are instantiated for (Cin, Cout) = (64, 3) and (32, 2) - ``conv_img`` at ngf = 64 and
+    ``conv_flow`` at nff = 32, the reference defaults.  Any other shape RAISES: this package has no silent
+    library path.  ``allow_library=True`` is the explicit opt-in to evaluate such a shape with the module
+    itself (cuDNN); it warns once per shape."""
     w = conv.weight
     usable = (x.is_cuda and tuple(w.shape[2:]) == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
               and conv.dilation == (1, 1) and conv.groups == 1
               and L.lib().ag2v_thin_conv3x3_supported(w.shape[1], w.shape[0]))
     if not usable:
+        what = 'thin_conv3x3: no sm_100a kernel for a %s convolution %d -> %d on a %s tensor' % (
+            'x'.join(str(k) for k in w.shape[2:]), w.shape[1], w.shape[0], x.device.type)
+        if not allow_library:
+            raise NotImplementedError(what + ' (instantiated: 64 -> 3 and 32 -> 2, 3x3 / stride 1 / padding 1); '
+                                      'pass allow_library=True to evaluate it with cuDNN instead')
+        key = (tuple(w.shape), x.device.type)
+        if key not in _WARNED:
+            _WARNED.add(key)
+            import warnings
+            warnings.warn(what + ': evaluated by the library (cuDNN) because allow_library=True', RuntimeWarning)
         z = conv(F.leaky_relu(x, slope_in) if slope_in != 1.0 else x)
         return torch.tanh(z) if act_out == 'tanh' else z
     return _ThinConvFn.apply(x, w, conv.bias, float(slope_in), _ACT[act_out])
+
+
+_WARNED = set()

@@ -60,13 +60,59 @@ def peaks():
     return p
 
 
-# DRAM bytes of ONE launch (read + write) from `ncu --set full` captures, keyed like the per-shape
-# breakdown: (kind, epilogue, resolution, Cin, Nout, images).  Source: profiles/r01_ncu_r34_spade_groups.csv
-NCU_DRAM_BYTES = {
-    ('conv3x3', 'epi4', 256, 128, 512, 6): 1.0e9 + 751.5e6,     # algorithmic: 201 MB in + 805 MB read-modify-write
-    ('conv3x3', 'epi3', 256, 256, 128, 6): 0.6e9 + 172.5e6,
-    ('wgrad3x3', 'wgrad', 256, 512, 128, 6): 1.0e9 + 4.6e6,
-}
+def ncu_traffic():
+    """DRAM bytes of ONE launch (dram__bytes_read.sum + dram__bytes_write.sum) per (kernel, shape) key, taken
+    from this round's `ncu --set full` capture by tools/ncu_summary.py and committed as
+    profiles/ncu_traffic.json ({"source": file, "launches": {key: bytes}}).  bench.py cannot run ncu, so
+    `roofline.traffic` cites that file; a shape without a capture reports null."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            return json.load(f)
+    except Exception:
+        return {'source': None, 'launches': {}}
+
+
+def so_sha256():
+    import hashlib
+    from ag2video_b200 import _lib as L
+    try:
+        with open(L.LIB_PATH, 'rb') as f:
+            return hashlib.sha256(f.read()).hexdigest()
+    except Exception:
+        return None
+
+
+def measure_tf32_peak(dev, seconds=1.5):
+    """cuBLAS TF32 GEMM 8192^3 with the protocol of MEASURED_PEAKS.json (which holds bf16 only): best of 10
+    (burst) and back to back for `seconds` (sustained, the regime of a kernel inside a long step)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); torch.matmul(a, b, out=c); e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        reps = max(10, int(seconds * 1e3 / best))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e.record()
+        torch.cuda.synchronize()
+        fl = 2.0 * n ** 3
+        return {'tf32_tflops': fl / (best / 1e3) / 1e12, 'tf32_tflops_sustained': fl * reps / (s.elapsed_time(e) / 1e3) / 1e12,
+                'how': 'torch.matmul fp32 with allow_tf32 (cuBLAS TF32) 8192^3: best of 10 / %d back to back' % reps}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 class ClockSampler(threading.Thread):
@@ -109,6 +155,9 @@ def surrogate_loss(out, batch):
 
 
 # ------------------------------------------------------------------ CPU arm ---
+METRIC = 'train-step frames/sec at CATER 256x256'
+
+
 def workload_text(args):
     if args.generator_only:
         return ('AG2Vid CATER %dx%d generator train step (GCN -> layout -> SPADE, fwd+bwd+Adam), batch %d clips/GPU x %d frames'
@@ -118,16 +167,25 @@ def workload_text(args):
             % (args.size, args.size, args.batch, args.frames, args.batch, 4 * args.frames))
 
 
-def cpu_sample(size, seconds_budget, steps, warmup, threads=None, generator_only=False, frames=4):
-    """The oracle (CPU port of the reference's algorithm, oracle/) on a bounded sample of the
-    workload: ONE clip, TWO frames (one generated frame) at the full resolution - the whole
-    iteration (generator, discriminator and graph step; the graph batch is one 4*frames-frame
-    clip), or the generator step alone.  Returns frames/s and details."""
+def bench_config(args):
+    """The `config` object - IDENTICAL in both arms (`--impl ours` / `--impl reference`): it names the workload
+    (BASELINE.json configs[2]); what each arm actually executes per step is in its own `cpu_baseline.sample`
+    / `impl_detail`."""
+    return {'workload': workload_text(args),
+            'loss': ('L1 image + box surrogate (generator step only)' if args.generator_only else
+                     'reference losses: GAN hinge + feature matching + flow warp (G), hinge (D), masked smooth-L1 (graph); no VGG'),
+            'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush',
+            'parallelism': 'dp%d (clips sharded per rank, gradient all-reduce per optimiser, SyncBN statistics)' % args.gpus}
+
+
+def cpu_step_fn(size, generator_only=False, frames=4):
+    """One step of the oracle (the CPU restatement of the reference, oracle/) on a bounded sample of the
+    workload: ONE clip, TWO frames (one generated frame) at the full resolution - the whole iteration
+    (generator, discriminator and graph step on a 1-clip x 4*frames-frame graph batch), or the generator
+    step alone.  Returns (step, description, frames_counted_per_step)."""
     from ag2video_b200.config import make_opt, synthetic_batch
     from oracle import losses as oloss
     from oracle import networks as onet
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     torch.manual_seed(0)
     opt = make_opt(size, batch_size=1)
     model = onet.AG2VideoModel(opt).train()
@@ -170,36 +228,150 @@ def cpu_sample(size, seconds_budget, steps, warmup, threads=None, generator_only
             o_graph.step()
             return float(G['total_loss'].detach())
         what = 'full iteration (G + D + graph step on a 1 clip x %d frames graph batch)' % (4 * frames)
+    desc = '1 clip x 2 frames (1 generated) at %dx%d, %s, oracle/ torch CPU fp32' % (size, size, what)
+    return step, desc, 2.0
 
-    t0 = time.perf_counter()
-    step()                                   # first step also serves as warm-up / cost probe
-    t_probe = time.perf_counter() - t0
-    n_warm = max(0, min(warmup, 1) - 1)
+
+def cpu_run(step, n_warm, n_steps):
     for _ in range(n_warm):
         step()
-    n = max(1, min(steps, int(seconds_budget / max(t_probe, 1e-3))))
     t0 = time.perf_counter()
-    for _ in range(n):
+    for _ in range(n_steps):
         step()
-    dt = (time.perf_counter() - t0) / n
-    return {'value': 2.0 / dt, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-            'sample': '1 clip x 2 frames (1 generated) at %dx%d, %s, oracle/ torch CPU fp32, '
-                      '%d timed step(s) of %.1f s' % (size, size, what, n, dt), 's_per_step': dt, 'steps': n}
+    return (time.perf_counter() - t0) / max(n_steps, 1)
+
+
+def cpu_pairs(threads):
+    """The two CPU-runnable BASELINE configs, timed on the host cores next to the 256x256 sample
+    (SURVEY.md 8d): C1 = generator fwd+bwd at 64x64, batch 2, 4 frames (median of 3 after one warm-up);
+    C4 = layout + GCN microbench (10 objects, 40 edges, 256x256, D=512; 2 of the 16 frames sampled)."""
+    from ag2video_b200.config import make_opt, microbench_graph, synthetic_batch
+    from oracle import networks as onet
+    from oracle import ops as oops
+    torch.manual_seed(0)
+    res = {}
+    opt = make_opt(64, batch_size=2)
+    model = onet.AG2VideoModel(opt).train()
+    b = synthetic_batch(B=2, F=4, image_size=64, seed=1234)
+
+    def c1():
+        model.zero_grad(set_to_none=True)
+        out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+        surrogate_loss(out, b).backward()
+    c1()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); c1(); ts.append(time.perf_counter() - t0)
+    ts.sort()
+    res['c1'] = {'config': 'BASELINE configs[0]: generator fwd+bwd, 64x64, batch 2, frames_per_action 4',
+                 'cpu_s_per_step': ts[1], 'cpu_frames_per_s': 8.0 / ts[1], 'protocol': 'median of 3 after 1 warm-up'}
+    # C4: layout for 2 sampled frames of the 16 (each frame is an independent call of the reference) + one GCN layer
+    bb = synthetic_batch(B=1, F=2, image_size=8, seed=1, n_objects=10, with_images=False)
+    vecs = torch.randn(2, 10, 512, requires_grad=True)
+
+    def c4_layout():
+        for f in range(2):
+            out = oops.boxes_to_layout(vecs[f], bb['boxes'][0, f, :10], 256)
+            out.sum().backward()
+    c4_layout()
+    t0 = time.perf_counter(); c4_layout(); t_lay = (time.perf_counter() - t0) / 2
+    layer = oops.GraphTripleConv(512, 128, 128, 128, 512)
+    edges, ind = microbench_graph(B=2, O=10)
+    obj = torch.randn(2, 11, 512, requires_grad=True)
+    pred = torch.randn(2, 40, 128, requires_grad=True)
+
+    def c4_gcn():
+        o, p_ = layer(obj, pred, edges, ind)
+        (o.sum() + p_.sum()).backward()
+    c4_gcn()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        c4_gcn()
+    t_gcn = (time.perf_counter() - t0) / 5
+    res['c4'] = {'config': 'BASELINE configs[3]: layout + GCN microbench, 10 objects, 40 edges, 16 frames, 256x256, fwd+bwd',
+                 'cpu_layout_ms_per_frame': t_lay * 1e3, 'cpu_gcn_layer_ms': t_gcn * 1e3,
+                 'cpu_ms_16_frames': (16 * t_lay + t_gcn) * 1e3,
+                 'protocol': 'boxes_to_layout fwd+bwd on 2 of the 16 frames (independent calls), GraphTripleConv layer 0 fwd+bwd x5'}
+    res['cores'] = threads
+    return res
+
+
+def gpu_pairs(dev):
+    """The same two configs on the B200 through the product path (CUDA events, after warm-up)."""
+    from ag2video_b200.config import make_opt, microbench_graph, synthetic_batch
+    from ag2video_b200.graph import GraphTripleConv
+    from ag2video_b200.layout import boxes_to_layout_batched
+    from ag2video_b200.networks import AG2VideoModel
+    res = {}
+    torch.manual_seed(0)
+    model = AG2VideoModel(make_opt(64, batch_size=2), dev).train()
+    b = synthetic_batch(B=2, F=4, image_size=64, seed=1234, device=dev)
+
+    def c1():
+        model.zero_grad(set_to_none=True)
+        out = model(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+        surrogate_loss(out, b).backward()
+
+    def ev_time(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ts.sort()
+        return ts[len(ts) // 2]
+    ms = ev_time(c1, 10, 3)
+    res['c1'] = {'gpu_ms_per_step': ms, 'gpu_frames_per_s': 8.0 / (ms / 1e3), 'protocol': 'eager (no CUDA graph), median of 10 after 3 warm-up'}
+    del model
+    bb = synthetic_batch(B=16, F=1, image_size=8, seed=1, n_objects=10, with_images=False)
+    boxes = bb['boxes'].reshape(16, -1, 4).to(dev)
+    valid = torch.ones(16, boxes.shape[1], dtype=torch.bool, device=dev)
+    valid[:, -1] = False
+    vecs = torch.randn(16, boxes.shape[1], 512, device=dev, requires_grad=True)
+
+    def c4_layout():
+        out = boxes_to_layout_batched(vecs, boxes, valid, 256)
+        torch.autograd.grad(out, vecs, out)
+    t_lay = ev_time(c4_layout, 10, 3)
+    layer = GraphTripleConv(512, 128, 128, 128, 512).to(dev)
+    edges, ind = microbench_graph(B=2, O=10)
+    edges, ind = edges.to(dev), ind.to(dev)
+    obj = torch.randn(2, 11, 512, device=dev, requires_grad=True)
+    pred = torch.randn(2, 40, 128, device=dev, requires_grad=True)
+
+    def c4_gcn():
+        o, p_ = layer(obj, pred, edges, ind)
+        torch.autograd.grad((o, p_), [obj, pred] + list(layer.parameters()), (o, p_))
+    t_gcn = ev_time(c4_gcn, 10, 3)
+    res['c4'] = {'gpu_layout_ms_16_frames': t_lay, 'gpu_gcn_layer_ms': t_gcn, 'gpu_ms_16_frames': t_lay + t_gcn,
+                 'protocol': 'K2 fwd+bwd for all 16 frames in one launch each, K1 layer 0 fwd+bwd; median of 10'}
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference(args):
+    """The reference arm: the oracle port on the host cores (the reference is pure Python on torch and does
+    not import under torch >= 2 without shims), EXACTLY --warmup + --steps steps, each a
+    bounded sample of the workload.  Rank 0 alone runs it."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    res = cpu_sample(args.size, 150.0, args.steps, args.warmup, generator_only=args.generator_only, frames=args.frames)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    step, desc, frames = cpu_step_fn(args.size, generator_only=args.generator_only, frames=args.frames)
+    dt = cpu_run(step, args.warmup, args.steps)
+    value = frames / dt
+    sample = '%s; %d warm-up + %d timed steps of %.1f s' % (desc, args.warmup, args.steps, dt)
     line = {
-        'impl': 'reference', 'metric': 'train-step frames/sec at CATER 256x256', 'value': res['value'],
-        'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': res['steps'], 'warmup': min(args.warmup, 1),
-        'ms_per_step': res['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_text(args), 'sample': res['sample']},
-        'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
-        'e2e': {'value': res['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': bench_config(args),
+        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
@@ -231,9 +403,24 @@ def run_ours(args):
     if world > 1:
         sp.set_sync_bn(True)
 
-    cpu_base = None
+    cpu_base, pairs = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_sample(args.size, 25.0, 1, 0, generator_only=args.generator_only, frames=args.frames)
+        # bounded CPU work (about 20 s): one step of the 256x256 sample + the two CPU-runnable BASELINE configs
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        step, desc, fr = cpu_step_fn(args.size, generator_only=args.generator_only, frames=args.frames)
+        dt = cpu_run(step, 0, 1)
+        cpu_base = {'value': fr / dt, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                    'sample': '%s; 1 timed step of %.1f s (no warm-up)' % (desc, dt)}
+        del step
+        pairs = cpu_pairs(threads)
+        for k, v in gpu_pairs(dev).items():
+            pairs[k].update(v)
+        pairs['c1']['same_config'] = pairs['c4']['same_config'] = True
+        pairs['c1']['gpu_over_cpu'] = pairs['c1']['gpu_frames_per_s'] / pairs['c1']['cpu_frames_per_s']
+        pairs['c4']['gpu_over_cpu'] = pairs['c4']['cpu_ms_16_frames'] / pairs['c4']['gpu_ms_16_frames']
+        cpu_base['pairs'] = pairs
+    tf32 = measure_tf32_peak(dev) if rank == 0 else None
 
     torch.manual_seed(0)
     opt = make_opt(args.size, batch_size=args.batch, frames_per_action=args.frames)
@@ -362,56 +549,64 @@ def run_ours(args):
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=3)
-    # per-launch CUDA events around every GEMM-shaped kernel: a separate EAGER pass over the
+    # per-launch CUDA events around every kernel of the path: a separate EAGER pass over the
     # same steps (events cannot be recorded inside a replayed graph)
-    sp.PROFILE = []
-    for i in range(min(args.steps, 3)):
+    L.PROFILE = []
+    prof_steps = min(args.steps, 3)
+    for i in range(prof_steps):
         eager_on_static()
     torch.cuda.synchronize()
-    prof, sp.PROFILE = sp.PROFILE, None
-    prof_steps = min(args.steps, 3)
+    prof, L.PROFILE = L.PROFILE, None
 
     frames = world * args.batch * args.frames
     value = frames * args.steps / (ms_dev / 1e3)
     e2e = frames * args.steps / (ms_e2e / 1e3)
 
-    # dominant kernel: the implicit-GEMM 3x3 convolution (modulation convs fwd + input gradients)
     pk = peaks()
-    roof = None
-    if prof:
+    roof, roof_all = None, None
+    if prof and rank == 0:
+        step_ms = ms_dev / args.steps
+        tensor_kinds = ('conv3x3', 'wgrad3x3')
+        tf32_peak = tf32['tf32_tflops_sustained']
+        hbm_peak = pk['hbm_gbs']
         agg, by_shape = {}, {}
-        for kind, flops, s, e, tag in prof:
+        for kind, work, s, e, tag in prof:
             ms_ = s.elapsed_time(e)
-            a = agg.setdefault(kind, [0.0, 0.0, 0])
-            a[0] += flops; a[1] += ms_; a[2] += 1
-            a = by_shape.setdefault((kind,) + tuple(tag or ()), [0.0, 0.0, 0])
-            a[0] += flops; a[1] += ms_; a[2] += 1
-        if os.environ.get('AG2V_BENCH_BREAKDOWN') and rank == 0:
+            for d, key in ((agg, kind), (by_shape, (kind,) + tuple(tag or ()))):
+                a = d.setdefault(key, [0.0, 0.0, 0])
+                a[0] += work; a[1] += ms_; a[2] += 1
+        if os.environ.get('AG2V_BENCH_BREAKDOWN'):
             with open(os.environ['AG2V_BENCH_BREAKDOWN'], 'w') as f:
-                f.write('kind epi r Cin Nout launches ms_per_step TFLOPs\n')
-                for key, (fl_, ms_, n_) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
-                    f.write('%s %d %.3f %.1f\n' % (' '.join(str(k) for k in key), n_, ms_ / prof_steps, fl_ / (ms_ / 1e3) / 1e12))
+                f.write('kind tag... launches ms_per_step TFLOP/s-or-GB/s\n')
+                for key, (w_, ms_, n_) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
+                    rate = w_ / (ms_ / 1e3) / (1e12 if key[0] in tensor_kinds else 1e9)
+                    f.write('%s %d %.3f %.1f\n' % (' '.join(str(k) for k in key), n_, ms_ / prof_steps, rate))
+
+        def entry(kind, w_, ms_, n_):
+            tensor = kind in tensor_kinds
+            ach = w_ / (ms_ / 1e3) / (1e12 if tensor else 1e9)
+            peak = tf32_peak if tensor else hbm_peak
+            return {'bound': 'tensor' if tensor else 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s' if tensor else 'GB/s',
+                    'frac': ach / peak, 'launches_per_step': n_ / prof_steps, 'ms_per_step': ms_ / prof_steps,
+                    'avg_launch_us': ms_ * 1e3 / n_, 'share_of_step': (ms_ / prof_steps) / step_ms}
+        # every timed kernel family of the path, with its own bound (K1 / K2 / K4 / K7 / element-wise K3: HBM)
+        roof_all = {k: entry(k, *v) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
         # the dominant kernel = the (kernel, shape) with the largest share of the step
         key = max(by_shape, key=lambda k: by_shape[k][1])
-        fl, ms, n = by_shape[key]
-        achieved = fl / (ms / 1e3) / 1e12
-        tf32_peak = pk['bf16_tflops_sustained'] / 2.0
+        w_, ms_, n_ = by_shape[key]
+        roof = entry(key[0], w_, ms_, n_)
         batch_imgs = args.batch * (args.frames - 1)
-        traffic = NCU_DRAM_BYTES.get(key + (batch_imgs,))
-        roof = {'bound': 'tensor', 'kernel': '%s %s r=%d Cin=%d Nout=%d (%d images)' % (key + (batch_imgs,)),
-                'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
-                'traffic': traffic,
-                'traffic_basis': ('dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full '
-                                  '(profiles/r01_ncu_r34_spade_groups.csv)') if traffic else None,
-                'flops_per_launch': fl / n,
-                'peak_basis': 'tf32 operands: half of the %s bf16 sustained peak (%.1f TFLOP/s)' % (pk['source'], pk['bf16_tflops_sustained']),
-                'frac_of_bf16_peak': achieved / pk['bf16_tflops_sustained'],
-                'launches': n, 'avg_launch_us': ms * 1e3 / n, 'share_of_step': (ms / prof_steps) / (ms_dev / args.steps),
-                'measured_in': 'eager pass of %d steps, CUDA events around every launch' % prof_steps,
-                'all_kernels': {k: {'TFLOPs': v[0] / (v[1] / 1e3) / 1e12, 'ms_per_step': v[1] / prof_steps, 'launches': v[2],
-                                    'frac': v[0] / (v[1] / 1e3) / 1e12 / tf32_peak,
-                                    'share_of_step': (v[1] / prof_steps) / (ms_dev / args.steps)}
-                                for k, v in agg.items()}}
+        tr = ncu_traffic()
+        tkey = ' '.join(str(k) for k in key + (batch_imgs,))
+        roof.update({
+            'kernel': '%s (%d images)' % (' '.join(str(k) for k in key), batch_imgs),
+            'traffic': tr['launches'].get(tkey), 'traffic_basis': ('dram__bytes_read.sum + dram__bytes_write.sum of one launch, '
+                                                                  'ncu --set full: %s' % tr['source']) if tr['launches'].get(tkey) else None,
+            'work_per_launch': w_ / n_,
+            'peak_basis': ('cuBLAS TF32 8192^3 sustained, measured in this run (%.1f TFLOP/s; burst %.1f); MEASURED_PEAKS.json (%s) '
+                           'holds bf16 only: %.1f sustained' % (tf32_peak, tf32['tf32_tflops'], pk['source'], pk['bf16_tflops_sustained'])),
+            'frac_of_half_bf16_peak': roof['achieved'] / (pk['bf16_tflops_sustained'] / 2.0) if roof['bound'] == 'tensor' else None,
+            'measured_in': 'eager pass of %d steps, CUDA events around every launch' % prof_steps})
     def shutdown():
         # Every rank leaves together and WITHOUT tearing NCCL down: destroying a communicator whose
         # collectives live inside a captured CUDA graph (and the interpreter's own teardown order
@@ -428,21 +623,19 @@ def run_ours(args):
         shutdown()
         return
     line = {
-        'metric': 'train-step frames/sec at CATER 256x256', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 GEMMs / f32 elsewhere', 'data': 'synthetic',
-        'config': {'workload': workload_text(args),
-                   'loss': ('L1 image + box surrogate (generator step only)' if args.generator_only else
-                            'reference losses: GAN hinge + feature matching + flow warp (G), hinge (D), masked smooth-L1 (graph); no VGG'),
-                   'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush',
-                   'parallelism': 'dp%d (clips sharded per rank, gradient all-reduce per optimiser, SyncBN stats for SPADE)' % world,
-                   'conv_impl': args.conv_impl, 'step_execution': mode},
+        'config': bench_config(args),
+        'impl_detail': {'conv_impl': args.conv_impl, 'step_execution': mode, 'native_so_sha256': so_sha256()},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': sampler.summary() if sampler else None,
         'roofline': roof,
-        'cpu_baseline': ({k: cpu_base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')} if cpu_base else None),
+        'roofline_kernels': roof_all,
+        'tf32_peak_measured': tf32,
+        'cpu_baseline': cpu_base,
     }
     print(json.dumps(line), flush=True)
     shutdown()

@@ -105,3 +105,9 @@ def dyadic_spade_state(state, seed=0, prefix_filter=None):
 
 def dyadic_seg(name, shape, seed, density):
     return dy_tensor(name, shape, seed, 1.0, 1, density=density)
+
+
+def c4_masks(name, M, O=10):
+    """Soft object masks for the BASELINE config-4 K2b cases, regenerated from the name (not stored)."""
+    keep = det_tensor('k2bc4.mask.keep.%s' % name, (O, M, M), 8) > -0.5
+    return keep.float() * det_tensor('k2bc4.mask.val.%s' % name, (O, M, M), 8).abs().clamp(max=1.0)

@@ -31,7 +31,7 @@ sys.path.insert(0, REF)
 torch.Tensor.cuda = lambda self, *a, **k: self
 torch.Tensor.get_device = lambda self: 0
 
-from _util import det_state, det_tensor, dyadic_seg, dyadic_spade_state  # noqa: E402
+from _util import c4_masks, det_state, det_tensor, dyadic_seg, dyadic_spade_state  # noqa: E402
 from ag2video_b200.config import cater_vocab, synthetic_batch  # noqa: E402
 
 from models.graph_models.graph import GraphTripleConv  # noqa: E402
@@ -348,6 +348,100 @@ def losses_case():
                       ['discriminator_0.model0.0.weight', 'discriminator_1.model3.0.0.weight_orig',
                        'gconvs.0.net1.0.weight', 'fc_objs_vecs.weight', 'acts_embeddings.weight']},
         graph_grad_norms={k: float(v.norm()) for k, v in gg_grads.items() if k.startswith('acts_to_boxes')}))
+
+
+def _iteration_golden(size, B, F, seed_batch, seed_graph, name_gen, name_loss, picks_g, full_grads=()):
+    """Generator fwd+bwd (surrogate L1 loss) and one iteration's three losses of the REFERENCE at
+    ``size`` x ``size`` on B clips x F frames (graph batch: B clips x 16 frames)."""
+    from models.spade_models.networks.discriminator import MultiscaleActionDiscriminator
+    from models.spade_models.loss_model import LossModel
+    opt = ref_opt(['--image_size', '%d,%d' % (size, size), '--batch_size', str(B)])
+    m = AG2VideoModel(opt, torch.device('cpu'))
+    load_det(m, 61)
+    m.train()
+    b = synthetic_batch(B=B, F=F, image_size=size, seed=seed_batch)
+    state0 = {k: v.clone() for k, v in m.state_dict().items()}
+    out = m(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], test_mode=False, use_gt=True)
+    imgs_pred, boxes_pred, flows, conf, _ = out
+    loss = (imgs_pred - b['imgs']).abs().mean() + (boxes_pred - b['boxes'])[:, 1:].abs().mean()
+    loss.backward()
+    grads = grads_of(m)
+    save(name_gen, dict(seed=61, batch_seed=seed_batch, size=size, B=B, F=F, imgs_pred=imgs_pred.detach(),
+                        boxes_pred=boxes_pred.detach(), flows=flows.detach(), conf=conf.detach(), loss=loss.detach(),
+                        grad_norms={k: float(v.norm()) for k, v in grads.items()},
+                        grad_picks={k: grads[k].flatten()[:4096].clone() for k in picks_g},
+                        grad_full={k: grads[k].clone() for k in full_grads}))
+    # the three losses of one iteration, on a FRESH copy of the weights / running statistics
+    m.load_state_dict(state0, strict=True)
+    m.zero_grad()
+    netD = MultiscaleActionDiscriminator(opt)
+    load_det(netD, 71)
+    netD.train()
+    lm = LossModel(opt, types.SimpleNamespace(img_discriminator=netD))
+    batch = (b['imgs'], b['objs'], b['boxes'], b['triplets'], b['actions'], None)
+    out = m(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], test_mode=False, use_gt=True)
+    G = {k: v.mean() for k, v in lm(batch, out, mode='compute_generator_loss').items()}
+    netD.zero_grad()
+    G['total_loss'].backward()
+    g_grads = grads_of(m)
+    netD.zero_grad()
+    D = {k: v.mean() for k, v in lm(batch, out, mode='compute_discriminator_loss').items()}
+    D['total_img_loss'].backward()
+    d_grads = {k: p.grad.clone() for k, p in netD.named_parameters() if p.grad is not None}
+    bg = synthetic_batch(B=B, F=16, image_size=size, seed=seed_graph, with_images=False)
+    bp = m(None, bg['objs'], bg['triplets'], bg['actions'], boxes_gt=bg['boxes'], test_mode=False, graph_only=True)
+    GG = lm((None, bg['objs'], bg['boxes'], bg['triplets'], bg['actions'], None), bp, mode='compute_graph_loss')
+    m.zero_grad()
+    GG['total_loss'].backward()
+    gg_grads = grads_of(m)
+    save(name_loss, dict(
+        seed_g=61, seed_d=71, batch_seed=seed_batch, graph_batch_seed=seed_graph, size=size, B=B, F=F,
+        G={k: v.detach().clone() for k, v in G.items()}, D={k: v.detach().clone() for k, v in D.items()},
+        graph={k: v.detach().clone() for k, v in GG.items()}, graph_boxes_pred=bp.detach().clone(),
+        g_grad_norms={k: float(v.norm()) for k, v in g_grads.items()},
+        d_grad_norms={k: float(v.norm()) for k, v in d_grads.items()},
+        graph_grad_norms={k: float(v.norm()) for k, v in gg_grads.items() if k.startswith('acts_to_boxes')},
+        graph_grad_full={k: v.clone() for k, v in gg_grads.items()
+                         if k in ('acts_to_boxes.box_net.2.weight', 'acts_to_boxes.gconvs.1.net2.2.weight',
+                                  'acts_to_boxes.obj_vecs_net.0.weight', 'acts_to_boxes.pred_embeddings.weight',
+                                  'acts_to_boxes.acts_embeddings.weight',
+                                  'acts_to_boxes.attribute_embedding.attribute_fc_gen.bias')}))
+
+
+def k2b_c4_case():
+    """masks_to_layout / crop_bbox_batch at BASELINE config 4 sizes (10 objects, 256x256; masks 16 and 256
+    wide; crops 256 -> 32, B=2, N=4).  Inputs are regenerated from seeds by the tests; D is 2 here to keep
+    the fixture small (every channel runs the same code; the full D=512 case is checked against the oracle)."""
+    vocab = cater_vocab()
+    cases = {}
+    batch = synthetic_batch(B=2, F=4, image_size=256, seed=404, n_objects=10)
+    boxes = batch['boxes'][0, 0, :10].clone()
+    for name, M, test_mode in [('m16_train', 16, False), ('m256_train', 256, False), ('m256_test', 256, True)]:
+        masks = c4_masks(name, M)
+        vecs = det_tensor('k2bc4.%s' % name, (10, 2), 8).requires_grad_()
+        out = masks_to_layout(vecs, boxes, masks, 256, test_mode=test_mode)
+        cot = det_tensor('k2bc4.cot.%s' % name, out.shape, 8)
+        (out * cot).sum().backward()
+        cases[name] = dict(M=M, test_mode=test_mode, boxes=boxes, out=out.detach(), dvecs=vecs.grad.clone())
+    imgs = batch['imgs'].clone().requires_grad_()
+    crops, objs_flat = crop_bbox_batch(imgs, batch['objs'], batch['boxes'], 32, vocab=vocab)
+    cots = [det_tensor('k2bc4.crop.cot.%d' % i, c.shape, 9) for i, c in enumerate(crops)]
+    sum((c * k).sum() for c, k in zip(crops, cots)).backward()
+    dimgs = imgs.grad
+    cases['crop'] = dict(batch_seed=404, crops=[c.detach() for c in crops], objs_flat=objs_flat,
+                         dimgs_norm=float(dimgs.norm()), dimgs_pick=dimgs[:, :, :, ::8, ::8].clone())
+    save('k2b_c4.pt', cases)
+
+
+def generator256_case():
+    """BASELINE config 3 shapes (256x256) on a bounded sample: 1 clip x 2 frames (one generated frame),
+    the reference's generator fwd+bwd and the three losses of one iteration (generator256.pt, losses256.pt)."""
+    picks = ['layout_to_video.netG.up_3.norm_1.mlp_gamma.weight',
+             'layout_to_video.netG.head_0.norm_0.mlp_shared.0.weight',
+             'layout_to_video.netG.up_1.conv_0.weight_orig',
+             'acts_to_objs.gconvs.0.net1.0.weight', 'acts_to_objs.gconvs.2.net2.2.weight',
+             'acts_to_boxes.box_net.2.weight', 'layout_to_video.attribute_embedding.att_emb_1.weight']
+    _iteration_golden(256, 1, 2, 199, 201, 'generator256.pt', 'losses256.pt', picks)
 
 
 if __name__ == '__main__':

@@ -30,7 +30,16 @@ def test_reference_arm_prints_the_contract_line():
     assert d['value'] > 0 and d['gpu_launches'] == 0 and d['vs_baseline'] is None
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
-    assert 'workload' in d['config'] and 'sample' in d['config']
+    assert 'workload' in d['config'] and 'sample' in d['cpu_baseline']
+    assert d['steps'] == 1 and d['warmup'] == 0          # exactly the K / W the driver asked for
+    # the reference arm reports on the product arm's config object (same function builds both)
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ns = argparse.Namespace(size=64, batch=2, frames=4, gpus=1, generator_only=False)
+    assert d['config'] == bench.bench_config(ns) and d['metric'] == bench.METRIC
 
 
 def test_reference_arm_other_ranks_exit_without_work():

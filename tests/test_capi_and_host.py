@@ -156,3 +156,18 @@ def test_missing_library_fails_loudly(monkeypatch):
         L.lib()
     with pytest.raises(RuntimeError):
         L.launch_count()
+
+
+def test_forced_build_recompiles_every_source():
+    """__graft_entry__.build(force=True): the object cache is discarded, every .cu is recompiled for
+    sm_100a and the library is relinked (the default build reuses mtime-cached objects)."""
+    import time
+    import __graft_entry__ as entry
+    from ag2video_b200 import build as B
+    t0 = time.time() - 1.0
+    path = entry.build(force=True)
+    objs = [os.path.join(B.OBJ, s[:-3] + '.o') for s in B._sources()]
+    assert objs and all(os.path.getmtime(o) >= t0 for o in objs)
+    assert os.path.getmtime(path) >= t0
+    logs = [open(o + '.ptxas.log').read() for o in objs]
+    assert any("Compiling entry function" in l and "sm_100a" in l for l in logs)

@@ -57,10 +57,18 @@ def test_grad_allreduce_and_sharding_two_ranks():
     assert res[0][2] >= 4
 
 
-def test_shard_clips_ragged():
-    parts = [shard_clips(7, r, 4) for r in range(4)]
-    assert sorted(sum(parts, [])) == list(range(7))
-    assert shard_clips(2, 3, 4) == []
+def test_shard_clips_equal_shards():
+    """Every rank gets the same number of clips (ragged shards bias the 1/world gradient average
+    and the SyncBN count, an empty shard hangs the collectives)."""
+    import pytest
+    parts = [shard_clips(7, r, 4) for r in range(4)]                       # drop_last: 7 -> 4 x 1
+    assert [len(p) for p in parts] == [1, 1, 1, 1] and len(set(sum(parts, []))) == 4
+    parts = [shard_clips(7, r, 4, drop_last=False) for r in range(4)]      # padded by wrapping: 4 x 2
+    assert [len(p) for p in parts] == [2, 2, 2, 2] and set(sum(parts, [])) == set(range(7))
+    assert [shard_clips(8, r, 2) for r in range(2)] == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    with pytest.raises(ValueError):
+        shard_clips(2, 3, 4)
+    assert shard_clips(2, 3, 4, drop_last=False) == [1]
 
 
 # ---- Trainer.iteration over two gloo ranks (host logic of the N>1 path, CPU stand-in networks) ----------

@@ -42,8 +42,13 @@ def test_thin_conv_matches_torch(ci, co, slope, act, cl, B, H, W):
         assert max_rel(a, b) <= 2e-5, (name, max_rel(a, b))
 
 
-def test_thin_conv_falls_back_for_other_shapes():
+def test_thin_conv_other_shapes_raise_unless_library_is_allowed():
+    """No silent library path: a shape without a kernel raises; the explicit opt-in warns and uses cuDNN."""
     from ag2video_b200.thinconv import thin_conv3x3
     conv = nn.Conv2d(16, 5, 3, padding=1).cuda()
     x = torch.randn(1, 16, 8, 8, device='cuda')
-    assert max_rel(thin_conv3x3(conv, x, 0.2, 'tanh'), torch.tanh(conv(F.leaky_relu(x, 0.2)))) <= 1e-6
+    with pytest.raises(NotImplementedError):
+        thin_conv3x3(conv, x, 0.2, 'tanh')
+    with pytest.warns(RuntimeWarning):
+        y = thin_conv3x3(conv, x, 0.2, 'tanh', allow_library=True)
+    assert max_rel(y, torch.tanh(conv(F.leaky_relu(x, 0.2)))) <= 1e-6

@@ -255,3 +255,66 @@ def test_gconv_edge_cases_match_reference(name):
     ((new_obj * c['c1']).sum() + (new_p * c['c2']).sum()).backward()
     assert max_rel(obj.grad, c['dobj']) <= TOL and max_rel(pred.grad, c['dpred']) <= TOL
     _check_grads(_grads(layer), c['dparams'])
+
+
+def test_generator256_and_losses256_match_reference():
+    """BASELINE config 3 shapes (256x256) on a bounded sample (1 clip x 2 frames): the oracle generator and
+    one iteration's three losses against the reference's (tests/golden/generator256.pt, losses256.pt)."""
+    from oracle import losses as oloss
+    c, cl = golden('generator256.pt'), golden('losses256.pt')
+    opt = make_opt(256, batch_size=1)
+    m = onet.AG2VideoModel(opt)
+    state0 = det_state(m.state_dict(), c['seed'])
+    m.load_state_dict(state0, strict=True)
+    m.train()
+    b = synthetic_batch(B=1, F=2, image_size=256, seed=c['batch_seed'])
+    imgs_pred, boxes_pred, flows, conf, _ = m(b['imgs'], b['objs'], b['triplets'], b['actions'],
+                                              boxes_gt=b['boxes'], use_gt=True)
+    assert max_rel(imgs_pred, c['imgs_pred']) <= 5e-4 and max_rel(boxes_pred, c['boxes_pred']) <= 2e-5
+    loss = (imgs_pred - b['imgs']).abs().mean() + (boxes_pred - b['boxes'])[:, 1:].abs().mean()
+    assert abs(float(loss) - float(c['loss'])) <= 1e-5 * abs(float(c['loss']))
+    loss.backward()
+    grads = _grads(m)
+    bad = [k for k, n in c['grad_norms'].items() if abs(float(grads[k].norm()) - n) > 5e-3 * max(n, 1e-6)]
+    assert not bad, bad[:5]
+    # the iteration's losses on a fresh copy of the weights
+    m.load_state_dict(state0, strict=True)
+    netD = oloss.MultiscaleActionDiscriminator(opt)
+    netD.load_state_dict(det_state(netD.state_dict(), cl['seed_d']), strict=True)
+    netD.train()
+    lm = oloss.LossModel(opt, netD)
+    out = m(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+    G = lm.compute_generator_loss(b, out)
+    for k, v in cl['G'].items():
+        tol = 5e-3 if k in ('loss_F_Warp', 'total_loss') else 1e-4
+        assert abs(float(G[k]) - float(v)) <= tol * abs(float(v)), (k, float(G[k]), float(v))
+    D = lm.compute_discriminator_loss(b, out)
+    for k, v in cl['D'].items():
+        assert abs(float(D[k]) - float(v)) <= 1e-4 * abs(float(v)), k
+    bg = synthetic_batch(B=1, F=16, image_size=256, seed=cl['graph_batch_seed'], with_images=False)
+    bp = m(None, bg['objs'], bg['triplets'], bg['actions'], boxes_gt=bg['boxes'], graph_only=True)
+    assert max_rel(bp, cl['graph_boxes_pred']) <= 2e-5
+    GG = lm.compute_graph_loss(bg, bp)
+    assert abs(float(GG['total_loss']) - float(cl['graph']['total_loss'])) <= 1e-5 * abs(float(cl['graph']['total_loss']))
+    m.zero_grad()
+    GG['total_loss'].backward()
+    gg = _grads(m)
+    for k, v in cl['graph_grad_full'].items():
+        assert max_rel(gg[k], v) <= 1e-4, k
+
+
+def test_k2b_config4_oracle_matches_reference():
+    """masks_to_layout / crop_bbox_batch at the BASELINE config 4 sizes: the oracle reproduces the
+    reference's outputs (tests/golden/k2b_c4.pt)."""
+    from _util import c4_masks, det_tensor
+    from ag2video_b200.config import cater_vocab
+    g = golden('k2b_c4.pt')
+    for name in ('m16_train', 'm256_train', 'm256_test'):
+        c = g[name]
+        out = oops.masks_to_layout(det_tensor('k2bc4.%s' % name, (10, 2), 8), c['boxes'], c4_masks(name, c['M']), 256,
+                                   test_mode=c['test_mode'])
+        assert max_rel(out, c['out']) <= TOL, name
+    b = synthetic_batch(B=2, F=4, image_size=256, seed=g['crop']['batch_seed'], n_objects=10)
+    crops, flat = oops.crop_bbox_batch(b['imgs'], b['objs'], b['boxes'], 32, vocab=cater_vocab())
+    for got, want, gf, wf in zip(crops, g['crop']['crops'], flat, g['crop']['objs_flat']):
+        assert max_rel(got, want) <= TOL and torch.equal(gf, wf)
