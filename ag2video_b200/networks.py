@@ -73,7 +73,9 @@ class Acts2LayoutModel(nn.Module):
         self.obj_vecs_net = nn.Sequential(nn.Linear(obj_in + 4, obj_in, bias=False), nn.ReLU(),
                                           nn.Linear(obj_in, obj_in, bias=False), nn.ReLU())
 
-    def forward(self, objs, triplets, actions, boxes_gt=None, test_mode=False):
+    def prepare(self, objs, triplets, actions):
+        """Everything of model.py:108-158 that does not depend on the recurrence, for all timesteps at once:
+        (emb [B,O,De], pred_vecs [B,T,E,Dp], edges [B,T,E,2], ind [B,T,E], actions_data)."""
         B, T = triplets.shape[:2]
         A = actions.shape[1]
         dev = actions.device
@@ -84,7 +86,6 @@ class Acts2LayoutModel(nn.Module):
         a_id = torch.where((rel_t >= 0) & (rel_t <= 1), act[..., 1], act[..., 1].new_full((), float(self.pad_act)))
         temporal_triplets = torch.stack([act[..., 0], a_id, act[..., 2]], dim=-1).long()
         x_end, y_end = act[..., 5], act[..., 6]
-        # everything that does not depend on the recurrence is prepared for all timesteps at once
         act_vecs = self.acts_embeddings(temporal_triplets[..., 1])
         act_vecs = torch.cat([act_vecs[..., :-3], x_end.unsqueeze(-1), y_end.unsqueeze(-1), rel_t.unsqueeze(-1)], dim=-1)
         edges = torch.stack([temporal_triplets[..., 0], temporal_triplets[..., 2]], dim=-1)   # (no list index: that is a host->device copy)
@@ -94,14 +95,21 @@ class Acts2LayoutModel(nn.Module):
             edges = torch.cat([torch.stack([triplets[..., 0], triplets[..., 2]], dim=-1), edges], dim=2)
             ind = torch.cat([triplets[..., 1] != self.pad_pred, ind], dim=2)
             pred_vecs = torch.cat([self.pred_embeddings(triplets[..., 1]), act_vecs], dim=2)
+        emb = self.attribute_embedding(objs)
+        locs = torch.stack([x_end, y_end], dim=-1)
+        return emb, pred_vecs, edges, ind, [triplets, temporal_triplets, rel_t, locs]
+
+    def recurrence_layerwise(self, emb, pred_vecs, edges, ind, box0):
+        """The frame loop of model.py:126-169 with one fused kernel per graph layer (csrc/k1_gcn.cu): the general
+        path, used when the persistent recurrence kernel does not cover the sizes."""
+        T = pred_vecs.shape[1]
         # time-major and unbound once: every per-timestep operand is then a contiguous view (no copy per
         # layer call) and the backward of the T slices is ONE stack instead of T zero-filled select_backwards
         edges_t = edges.transpose(0, 1).contiguous().unbind(0)
         ind_t = ind.transpose(0, 1).contiguous().unbind(0)
         preds_t = pred_vecs.transpose(0, 1).contiguous().unbind(0)
-        emb = self.attribute_embedding(objs)
-        boxes = [boxes_gt[:, 0]]
-        per_t = [emb.new_zeros(objs.shape[0], objs.shape[1], self.embedding_dim)]
+        boxes = [box0]
+        per_t = [emb.new_zeros(emb.shape[0], emb.shape[1], self.gconvs[-1].net2[2].weight.shape[0])]
         for t in range(1, T):
             obj_vecs = self.obj_vecs_net(torch.cat([emb, boxes[-1]], dim=-1))
             p_vecs = preds_t[t]
@@ -109,8 +117,26 @@ class Acts2LayoutModel(nn.Module):
                 obj_vecs, p_vecs = layer(obj_vecs, p_vecs, edges_t[t], ind_t[t])
             per_t.append(obj_vecs)
             boxes.append(boxes[-1] + self.box_net(obj_vecs))                           # model.py:168
-        locs = torch.stack([x_end, y_end], dim=-1)
-        return torch.stack(per_t, dim=1), torch.stack(boxes, dim=1), [triplets, temporal_triplets, rel_t, locs]
+        return torch.stack(per_t, dim=1), torch.stack(boxes, dim=1)
+
+    def forward(self, objs, triplets, actions, boxes_gt=None, test_mode=False):
+        return acts2layout_forward([self], objs, triplets, actions, boxes_gt)[0]
+
+
+def acts2layout_forward(models, objs, triplets, actions, boxes_gt):
+    """``Acts2LayoutModel.forward`` for one or several models on the same clips (the generator step evaluates
+    ``acts_to_boxes`` and ``acts_to_objs`` side by side): the whole recurrence of all of them is ONE launch of
+    the persistent kernel (recurrence.run); sizes it does not cover walk the layers instead."""
+    from . import recurrence
+    prep = [m.prepare(objs, triplets, actions) for m in models]
+    box0 = boxes_gt[:, 0]
+    edges, ind = prep[0][2], prep[0][3]
+    res = None
+    if all(isinstance(g, GraphTripleConv) for m in models for g in m.gconvs) and objs.is_cuda:
+        res = recurrence.run(models, [p[0] for p in prep], box0, [p[1] for p in prep], edges, ind)
+    if res is None:
+        res = [m.recurrence_layerwise(p[0], p[1], p[2], p[3], box0) for m, p in zip(models, prep)]
+    return [(ov, bx, p[4]) for (ov, bx), p in zip(res, prep)]
 
 
 class _BN2d(nn.Module):
@@ -400,10 +426,11 @@ class AG2VideoModel(nn.Module):
             self.to(memory_format=CL)
 
     def forward(self, imgs, objs, triplets, actions, boxes_gt=None, test_mode=False, use_gt=False, graph_only=False):
-        _, boxes_pred, actions_data = self.acts_to_boxes(objs, triplets, actions, boxes_gt, test_mode)
         if graph_only:
-            return boxes_pred
-        obj_vecs, _, actions_data = self.acts_to_objs(objs, triplets, actions, boxes_gt, test_mode)
+            return self.acts_to_boxes(objs, triplets, actions, boxes_gt, test_mode)[1]
+        # both graph models on the same clips: one launch of the recurrence kernel for the two of them
+        (_, boxes_pred, _), (obj_vecs, _, actions_data) = acts2layout_forward(
+            [self.acts_to_boxes, self.acts_to_objs], objs, triplets, actions, boxes_gt)
         boxes_in = boxes_gt if use_gt else boxes_pred.detach()
         imgs_pred, flows, conf = self.layout_to_video(imgs, objs, obj_vecs, boxes_in, test_mode=test_mode)
         return imgs_pred, boxes_pred, flows, conf, actions_data

@@ -53,6 +53,48 @@ int ag2v_gcn_layer_bwd(const float* obj, const float* pred, const long long* edg
                        float* workspace, float* dobj, float* dpred, float* dW1a, float* db1a, float* dW1b,
                        float* db1b, float* dW2a, float* db2a, float* dW2b, float* db2b, ag2v_stream_t stream);
 
+/* ---- K1r: the Acts2LayoutModel recurrence as one persistent kernel per direction ---------------
+ * Replaces the frame loop of Acts2LayoutModel.forward (models/graph_models/model.py:126-169):
+ *   for t = 1..T-1: x = obj_vecs_net([emb | boxes[t-1]]); (x, p) = gconv_l(x, p, edges[t], ind[t]) for all layers
+ *                   (GraphTripleConv.forward, graph.py:41-107); boxes[t] = boxes[t-1] + box_net(x)
+ * One thread-block cluster of CS CTAs per chain = (model, clip); NC chains per launch.  The ten leading ints are
+ * (O nodes <= 16, E edges per timestep <= 16, T frames, Kx = De = width of the attribute embedding, Dp, H, Dout, Dpo, NL).
+ * Parameter order of `params` / `grads` (host arrays of device pointers): obj_vecs_net[0].weight [De][Kx+4],
+ * obj_vecs_net[2].weight [De][De], per layer net1[0].{weight,bias}, net1[2].{weight,bias}, net2[0].{weight,bias},
+ * net2[2].{weight,bias}, then box_net[0].{weight,bias}, box_net[2].{weight,bias}.
+ * ag2v_recur_pack re-lays the parameters out per CTA (both directions) once per optimiser step. */
+int ag2v_recur_cluster_size(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL);
+int ag2v_recur_cluster_fits(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int CS);
+int ag2v_recur_max_active_clusters(int CS);
+int ag2v_recur_num_params(int NL);
+int ag2v_recur_set_profile(unsigned long long* buf);   /* debug timeline of CTA 0, see k1r_recur.cu */
+size_t ag2v_recur_pack_floats(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int CS);
+size_t ag2v_recur_saved_floats(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int NC);
+size_t ag2v_recur_z_floats(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int NC);
+int ag2v_recur_pack(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int CS,
+                    const float* const* params, float* pack, ag2v_stream_t stream);
+/* emb [NC][O][Kx], pred [NC][T][E][Dp] (model-major, NC = n_models * clips); box0 [clips][O][4],
+ * edges [clips][T][E][2] int64, ind [clips][T][E] uint8 are data shared by the models; objv [NC][T][O][Dout],
+ * boxes [NC][T][O][4]; saved: ag2v_recur_saved_floats floats kept for the backward. */
+int ag2v_recur_fwd(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int CS, int NC,
+                   int n_models, const float* const* packs, const float* emb, const float* box0, const float* pred,
+                   const long long* edges, const unsigned char* ind, float* objv, float* boxes, float* saved,
+                   ag2v_stream_t stream);
+/* Reverse chain of ONE model = chains [chain0, chain0 + nchains) of the forward launch: data gradients and the
+ * Z buffer (gated output gradient of every Linear) for ag2v_recur_wgrad.  Model-local arrays: boxes, d_objv and
+ * d_boxes (may be NULL = zero), d_emb, d_box0, d_pred, and the per-chain partial sums dw0box [nchains][De][4],
+ * dwb2 [nchains][4][H], dbb2 [nchains][4]. */
+int ag2v_recur_bwd(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int CS, int NC,
+                   int chain0, int nchains, const float* pack, const float* saved, const float* boxes,
+                   const float* d_objv, const float* d_boxes, const long long* edges, const unsigned char* ind,
+                   float* z, float* d_emb, float* d_box0, float* d_pred, float* dw0box, float* dwb2, float* dbb2,
+                   ag2v_stream_t stream);
+/* All weight / bias gradients of the model as ONE grouped GEMM over the (chain, t, row) rows + one column-sum
+ * kernel; obj_vecs_net[0].weight receives its first Kx columns, box_net[2] comes from dwb2 / dbb2. */
+int ag2v_recur_wgrad(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int NC,
+                     int chain0, int nchains, const float* saved, const float* z, const float* emb,
+                     float* const* grads, ag2v_stream_t stream);
+
 /* ---- K2: layout composition ---------------------------------------------------
  * Replaces boxes_to_layout (models/layout.py:28-63) incl. _boxes_to_grid (:98-130)
  * and _pool_samples (:205-237), batched over N (clip, frame) samples.
