@@ -177,11 +177,13 @@ static bool plan_ok(const Plan& p) {
 struct Saved {
   long long u0, x0, hb, cnt;                                         // [O][De], [O][De], [O][H], [16]
   long long part;                                                    // scratch [NC][2][16 ranks][16][4]: box partial sums
+  long long p0;                                                      // [NC][O][De]: emb W0[:, :Kx]^T, the time-invariant part of obj_vecs_net[0]
   long long trow[kMaxLayers], h1[kMaxLayers], h2[kMaxLayers], pooled[kMaxLayers], g1[kMaxLayers], nobj[kMaxLayers];
   long long total;
 };
 struct Zbuf {
   long long zu0, zx0, zb1, zb2;                                      // [O][De], [O][De], [O][H], [O][4]
+  long long part, ssum;                                              // scratch [NC][2][16][16][4]; [NC][O][De] = sum_t zu0
   long long z1[kMaxLayers], z2[kMaxLayers], z3[kMaxLayers], z4[kMaxLayers];
   long long total;
 };
@@ -193,6 +195,7 @@ __host__ __device__ inline Saved saved_layout(const Dims& d, int NC) {
   auto take = [&](long long rows, long long cols) { long long o = off; off += ct * rows * cols; return o; };
   s.u0 = take(d.O, d.De); s.x0 = take(d.O, d.De); s.hb = take(d.O, d.H); s.cnt = take(1, 16);
   s.part = off; off += (long long)NC * 2 * 16 * (kRows * 4);
+  s.p0 = off; off += (long long)NC * d.O * d.De;
   for (int l = 0; l < d.NL; ++l) {
     s.trow[l] = take(d.E, d.K1(l)); s.h1[l] = take(d.E, d.H); s.h2[l] = take(d.E, d.N2());
     s.pooled[l] = take(d.O, d.H); s.g1[l] = take(d.O, d.H); s.nobj[l] = take(d.O, d.Dout);
@@ -209,6 +212,8 @@ __host__ __device__ inline Zbuf z_layout(const Dims& d, int NC) {
   for (int l = 0; l < d.NL; ++l) {
     z.z1[l] = take(d.E, d.H); z.z2[l] = take(d.E, d.N2()); z.z3[l] = take(d.O, d.H); z.z4[l] = take(d.O, d.Dout);
   }
+  z.part = off; off += (long long)NC * 2 * 16 * (kRows * 4);
+  z.ssum = off; off += (long long)NC * d.O * d.De;
   z.total = off;
   return z;
 }
@@ -357,11 +362,18 @@ __device__ __forceinline__ void stamp(Ctx& cx, int what) {
 }
 
 // the producer warp: stream every chunk of every stage of every timestep, in consumer order
-__device__ __noinline__ void producer_loop(Smem* sm, const float* model, const Table& tab, int rank, int steps) {
+__device__ __noinline__ void producer_loop(Smem* sm, const float* model, const Table& tab, int rank, int steps, bool once_first) {
+  // the time-invariant stage (obj_vecs_net[0] on the embedding) runs once: before the loop in the forward
+  // (first entry of the table), after it in the backward (last entry)
   if ((threadIdx.x & 31) != 0) return;
   int slot = 0; uint32_t phase = 0;
-  for (int t = 0; t < steps; ++t) {
-    for (int s = 0; s < tab.n; ++s) {
+  const int lo = once_first ? 1 : 0, hi = once_first ? tab.n : tab.n - 1;
+  for (int t = -1; t <= steps; ++t) {
+    int s0, s1;
+    if (t < 0) { if (!once_first) continue; s0 = 0; s1 = 1; }
+    else if (t == steps) { if (once_first) continue; s0 = tab.n - 1; s1 = tab.n; }
+    else { s0 = lo; s1 = hi; }
+    for (int s = s0; s < s1; ++s) {
       const StageDev& st = tab.s[s];
       const float* slab = model + st.off + (long long)rank * st.ncta * st.K8 * 8;
       for (int c = 0; c < st.nchunk; ++c) {
@@ -635,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_fwd_kernel(const __grid_con
   const float* model = a.model[chain / a.chains_per_model];
   init_cta(sm, CS);
   const int steps = d.T - 1;
-  if (threadIdx.x >= kConsumers) { producer_loop(sm, model, a.tab, rank, steps); return; }
+  if (threadIdx.x >= kConsumers) { producer_loop(sm, model, a.tab, rank, steps, true); return; }
 
   Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, (blockIdx.x == 0) ? a.prof : nullptr};
   const Saved sv = saved_layout(d, a.NC);
@@ -649,24 +661,39 @@ __global__ void __launch_bounds__(kThreads, 1) recur_fwd_kernel(const __grid_con
   consumer_sync();
   const long long* edges0 = a.edges + (size_t)clip * d.T * E * 2;
   const unsigned char* ind0 = a.ind + (size_t)clip * d.T * E;
+  const int wDe = De / CS;
+  float* p0 = a.saved + sv.p0 + (size_t)chain * O * De;
+  {  // obj_vecs_net[0] = [emb | box] W0^T: the embedding part does not depend on t - ONE product per chain
+    load_rows(cx, a.emb + (size_t)chain * O * d.Kx, d.Kx, O, d.Kx);
+    run_stage(cx, a.tab.s[0], epi_make(nullptr, nullptr, p0, De, O, 0));
+    stage_sync(cx);
+  }
 
   for (int t = 1; t < d.T; ++t) {
     const long long ct = (long long)chain * steps + (t - 1);
     load_graph(sm, edges0 + (size_t)t * E * 2, ind0 + (size_t)t * E, t > 1,
                t + 1 < d.T ? edges0 + (size_t)(t + 1) * E * 2 : nullptr, ind0 + (size_t)(t + 1 < d.T ? t + 1 : t) * E, O, E);
     if (rank == 0 && threadIdx.x < kRows) a.saved[sv.cnt + ct * 16 + threadIdx.x] = sm->cnt[threadIdx.x];
-    int s = 0;
-    {  // obj_vecs_net[0]: u0 = relu([emb | box] W0^T), the 4 box columns in the epilogue (model.py:136-137)
-      const StageDev& st = a.tab.s[s++];
-      load_rows(cx, a.emb + (size_t)chain * O * d.Kx, d.Kx, O, d.Kx);
-      Epi ep = epi_make(nullptr, nullptr, a.saved + sv.u0 + ct * O * De, De, O, 1);
-      ep.w4 = model + a.small.w0box;
-      run_stage(cx, st, ep);
-      stage_sync(cx);
+    int s = 1;
+    {  // u0 = relu(P + box W0[:, Kx:]^T) (model.py:136-137): 4 FMAs per element, every CTA builds the whole operand
+       // for itself and keeps its own columns for the backward
+      load_rows(cx, p0, De, O, De);
+      const float* wbox = model + a.small.w0box;
+      float* u0 = a.saved + sv.u0 + ct * O * De;
+      for (int i = threadIdx.x; i < O * De; i += kConsumers) {
+        const int m = i / De, k = i - m * De;
+        const float4 w = *reinterpret_cast<const float4*>(wbox + (size_t)k * 4);
+        const float* bx = sm->box + m * 4;
+        float v = sm->abuf[m * kLda + k];
+        v += bx[0] * w.x; v += bx[1] * w.y; v += bx[2] * w.z; v += bx[3] * w.w;
+        v = fmaxf(v, 0.f);
+        sm->abuf[m * kLda + k] = v;
+        if (k / wDe == rank) u0[i] = v;
+      }
+      consumer_sync();
     }
     {  // obj_vecs_net[2]
       const StageDev& st = a.tab.s[s++];
-      load_rows(cx, a.saved + sv.u0 + ct * O * De, De, O, De);
       run_stage(cx, st, epi_make(nullptr, nullptr, a.saved + sv.x0 + ct * O * De, De, O, 1));
       stage_sync(cx);
     }
@@ -784,13 +811,12 @@ __global__ void __launch_bounds__(kThreads, 1) recur_bwd_kernel(const __grid_con
   const float* model = a.model;
   init_cta(sm, CS);
   const int steps = d.T - 1;
-  if (threadIdx.x >= kConsumers) { producer_loop(sm, model, a.tab, rank, steps); return; }
+  if (threadIdx.x >= kConsumers) { producer_loop(sm, model, a.tab, rank, steps, false); return; }
 
   Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, nullptr};
   const Saved sv = saved_layout(d, a.NC);
   const Zbuf zz = z_layout(d, a.NC);
   const int O = d.O, E = d.E, H = d.H, De = d.De, N2 = d.N2(), Dout = d.Dout, Dpo = d.Dpo;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wH = H / CS, wDe = De / CS;
   for (int i = threadIdx.x; i < kRows * kMaxNcta; i += kConsumers) sm->acc0[i] = 0.f;
   for (int i = threadIdx.x; i < 4 * kMaxNcta; i += kConsumers) { sm->acc1[i] = 0.f; sm->acc2[i] = 0.f; }
@@ -908,49 +934,45 @@ __global__ void __launch_bounds__(kThreads, 1) recur_bwd_kernel(const __grid_con
         stage_sync(cx);
       }
     }
-    {  // obj_vecs_net[2]^T
+    {  // obj_vecs_net[2]^T -> zu0 columns owned here; obj_vecs_net[0]^T is linear in zu0, so its embedding part waits
+       // for the sum over t (one product per chain, below) and only the 4 box columns are needed now: per-CTA
+       // partials over the owned columns, exchanged through L2 and added in rank order -> the carry into step t-1
       const StageDev& st = a.tab.s[s++];
       load_rows(cx, a.z + zz.zx0 + ct * O * De, De, O, De);
       run_stage(cx, st, epi_make(nullptr, a.saved + sv.u0 + ct * O * De, a.z + zz.zu0 + ct * O * De, De, O, 0));
-      stage_sync(cx);
-    }
-    {  // obj_vecs_net[0]^T: d emb columns owned here accumulate over t; the 4 box columns close the recurrence
-      const StageDev& st = a.tab.s[s++];
-      load_rows(cx, a.z + zz.zu0 + ct * O * De, De, O, De);
-      run_stage(cx, st, epi_make(nullptr, nullptr, nullptr, d.Kx, O, 0));
       for (int i = threadIdx.x; i < O * st.ncta; i += kConsumers) sm->acc0[i] += sm->tile[i];
       const float* wbox = model + a.small.w0box;
-      for (int m = warp; m < O; m += 8) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = lane; k < De; k += 32) {
-          const float x = sm->abuf[m * kLda + k];
-          const float4 w = *reinterpret_cast<const float4*>(wbox + (size_t)k * 4);
-          acc[0] = fmaf(x, w.x, acc[0]); acc[1] = fmaf(x, w.y, acc[1]); acc[2] = fmaf(x, w.z, acc[2]); acc[3] = fmaf(x, w.w, acc[3]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
-        const float mine = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
-        if (lane < 4) sm->tmp4[m * 4 + lane] = sm->gb[m * 4 + lane] + mine;
+      float* part = a.z + zz.part + ((size_t)(a.chain0 + chain) * 2 + (t & 1)) * 16 * (kRows * 4);
+      for (int i = threadIdx.x; i < O * 4; i += kConsumers) {
+        const int m = i >> 2, j = i & 3;
+        float acc = 0.f;
+        for (int c = 0; c < st.ncta; ++c) acc = fmaf(sm->tile[m * st.ncta + c], wbox[(size_t)(rank * st.ncta + c) * 4 + j], acc);
+        part[(size_t)rank * (kRows * 4) + i] = acc;
       }
       // d W0[:, Kx:Kx+4] rows owned here: acc2[c][j] += sum_m zu0[m][rank*wDe + c] * boxes[t-1][m][j]
       const float* bprev = a.boxes + ((size_t)chain * d.T + (t - 1)) * O * 4;
       for (int i = threadIdx.x; i < 4 * wDe; i += kConsumers) {
         const int c = i >> 2, j = i & 3;
         float acc = sm->acc2[i];
-        for (int m = 0; m < O; ++m) acc = fmaf(sm->abuf[m * kLda + rank * wDe + c], bprev[m * 4 + j], acc);
+        for (int m = 0; m < O; ++m) acc = fmaf(sm->tile[m * st.ncta + c], bprev[m * 4 + j], acc);
         sm->acc2[i] = acc;
       }
-      consumer_sync();
-      for (int i = threadIdx.x; i < O * 4; i += kConsumers) sm->box[i] = sm->tmp4[i];
+      stage_sync(cx);
+      for (int i = threadIdx.x; i < O * 4; i += kConsumers) sm->box[i] = sm->gb[i] + sum_parts(part, CS, i);
       consumer_sync();
     }
   }
-  // results that accumulate over the chain
-  const StageDev& last = a.tab.s[a.tab.n - 1];
-  for (int i = threadIdx.x; i < O * last.ncta; i += kConsumers) {
-    const int m = i / last.ncta, c = i - m * last.ncta;
-    a.d_emb[((size_t)chain * O + m) * d.Kx + rank * last.ncta + c] = sm->acc0[i];
+  {  // d emb = (sum_t zu0) W0[:, :Kx]: the owned columns of the sum go to L2, then one product per chain
+    float* ssum = a.z + zz.ssum + (size_t)(a.chain0 + chain) * O * De;
+    for (int i = threadIdx.x; i < O * wDe; i += kConsumers) {
+      const int m = i / wDe, c = i - m * wDe;
+      ssum[(size_t)m * De + rank * wDe + c] = sm->acc0[i];
+    }
+    stage_sync(cx);
+    load_rows(cx, ssum, De, O, De);
+    run_stage(cx, a.tab.s[a.tab.n - 1], epi_make(nullptr, nullptr, a.d_emb + (size_t)chain * O * d.Kx, d.Kx, O, 0));
   }
+  // results that accumulate over the chain
   for (int i = threadIdx.x; i < 4 * wDe; i += kConsumers) a.dw0box[((size_t)chain * De + rank * wDe) * 4 + i] = sm->acc2[i];
   for (int i = threadIdx.x; i < 4 * wH; i += kConsumers) {
     const int j = i / wH, c = i - j * wH;
@@ -1290,21 +1312,25 @@ extern "C" int ag2v_recur_wgrad(int O, int E, int T, int Kx, int De, int Dp, int
   WArgs wa; wa.njobs = 0;
   BArgs ba; ba.njobs = 0;
   int tiles = 0, blks = 0;
-  auto job = [&](long long zoff, int rows, int N, const float* X, long long xoff, int K, int xdiv, float* dW, int ldw, float* db) {
-    const float* Z = z + zoff + ct0 * rows * N;
+  auto job2 = [&](const float* Z, long long R, int rows, int N, const float* X, int K, int xdiv, float* dW, int ldw, float* db) {
     if (dW) {
       WJob& j = wa.job[wa.njobs++];
-      j.Z = Z; j.X = X + xoff; j.dW = dW; j.db = nullptr; j.N = N; j.K = K; j.ldw = ldw; j.R = (int)(ctn * rows);
+      j.Z = Z; j.X = X; j.dW = dW; j.db = nullptr; j.N = N; j.K = K; j.ldw = ldw; j.R = (int)R;
       j.xdiv = xdiv; j.xrows = rows; j.tile0 = tiles; j.tiles_k = (K + kWT - 1) / kWT;
       tiles += ((N + kWT - 1) / kWT) * j.tiles_k;
     }
     if (db) {
       BJob& b = ba.job[ba.njobs++];
-      b.Z = Z; b.db = db; b.N = N; b.R = (int)(ctn * rows); b.blk0 = blks;
+      b.Z = Z; b.db = db; b.N = N; b.R = (int)R; b.blk0 = blks;
       blks += (N + 31) / 32;
     }
   };
-  job(zz.zu0, O, De, emb, 0, Kx, T - 1, grads[0], Kx + 4, nullptr);          // emb is the model's own [nchains][O][Kx]
+  auto job = [&](long long zoff, int rows, int N, const float* X, long long xoff, int K, int xdiv, float* dW, int ldw, float* db) {
+    job2(z + zoff + ct0 * rows * N, ctn * rows, rows, N, X + xoff, K, xdiv, dW, ldw, db);
+  };
+  // obj_vecs_net[0].weight[:, :Kx] = (sum_t zu0)^T emb: the backward leaves the per-chain sum in the Z buffer; emb is
+  // the model's own [nchains][O][Kx]
+  job2(z + zz.ssum + (long long)chain0 * O * De, (long long)nchains * O, O, De, emb, Kx, 1, grads[0], Kx + 4, nullptr);
   job(zz.zx0, O, De, saved, sv.u0 + ct0 * O * De, De, 1, grads[1], De, nullptr);
   for (int l = 0; l < NL; ++l) {
     const int b = 2 + 8 * l, K1 = d.K1(l), N2 = d.N2();

@@ -7,7 +7,8 @@ same dictionary keys.  Two things are evaluated differently from the reference
 without changing a single result:
 
 * the discriminator's conditioning (action-graph vectors and layout vectors) is
-  computed once per loss and shared by the fake and the real pass;
+  computed once per ITERATION: shared by the fake and the real pass of a loss, and
+  by the generator loss and the discriminator loss of the same ``model_out``;
 * in the generator loss nothing needs a gradient with respect to the
   discriminator's parameters (train.py:523 zeroes them before the discriminator
   step) and the real pass only supplies detached feature targets
@@ -85,12 +86,21 @@ class LossModel(nn.Module):
         n = opt.n_frames_G - 1
         objs, r_imgs, r_boxes, r_pred, r_act = self._relevant(batch, model_out)
         D = self.netD_img
+        # The conditioning depends on the discriminator's parameters and on data only, and those parameters do not
+        # move between this loss and the discriminator loss of the same iteration (train.py:446-464): evaluate it
+        # ONCE, with its autograd graph, use a detached copy here and hand the attached one to
+        # compute_discriminator_loss (keyed on the generator output it belongs to).
+        cond_full = D.condition(objs, r_boxes, r_act) if torch.is_grad_enabled() else None
+        self._cond_cache = (model_out[0], cond_full) if cond_full is not None else None
         params = [p for p in D.parameters() if p.requires_grad]
         for p in params:                   # no gradient w.r.t. the discriminator in the generator step
             p.requires_grad_(False)
         try:
-            with torch.no_grad():
-                cond = D.condition(objs, r_boxes, r_act)
+            if cond_full is not None:
+                cond = (cond_full[0].detach(),) + tuple(cond_full[1:])
+            else:
+                with torch.no_grad():
+                    cond = D.condition(objs, r_boxes, r_act)
             fake = D(r_pred, objs, r_boxes, r_act, cond=cond)
             out = {'GAN_Img': hinge_loss(fake, True, False) * getattr(opt, 'discriminator_img_loss_weight', 1.0)}
             if not getattr(opt, 'no_ganFeat_loss', False):
@@ -116,7 +126,12 @@ class LossModel(nn.Module):
         """loss_model.py:107-133."""
         objs, r_imgs, r_boxes, r_pred, r_act = self._relevant(batch, model_out)
         D = self.netD_img
-        cond = D.condition(objs, r_boxes, r_act)
+        cached = getattr(self, '_cond_cache', None)
+        self._cond_cache = None
+        if cached is not None and cached[0] is model_out[0]:
+            cond = cached[1]               # built by compute_generator_loss on the same model_out, graph attached
+        else:
+            cond = D.condition(objs, r_boxes, r_act)
         fake = D(r_pred.detach(), objs, r_boxes, r_act, cond=cond)
         real = D(r_imgs, objs, r_boxes, r_act, cond=cond)
         out = {'D_img_fake': hinge_loss(fake, False, True), 'D_img_real': hinge_loss(real, True, True)}

@@ -444,6 +444,33 @@ def generator256_case():
     _iteration_golden(256, 1, 2, 199, 201, 'generator256.pt', 'losses256.pt', picks)
 
 
+def cater_case():
+    """The reference's CATERDataset + collate_fn (data/cater.py, data/dataset_params.py) on the tiny on-disk fixture of
+    tests/_cater_fixture.py: test-time window (deterministic) and a seeded training-time window.  scikit-video, which
+    the reference imports to decode .avi files, is stubbed: the fixture ships the frame cache the reference reads."""
+    import tempfile
+    import numpy as np
+    sk, skio = types.ModuleType('skvideo'), types.ModuleType('skvideo.io')
+    skio.FFmpegReader = object
+    sk.io = skio
+    sys.modules['skvideo'], sys.modules['skvideo.io'] = sk, skio
+    from data.cater import CATERDataset
+    from data.dataset_params import collate_fn
+    import _cater_fixture
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        labels, data_root = _cater_fixture.write(root)
+        for mode, is_test in (('test', True), ('train', False)):
+            ds = CATERDataset(labels, data_root, is_test=is_test, image_size=(16, 16), frames_per_action=4,
+                              initial_frames_per_sample=48)
+            np.random.seed(7)
+            items = [ds[i] for i in range(len(ds))]
+            imgs, objs, boxes, triplets, actions, ids = collate_fn(ds.vocab, items)
+            out[mode] = dict(n=len(ds), names=list(ds.vid_names), imgs=imgs, objs=objs, boxes=boxes, triplets=triplets,
+                             actions=actions, ids=ids)
+    save('cater.pt', out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['gconv', 'gconv_edge', 'gconv_net', 'layout', 'masks', 'crop', 'spade', 'block',
                              'acts2layout', 'generator', 'losses']
