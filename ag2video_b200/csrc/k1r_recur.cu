@@ -340,6 +340,12 @@ struct Smem {
   unsigned long long full[kRing], empty[kRing], abar, sbar[2];
 };
 
+extern __shared__ __align__(128) unsigned char recur_smem_raw[];
+// Every function takes the shared image from the symbol itself, never through a pointer that crossed a call: a
+// pointer handed to a non-inlined function is generic, and its loads become LD.E (long scoreboard, ~10x the latency
+// of LDS; ncu source view of round 2) instead of LDS.
+#define RECUR_SMEM() (reinterpret_cast<Smem*>(recur_smem_raw))
+
 struct Pipe { int slot; uint32_t phase; };        // ring position shared by construction between producer and consumers
 
 struct Ctx {
@@ -362,10 +368,11 @@ __device__ __forceinline__ void stamp(Ctx& cx, int what) {
 }
 
 // the producer warp: stream every chunk of every stage of every timestep, in consumer order
-__device__ __noinline__ void producer_loop(Smem* sm, const float* model, const Table& tab, int rank, int steps, bool once_first) {
+__device__ __noinline__ void producer_loop(const float* model, const Table& tab, int rank, int steps, bool once_first) {
   // the time-invariant stage (obj_vecs_net[0] on the embedding) runs once: before the loop in the forward
   // (first entry of the table), after it in the backward (last entry)
   if ((threadIdx.x & 31) != 0) return;
+  Smem* sm = RECUR_SMEM();
   int slot = 0; uint32_t phase = 0;
   const int lo = once_first ? 1 : 0, hi = once_first ? tab.n : tab.n - 1;
   for (int t = -1; t <= steps; ++t) {
@@ -391,11 +398,11 @@ __device__ __noinline__ void producer_loop(Smem* sm, const float* model, const T
 // A operand: rows [0, M) of a row-major global matrix -> abuf (bulk copies by warp 0, everyone waits)
 struct RowSrc { const float* p0; const float* p1; const float* p2; };      // up to three pieces per row
 __device__ __forceinline__ void a_begin(Ctx& cx, uint32_t bytes) {
-  if (threadIdx.x == 0) mbar_expect_tx(smem_u32(&cx.sm->abar), bytes);
+  if (threadIdx.x == 0) mbar_expect_tx(smem_u32(&RECUR_SMEM()->abar), bytes);
   __syncwarp();
 }
 __device__ __forceinline__ void a_wait(Ctx& cx) {
-  mbar_wait(smem_u32(&cx.sm->abar), cx.aphase);
+  mbar_wait(smem_u32(&RECUR_SMEM()->abar), cx.aphase);
   cx.aphase ^= 1u;
 }
 __device__ __noinline__ void load_rows(Ctx& cx, const float* src, int ld, int M, int K) {
@@ -403,7 +410,7 @@ __device__ __noinline__ void load_rows(Ctx& cx, const float* src, int ld, int M,
   if (threadIdx.x < 32) {
     a_begin(cx, (uint32_t)(M * K) * 4u);
     for (int m = threadIdx.x; m < M; m += 32)
-      bulk_g2s(smem_u32(cx.sm->abuf + m * kLda), src + (size_t)m * ld, (uint32_t)K * 4u, smem_u32(&cx.sm->abar));
+      bulk_g2s(smem_u32(RECUR_SMEM()->abuf + m * kLda), src + (size_t)m * ld, (uint32_t)K * 4u, smem_u32(&RECUR_SMEM()->abar));
   }
   a_wait(cx);
 }
@@ -435,7 +442,7 @@ __device__ __forceinline__ Epi epi_make(const float* bias, const float* gate, fl
 // global operands (bias, gate, ...) are fetched BEFORE the product so their L2 latency hides behind it.
 template <int TN>
 __device__ __noinline__ void stage_tn(Ctx& cx, const StageDev& st, const Epi& ep) {
-  Smem* sm = cx.sm;
+  Smem* sm = RECUR_SMEM();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mg = lane >> 3, ng = lane & 7;
   constexpr int kElems = (kRows * TN * 8 + kConsumers - 1) / kConsumers;      // tile elements per thread in the epilogue
@@ -545,19 +552,29 @@ __device__ __noinline__ void run_stage(Ctx& cx, const StageDev& st, const Epi& e
 
 // end of a stage: everything this CTA wrote to global memory becomes visible to the cluster, and vice versa
 __device__ __noinline__ void stage_sync(Ctx& cx) {
+  // release: every consumer's global writes happen before the CTA barrier, then CS threads arrive (release.cluster) on
+  // the peers' barriers.  acquire: only warp 0 waits at cluster scope - it alone issues the bulk copies that read what
+  // the peers wrote (everything else a CTA reads from peers goes through ld.global.cg) - and the second CTA barrier
+  // releases the other warps.  An acquire.cluster by all 256 threads costs a CCTL.IVALL each (6.5% of all stall
+  // samples in the first ncu capture).
+  Smem* sm = RECUR_SMEM();
   stamp(cx, 4);
   consumer_sync();
   const int which = cx.scount & 1;
-  const uint32_t bar = smem_u32(&cx.sm->sbar[which]);
+  const uint32_t bar = smem_u32(&sm->sbar[which]);
   if (threadIdx.x < cx.CS) mbar_arrive_remote(bar, threadIdx.x);
-  mbar_wait_cluster(bar, cx.sphase[which]);
+  if (threadIdx.x < 32) {
+    mbar_wait_cluster(bar, cx.sphase[which]);
+    fence_proxy_async();
+  }
   cx.sphase[which] ^= 1u;
   ++cx.scount;
-  fence_proxy_async();
+  consumer_sync();
   stamp(cx, 5);
 }
 
-__device__ void init_cta(Smem* sm, int CS) {
+__device__ void init_cta(int CS) {
+  Smem* sm = RECUR_SMEM();
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) { mbar_init(smem_u32(&sm->full[i]), 1); mbar_init(smem_u32(&sm->empty[i]), 8); }
     mbar_init(smem_u32(&sm->abar), 1);
@@ -572,8 +589,9 @@ __device__ void init_cta(Smem* sm, int CS) {
 // indices, live / all incident-edge lists and counts of one timestep (graph.py:79-100).  `cur` = this timestep's
 // edges (used when nothing was prefetched), `nxt` = the timestep the chain visits next (or null): its edges are
 // fetched by the last consumer warp while the stages of this timestep run.
-__device__ __noinline__ void load_graph(Smem* sm, const long long* cur_e, const unsigned char* cur_i, bool have,
+__device__ __noinline__ void load_graph(const long long* cur_e, const unsigned char* cur_i, bool have,
                                         const long long* nxt_e, const unsigned char* nxt_i, int O, int E) {
+  Smem* sm = RECUR_SMEM();
   if (threadIdx.x < kRows) {
     const int e = threadIdx.x;
     int s = 0, o = 0, live = 0;
@@ -630,8 +648,6 @@ struct FwdArgs {
   unsigned long long* prof;
 };
 
-extern __shared__ __align__(128) unsigned char recur_smem_raw[];
-
 // per-CTA partial sums of a 4-wide product, exchanged through global memory and added in rank order
 __device__ __forceinline__ float sum_parts(const float* part, int CS, int i) {
   float v = 0.f;
@@ -645,9 +661,9 @@ __global__ void __launch_bounds__(kThreads, 1) recur_fwd_kernel(const __grid_con
   const int CS = d.CS, rank = (int)cluster_rank(), chain = blockIdx.x / CS;
   const int clip = chain % a.chains_per_model;        // box0 / edges / ind are data: shared by the models of a launch
   const float* model = a.model[chain / a.chains_per_model];
-  init_cta(sm, CS);
+  init_cta(CS);
   const int steps = d.T - 1;
-  if (threadIdx.x >= kConsumers) { producer_loop(sm, model, a.tab, rank, steps, true); return; }
+  if (threadIdx.x >= kConsumers) { producer_loop(model, a.tab, rank, steps, true); return; }
 
   Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, (blockIdx.x == 0) ? a.prof : nullptr};
   const Saved sv = saved_layout(d, a.NC);
@@ -671,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_fwd_kernel(const __grid_con
 
   for (int t = 1; t < d.T; ++t) {
     const long long ct = (long long)chain * steps + (t - 1);
-    load_graph(sm, edges0 + (size_t)t * E * 2, ind0 + (size_t)t * E, t > 1,
+    load_graph(edges0 + (size_t)t * E * 2, ind0 + (size_t)t * E, t > 1,
                t + 1 < d.T ? edges0 + (size_t)(t + 1) * E * 2 : nullptr, ind0 + (size_t)(t + 1 < d.T ? t + 1 : t) * E, O, E);
     if (rank == 0 && threadIdx.x < kRows) a.saved[sv.cnt + ct * 16 + threadIdx.x] = sm->cnt[threadIdx.x];
     int s = 1;
@@ -809,9 +825,9 @@ __global__ void __launch_bounds__(kThreads, 1) recur_bwd_kernel(const __grid_con
   const Dims& d = a.d;
   const int CS = d.CS, rank = (int)cluster_rank(), chain = blockIdx.x / CS;      // model-local chain (clip) index
   const float* model = a.model;
-  init_cta(sm, CS);
+  init_cta(CS);
   const int steps = d.T - 1;
-  if (threadIdx.x >= kConsumers) { producer_loop(sm, model, a.tab, rank, steps, false); return; }
+  if (threadIdx.x >= kConsumers) { producer_loop(model, a.tab, rank, steps, false); return; }
 
   Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, nullptr};
   const Saved sv = saved_layout(d, a.NC);
@@ -830,7 +846,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_bwd_kernel(const __grid_con
 
   for (int t = d.T - 1; t >= 1; --t) {
     const long long ct = (long long)(a.chain0 + chain) * steps + (t - 1);      // row block inside the saved / Z buffers
-    load_graph(sm, edges0 + (size_t)t * E * 2, ind0 + (size_t)t * E, t < d.T - 1,
+    load_graph(edges0 + (size_t)t * E * 2, ind0 + (size_t)t * E, t < d.T - 1,
                t > 1 ? edges0 + (size_t)(t - 1) * E * 2 : nullptr, ind0 + (size_t)(t > 1 ? t - 1 : t) * E, O, E);
     for (int i = threadIdx.x; i < O * 4; i += kConsumers)
       sm->gb[i] = sm->box[i] + (a.d_boxes ? a.d_boxes[((size_t)chain * d.T + t) * O * 4 + i] : 0.f);

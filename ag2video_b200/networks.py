@@ -21,7 +21,7 @@ from torch.nn.utils import spectral_norm
 
 from .graph import GraphTripleConv
 from .layout import boxes_to_layout_batched, layout_conv3x3, layout_tables
-from .spade import SPADEResnetBlock, SharedSeg, bn_act
+from .spade import SPADEResnetBlock, SharedSeg, bn_act, plain_conv3x3, plain_conv3x3_usable
 from .specnorm import SpectralNormGroup, conv_scaled, conv_unscaled
 from .thinconv import thin_conv3x3
 
@@ -241,7 +241,10 @@ class SPADEGenerator(nn.Module):
     def forward(self, layout, groups=1):
         seg = SharedSeg.wrap(layout)                       # one NHWC copy + one gradient buffer for all 18 SPADEs
         up = lambda z: F.interpolate(z, scale_factor=2, mode='nearest')
-        x = self.fc(seg.nearest(self.sh, self.sw))           # = F.interpolate(layout, size=(sh, sw))
+        x = seg.nearest(self.sh, self.sw)                    # = F.interpolate(layout, size=(sh, sw))
+        # fc on the tcgen05 implicit GEMM like the block convolutions (channels_last weights); the torch-layout
+        # model of the tests (opt.channels_last = False) keeps the module call
+        x = plain_conv3x3(self.fc, x) if plain_conv3x3_usable(self.fc, x) else self.fc(x)
         x = self.head_0(x, seg, groups)
         x = self.G_middle_0(up(x), seg, groups)
         x = self.G_middle_1(x, seg, groups)

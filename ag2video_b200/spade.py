@@ -459,6 +459,21 @@ def sn_conv3x3(conv, x, groups=1, res=None):
     return _SnConvFn.apply(x, getattr(conv, entry.name + '_orig'), conv.bias, entry.scale_g, res, conv, int(groups))
 
 
+def plain_conv3x3(conv, x):
+    """``conv(x)`` for a plain (not spectrally normalised) 3x3 / stride 1 / padding 1 ``nn.Conv2d`` with channels_last
+    weights on the tcgen05 implicit-GEMM kernel, forward, input and weight gradient - the generator's ``fc``
+    (spade_generator.py:16,56).  ``x``: float32 channels_last, already rounded to TF32 (e.g. ``SharedSeg.nearest``)."""
+    return _SnConvFn.apply(x, conv.weight, conv.bias, None, None, conv, 1)
+
+
+def plain_conv3x3_usable(conv, x):
+    w = conv.weight
+    return (tuple(w.shape[2:]) == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+            and conv.groups == 1 and w.shape[1] % 4 == 0 and w.shape[0] % 4 == 0 and not w.is_contiguous()
+            and w.is_contiguous(memory_format=torch.channels_last) and x.is_cuda and x.dtype == torch.float32
+            and x.is_contiguous(memory_format=torch.channels_last) and not _precise())
+
+
 def sn_conv3x3_usable(conv, x):
     entry = conv.__dict__.get('_ag2v_sn_entry')
     w = getattr(conv, entry.name + '_orig', None) if entry is not None else None

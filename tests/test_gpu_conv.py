@@ -160,3 +160,27 @@ def test_wgrad_kernels(B, r, rw, Cin, Nout, stride, two, impl):
         finally:
             sp.CONV_IMPL = old
     assert max_rel(got, w.grad) <= TOL
+
+
+def test_plain_conv3x3_fc_shape_forward_and_gradients_tol1e3():
+    """The generator's `fc` (spade_generator.py:16,56: 512 -> 1024 at 8x8, 6 images) on the tcgen05 implicit-GEMM
+    kernel: output, input gradient, weight gradient and bias gradient against torch's fp32 convolution."""
+    import ag2video_b200.spade as sp
+    g = torch.Generator().manual_seed(3)
+    conv = torch.nn.Conv2d(512, 1024, 3, padding=1).cuda().to(memory_format=torch.channels_last)
+    x0 = torch.randn(6, 512, 8, 8, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    x0 = x0.view(torch.int32).bitwise_and(-8192).view(torch.float32)         # TF32-representable operand, as SharedSeg hands it over
+    cot = torch.randn(6, 1024, 8, 8, generator=g).cuda()
+    x = x0.clone().requires_grad_()
+    assert sp.plain_conv3x3_usable(conv, x)
+    y = sp.plain_conv3x3(conv, x)
+    (y * cot).sum().backward()
+    got = [y.detach(), x.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone()]
+    conv.zero_grad()
+    x2 = x0.clone().requires_grad_()
+    ref = F.conv2d(x2, conv.weight, conv.bias, padding=1)
+    (ref * cot).sum().backward()
+    want = [ref.detach(), x2.grad, conv.weight.grad, conv.bias.grad]
+    errs = {n: max_rel(a, b) for n, a, b in zip(('y', 'dx', 'dw', 'db'), got, want)}
+    print('plain_conv3x3 512->1024 @8x8: ' + ' '.join('%s %.1e' % kv for kv in errs.items()))
+    assert max(errs.values()) <= TOL, errs
