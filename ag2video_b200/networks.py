@@ -123,19 +123,27 @@ class Acts2LayoutModel(nn.Module):
         return acts2layout_forward([self], objs, triplets, actions, boxes_gt)[0]
 
 
-def acts2layout_forward(models, objs, triplets, actions, boxes_gt):
+def acts2layout_forward(models, objs, triplets, actions, boxes_gt, needs_grad=None):
     """``Acts2LayoutModel.forward`` for one or several models on the same clips (the generator step evaluates
     ``acts_to_boxes`` and ``acts_to_objs`` side by side): the whole recurrence of all of them is ONE launch of
-    the persistent kernel (recurrence.run); sizes it does not cover walk the layers instead."""
+    the persistent kernel (recurrence.run); sizes it does not cover walk the layers instead.
+    ``needs_grad[i] = False`` evaluates model i without an autograd graph (its outputs are plain tensors)."""
     from . import recurrence
-    prep = [m.prepare(objs, triplets, actions) for m in models]
+    needs_grad = [True] * len(models) if needs_grad is None else list(needs_grad)
+    prep = []
+    for m, g in zip(models, needs_grad):
+        with torch.set_grad_enabled(g and torch.is_grad_enabled()):
+            prep.append(m.prepare(objs, triplets, actions))
     box0 = boxes_gt[:, 0]
     edges, ind = prep[0][2], prep[0][3]
     res = None
     if all(isinstance(g, GraphTripleConv) for m in models for g in m.gconvs) and objs.is_cuda:
-        res = recurrence.run(models, [p[0] for p in prep], box0, [p[1] for p in prep], edges, ind)
+        res = recurrence.run(models, [p[0] for p in prep], box0, [p[1] for p in prep], edges, ind, needs_grad)
     if res is None:
-        res = [m.recurrence_layerwise(p[0], p[1], p[2], p[3], box0) for m, p in zip(models, prep)]
+        res = []
+        for m, p, g in zip(models, prep, needs_grad):
+            with torch.set_grad_enabled(g and torch.is_grad_enabled()):
+                res.append(m.recurrence_layerwise(p[0], p[1], p[2], p[3], box0))
     return [(ov, bx, p[4]) for (ov, bx), p in zip(res, prep)]
 
 
@@ -428,12 +436,17 @@ class AG2VideoModel(nn.Module):
         if self.channels_last:
             self.to(memory_format=CL)
 
-    def forward(self, imgs, objs, triplets, actions, boxes_gt=None, test_mode=False, use_gt=False, graph_only=False):
+    def forward(self, imgs, objs, triplets, actions, boxes_gt=None, test_mode=False, use_gt=False, graph_only=False,
+                boxes_pred_grad=True):
+        """``boxes_pred_grad=False`` (not a reference argument): the returned ``boxes_pred`` carries no autograd graph.
+        The training loop's generator step never differentiates it (train.py:446-459: its losses are image losses and
+        ``optimizer_generator`` excludes ``acts_to_boxes``), and leaving ``acts_to_boxes`` out of that graph lets the
+        graph step own its gradient accumulators on its own stream (Trainer.iteration)."""
         if graph_only:
             return self.acts_to_boxes(objs, triplets, actions, boxes_gt, test_mode)[1]
         # both graph models on the same clips: one launch of the recurrence kernel for the two of them
         (_, boxes_pred, _), (obj_vecs, _, actions_data) = acts2layout_forward(
-            [self.acts_to_boxes, self.acts_to_objs], objs, triplets, actions, boxes_gt)
+            [self.acts_to_boxes, self.acts_to_objs], objs, triplets, actions, boxes_gt, [bool(boxes_pred_grad), True])
         boxes_in = boxes_gt if use_gt else boxes_pred.detach()
         imgs_pred, flows, conf = self.layout_to_video(imgs, objs, obj_vecs, boxes_in, test_mode=test_mode)
         return imgs_pred, boxes_pred, flows, conf, actions_data

@@ -162,7 +162,7 @@ class _RecurFn(torch.autograd.Function):
         return (d_emb, d_box0 if ctx.needs_input_grad[1] else None, d_pred, None, None, None, *grads)
 
 
-def run(models, embs, box0, preds, edges, ind):
+def run(models, embs, box0, preds, edges, ind, needs_grad=None):
     """models: list of Acts2LayoutModel sharing the graph data; embs[m] [B,O,Kx], preds[m] [B,T,E,Dp] per model;
     box0 [B,O,4], edges [B,T,E,2] int64, ind [B,T,E] bool.  Returns [(obj_vecs [B,T,O,Dout], boxes [B,T,O,4])]
     per model, or None when the kernel does not cover these sizes (the caller then walks the layers)."""
@@ -198,5 +198,8 @@ def run(models, embs, box0, preds, edges, ind):
                              edges=edges_c, ind=ind_c)
     out = []
     for i, m in enumerate(models):
-        out.append(_RecurFn.apply(embs[i], box0, preds[i], shared, i, m, *model_params(m)))
+        if needs_grad is not None and not needs_grad[i]:
+            out.append((objv[i * B:(i + 1) * B], boxes[i * B:(i + 1) * B]))        # forward only: no autograd node
+        else:
+            out.append(_RecurFn.apply(embs[i], box0, preds[i], shared, i, m, *model_params(m)))
     return out

@@ -55,6 +55,10 @@ class Trainer:
         self.optimizer_d_img = discriminator.optimizer_d_img
         self.t, self.epoch = 0, 0
         self.world = world
+        self.overlap_graph_step = bool(getattr(opt, 'overlap_graph_step', False))     # measured on B200: no gain (the 227 KB clusters need whole SMs)
+        self._side = None
+        import inspect
+        self._model_takes_flag = 'boxes_pred_grad' in inspect.signature(model.forward).parameters
         self.buckets = None
         if world > 1:
             self.buckets = {k: agdist.GradBuckets(p) for k, p in
@@ -83,12 +87,37 @@ class Trainer:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         return flag
 
+    def _graph_forward_backward(self, graph_batch):
+        model, gm = self.model, self.gans_model
+        boxes_pred = model(graph_batch.get('imgs'), graph_batch['objs'], graph_batch['triplets'], graph_batch['actions'],
+                           boxes_gt=graph_batch['boxes'], test_mode=False, graph_only=True)
+        GG = gm(graph_batch, boxes_pred, mode='compute_graph_loss')
+        self.optimizer_graph.zero_grad(set_to_none=True)
+        GG['total_loss'].backward()
+        return GG
+
     def iteration(self, batch, graph_batch):
         """batch / graph_batch: dicts with imgs, objs, boxes, triplets, actions (graph_batch needs no
-        imgs).  Returns (G_losses, D_losses, G_graph_losses) as dicts of 0-d tensors."""
+        imgs).  Returns (G_losses, D_losses, G_graph_losses) as dicts of 0-d tensors.
+
+        The graph step's forward and backward (a 15-step recurrence on 2 clips: 32 busy SMs, latency-bound) depend
+        on nothing the generator and discriminator steps produce, and neither of those writes ``acts_to_boxes``:
+        with ``overlap_graph_step`` they run on a side stream next to the generator / discriminator steps and join
+        before the graph gradients are all-reduced and ``optimizer_graph`` steps, so the arithmetic and the update
+        order (train.py:440-493) are unchanged."""
         model, gm = self.model, self.gans_model
+        kw = {'boxes_pred_grad': False} if self._model_takes_flag else {}
         out = model(batch['imgs'], batch['objs'], batch['triplets'], batch['actions'], boxes_gt=batch['boxes'],
-                    test_mode=False, use_gt=True)
+                    test_mode=False, use_gt=True, **kw)
+        GG = None
+        overlap = self.overlap_graph_step and out[0].is_cuda
+        if overlap:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=out[0].device)
+            self._side.wait_stream(main)          # after the generator forward: it built this step's weight packs
+            with torch.cuda.stream(self._side):
+                GG = self._graph_forward_backward(graph_batch)
         G = gm(batch, out, mode='compute_generator_loss')
         flag = self._nan_flag(G)
         skip_host = False
@@ -109,11 +138,10 @@ class Trainer:
             self._sync('d')
             self.optimizer_d_img.step()
 
-        boxes_pred = model(graph_batch.get('imgs'), graph_batch['objs'], graph_batch['triplets'], graph_batch['actions'],
-                           boxes_gt=graph_batch['boxes'], test_mode=False, graph_only=True)
-        GG = gm(graph_batch, boxes_pred, mode='compute_graph_loss')
-        self.optimizer_graph.zero_grad(set_to_none=True)
-        GG['total_loss'].backward()
+        if overlap:
+            torch.cuda.current_stream().wait_stream(self._side)
+        else:
+            GG = self._graph_forward_backward(graph_batch)
         self._sync('graph')
         self.optimizer_graph.step()
         self.t += 1
