@@ -53,10 +53,19 @@ def shard_clips(n_clips, rank, world, drop_last=True):
 
 
 class GradBuckets:
-    """Flat gradient buckets in reverse parameter order (the order backward fills
-    them).  ``allreduce()`` averages all gradients across ranks."""
+    """Gradient all-reduce(avg) in flat buckets, overlapped with the backward pass.
 
-    def __init__(self, params, bucket_mb=48, group=None):
+    Parameters are grouped in reverse order (the order backward produces their gradients) into buckets of
+    ``bucket_mb``.  Every bucket owns a persistent flat buffer; a post-accumulate hook on each parameter counts the
+    bucket's gradients as they appear, and the moment the last one lands the bucket is copied into its buffer (one
+    multi-tensor copy), ``p.grad`` is re-pointed at the buffer's views (same strides as the parameter, so the fused
+    optimiser reads the reduced values in place: no copy back) and an asynchronous all-reduce with the AVG reduction
+    starts (no separate divide) - while the rest of the backward keeps running.  ``allreduce()`` after the backward
+    launches whatever did not complete through the hooks (parameters without a gradient contribute zeros), then makes
+    the current stream wait for all of them.  Everything is stream-ordered, so it can be captured in a CUDA graph.
+    """
+
+    def __init__(self, params, bucket_mb=48, group=None, overlap=True):
         self.group = group
         self.params = [p for p in params if p.requires_grad]
         self.buckets = []
@@ -70,29 +79,81 @@ class GradBuckets:
         if cur:
             self.buckets.append(cur)
         self.flat = [None] * len(self.buckets)
+        self.views = [None] * len(self.buckets)
+        self._ready = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self._hooks = []
+        if overlap:
+            for i, bucket in enumerate(self.buckets):
+                for p in bucket:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _make_hook(self, i):
+        def hook(param):
+            if not self._active():
+                return
+            self._ready[i] += 1
+            if self._ready[i] == len(self.buckets[i]) and not self._launched[i]:
+                self._launch(i)
+        return hook
+
+    def _views(self, i):
+        if self.views[i] is None:
+            bucket = self.buckets[i]
+            n = sum(p.numel() for p in bucket)
+            self.flat[i] = torch.zeros(n, device=bucket[0].device, dtype=bucket[0].dtype)
+            views, off = [], 0
+            for p in bucket:
+                dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)
+                v = self.flat[i][off:off + p.numel()]
+                views.append(v.as_strided(p.shape, p.stride()) if dense else v.view(p.shape))
+                off += p.numel()
+            self.views[i] = views
+        return self.views[i]
+
+    def _launch(self, i):
+        bucket, views = self.buckets[i], self._views(i)
+        have = [(v, p.grad) for v, p in zip(views, bucket) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        missing = [v for v, p in zip(views, bucket) if p.grad is None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        if missing:
+            torch._foreach_zero_(missing)
+        for v, p in zip(views, bucket):
+            p.grad = v
+        world = dist.get_world_size(self.group)
+        if dist.get_backend(self.group) == 'nccl':
+            work = dist.all_reduce(self.flat[i], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self._works.append((work, None))
+        else:                                              # gloo (CPU tests) has no AVG
+            work = dist.all_reduce(self.flat[i], group=self.group, async_op=True)
+            self._works.append((work, (self.flat[i], float(world))))
+        self._launched[i] = True
+
+    def begin(self):
+        """Call right before the backward whose gradients this object reduces (after ``zero_grad``): forgets launches
+        triggered by someone else's backward through these parameters (their collectives are waited for first, so every
+        rank keeps issuing the same sequence)."""
+        for work, _ in self._works:
+            work.wait()
+        self._works = []
+        self._ready = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
 
     def allreduce(self):
-        if not (dist.is_available() and dist.is_initialized()):
+        if not self._active():
             return
-        world = dist.get_world_size(self.group)
-        if world == 1:
-            return
-        works = []
-        for i, bucket in enumerate(self.buckets):
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
-            n = sum(g.numel() for g in grads)
-            if self.flat[i] is None or self.flat[i].numel() != n:
-                self.flat[i] = torch.empty(n, device=grads[0].device, dtype=grads[0].dtype)
-            views, off = [], 0
-            for g in grads:
-                views.append(self.flat[i][off:off + g.numel()].view(g.shape))
-                off += g.numel()
-            torch._foreach_copy_(views, [g.contiguous() for g in grads])
-            works.append((dist.all_reduce(self.flat[i], group=self.group, async_op=True), bucket, views))
-        for work, bucket, views in works:
+        for i in range(len(self.buckets)):
+            if not self._launched[i]:
+                self._launch(i)
+        for work, post in self._works:
             work.wait()
-            for p, v in zip(bucket, views):
-                if p.grad is None:
-                    p.grad = torch.empty_like(p)
-            torch._foreach_copy_([p.grad for p in bucket], views)
-            torch._foreach_div_([p.grad for p in bucket], float(world))
+            if post is not None:
+                post[0].div_(post[1])
+        self._works = []
+        self._ready = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)

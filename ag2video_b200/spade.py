@@ -249,19 +249,24 @@ class _SpadeFn(torch.autograd.Function):
             with _Timed('k3_bn_stats', 4.0 * G * Ps * C, (r, C)):
                 L.check(lib.ag2v_bn_stats(L.ptr(x), Ps, C, G, L.ptr(part), L.ptr(sums), L.stream()))
             dist, world = _world()
+            pending = None
             if world > 1:
-                dist.all_reduce(sums, group=_sync_group['group'])
+                # SyncBN: the sums travel while the shared convolution (which does not need them) runs
+                pending = dist.all_reduce(sums, group=_sync_group['group'], async_op=True)
             count = float(Pg * world)
-            L.check(lib.ag2v_bn_finalize(L.ptr(sums), float(Ps * world), count, C, G, bn.eps, bn.momentum, None,
-                                         L.ptr(bn.running_mean), L.ptr(bn.running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
-        else:                                      # same running estimates for every group
-            L.check(lib.ag2v_bn_eval_stats(L.ptr(bn.running_mean), L.ptr(bn.running_var), C, G, bn.eps, None, L.ptr(mean),
-                                           L.ptr(rstd), L.stream()))
         _cache_of(mod).forward_begin()
         pk = mod._packed(w_sh, b_sh, w_g, b_g, w_b, b_b)
         actv = torch.empty(B, r, rw, NHIDDEN, device=dev, dtype=torch.float32)
         _conv(seg, seg_strides, B, r, rw, Lc, pk['w1'], pk['b1'], NHIDDEN, actv, (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN),
               EPI_BIAS_RELU, round_out=1)
+        if training:
+            if pending is not None:
+                pending.wait()                     # stream-level wait, the host does not block
+            L.check(lib.ag2v_bn_finalize(L.ptr(sums), float(Ps * world), count, C, G, bn.eps, bn.momentum, None,
+                                         L.ptr(bn.running_mean), L.ptr(bn.running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
+        else:                                      # same running estimates for every group
+            L.check(lib.ag2v_bn_eval_stats(L.ptr(bn.running_mean), L.ptr(bn.running_var), C, G, bn.eps, None, L.ptr(mean),
+                                           L.ptr(rstd), L.stream()))
         out = torch.empty(B, C, r, rw, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
         need_grad = any(ctx.needs_input_grad)
         gamma = torch.empty(B, r, rw, C, device=dev, dtype=torch.float32) if need_grad else None
@@ -300,16 +305,12 @@ class _SpadeFn(torch.autograd.Function):
         if next_scale is not None and ctx.needs_input_grad[13]:
             # y = conv(out) * scale_g: d scale_g = <dy_g, conv(out)_g> = <dout_g, out_g> / scale_g  (adjoint of the conv)
             dscale = (sums.view(G, 5, C)[:, 4].sum(dim=1) / next_scale.double()).float()
+        pending = None
         if training:
             dist, world = _world()
-            if world > 1:              # db (local sums) is already extracted; the BN backward needs global sums
-                dist.all_reduce(sums, group=_sync_group['group'])
-        dx_low = torch.empty_like(x, memory_format=torch.channels_last) if upsample else None
-        with _Timed('k3_spade_bwd_dx', 4.0 * P * C * (2.5 if upsample else 3), (r, C)):
-            L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
-                                          int(training), Pg, C, G, uh, uw, L.ptr(dx_low), L.stream()))
-        if upsample:
-            dx = dx_low
+            if world > 1:              # db (local sums) is already extracted; the BN backward needs global sums:
+                # they travel while the gamma / beta weight and input gradients (which do not need them) run
+                pending = dist.all_reduce(sums, group=_sync_group['group'], async_op=True)
         a_strides = (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN)
         # gamma / beta convolutions: weight gradient, then input gradient gated by the ReLU of actv
         dw_g, dw_b = _wgrad(dgb, 2 * C, actv, a_strides, NHIDDEN, B, r, rw, True, w_g, w_b)
@@ -317,6 +318,14 @@ class _SpadeFn(torch.autograd.Function):
         dactv = torch.empty(B, r, rw, NHIDDEN, device=dev, dtype=torch.float32)
         _conv(dgb, (r * rw * 2 * C, rw * 2 * C, 2 * C), B, r, rw, 2 * C, pkt['w2t'], None, NHIDDEN, dactv, a_strides,
               EPI_GATE, round_out=1, gate=actv)
+        if pending is not None:
+            pending.wait()
+        dx_low = torch.empty_like(x, memory_format=torch.channels_last) if upsample else None
+        with _Timed('k3_spade_bwd_dx', 4.0 * P * C * (2.5 if upsample else 3), (r, C)):
+            L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
+                                          int(training), Pg, C, G, uh, uw, L.ptr(dx_low), L.stream()))
+        if upsample:
+            dx = dx_low
         # shared convolution: bias / weight gradients, then the gradient w.r.t. the (strided) segmap
         part1 = torch.empty(lib.ag2v_chan_partial_floats(P, NHIDDEN, 2), device=dev, dtype=torch.float32)
         sums1 = torch.empty(2 * NHIDDEN, device=dev, dtype=torch.float64)

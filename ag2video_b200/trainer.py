@@ -77,6 +77,10 @@ class Trainer:
         if self.buckets is not None:
             self.buckets[which].allreduce()
 
+    def _begin(self, which):
+        if self.buckets is not None:
+            self.buckets[which].begin()
+
     def _nan_flag(self, G):
         terms = [G[k].detach() for k in ('GAN_Img', 'GAN_Feat') if k in G]
         if not terms:
@@ -93,6 +97,7 @@ class Trainer:
                            boxes_gt=graph_batch['boxes'], test_mode=False, graph_only=True)
         GG = gm(graph_batch, boxes_pred, mode='compute_graph_loss')
         self.optimizer_graph.zero_grad(set_to_none=True)
+        self._begin('graph')
         GG['total_loss'].backward()
         return GG
 
@@ -128,12 +133,14 @@ class Trainer:
         D = None
         if not skip_host:
             self.optimizer_generator.zero_grad(set_to_none=True)
+            self._begin('gen')
             G['total_loss'].backward()
             self._sync('gen')
             self.optimizer_generator.step()
 
             D = gm(batch, out, mode='compute_discriminator_loss')
             self.optimizer_d_img.zero_grad(set_to_none=True)
+            self._begin('d')
             D['total_img_loss'].backward()
             self._sync('d')
             self.optimizer_d_img.step()
