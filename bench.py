@@ -566,7 +566,7 @@ def run_ours(args):
     roof, roof_all = None, None
     if prof and rank == 0:
         step_ms = ms_dev / args.steps
-        tensor_kinds = ('conv3x3', 'wgrad3x3')
+        tensor_kinds = ('conv3x3', 'wgrad3x3', 'k1r_recur_wgrad')       # work given in FLOPs; everything else in bytes
         tf32_peak = tf32['tf32_tflops_sustained']
         hbm_peak = pk['hbm_gbs']
         agg, by_shape = {}, {}
