@@ -244,7 +244,7 @@ __device__ __forceinline__ int col_of(const StageDev& s, int rank, int nl) {
 
 // ---- pack kernel: parameters -> per-CTA slabs in mma.sync B-fragment order ------------------------------------------
 struct PackJob { const float* W; int ld, trans, N, K, ncta, CS, nseg, base[3], w[3]; long long off; };
-struct PackArgs { int njobs; PackJob job[2 * kMaxStages]; };
+struct PackArgs { int njobs; int mma; PackJob job[2 * kMaxStages]; };
 
 __global__ void __launch_bounds__(256) recur_pack_kernel(PackArgs a, float* __restrict__ dst) {
   // slab of CTA `rank`: [k4 = K/4][j = ncta/8][ng = 8][4]  ->  B(k = 4*k4 + i, local column nl = ng + 8*j):
@@ -255,15 +255,24 @@ __global__ void __launch_bounds__(256) recur_pack_kernel(PackArgs a, float* __re
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int rank = (int)(e / slab);
     int r = (int)(e - (long long)rank * slab);
-    const int i = r & 3; r >>= 2;
-    const int ng = r & 7; r >>= 3;
-    const int jj = r % tn, k4 = r / tn;
-    const int nl = ng + 8 * jj;
+    int nl, k;
+    if (a.mma) {       // mma.sync m16n8k8 B fragments: [k8][j][lane = 4g + t][2] -> B(k = 8*k8 + 2t + i, nl = 8j + g)
+      const int i = r & 1; r >>= 1;
+      const int lane = r & 31; r >>= 5;
+      const int jj = r % tn, k8 = r / tn;
+      nl = 8 * jj + (lane >> 2);
+      k = k8 * 8 + 2 * (lane & 3) + i;
+    } else {
+      const int i = r & 3; r >>= 2;
+      const int ng = r & 7; r >>= 3;
+      const int jj = r % tn, k4 = r / tn;
+      nl = ng + 8 * jj;
+      k = k4 * 4 + i;
+    }
     int col;
     if (nl < j.w[0]) col = j.base[0] + rank * j.w[0] + nl;
     else if (nl < j.w[0] + j.w[1]) col = j.base[1] + rank * j.w[1] + (nl - j.w[0]);
     else col = j.base[2] + rank * j.w[2] + (nl - j.w[0] - j.w[1]);
-    const int k = k4 * 4 + i;
     dst[j.off + e] = j.trans ? j.W[(size_t)k * j.ld + col] : j.W[(size_t)col * j.ld + k];
   }
 }
@@ -356,6 +365,7 @@ struct Ctx {
   uint32_t aphase, sphase[2];
   int scount;
   unsigned long long* prof;     // optional timeline of CTA 0 (tools/recur_timeline.py), else null
+  int mma;                      // product core: 0 = fp32 FFMA register tiles, 1 = 3xTF32 mma.sync fragments
 };
 
 __device__ __forceinline__ void stamp(Ctx& cx, int what) {
@@ -536,7 +546,109 @@ __device__ __noinline__ void stage_tn(Ctx& cx, const StageDev& st, const Epi& ep
   consumer_sync();
 }
 
+// The same stage on legacy tensor cores: 3xTF32 mma.sync m16n8k8 (hi/lo split, fp32-class accuracy).  A fragment
+// load feeds 8x more multiply-adds than an FFMA operand load, so this core is not bound by the shared-memory
+// pipe; the two small cross terms and the main term go to separate accumulators (no chain of three dependent MMAs).
+template <int TN>
+__device__ __noinline__ void stage_tn_mma(Ctx& cx, const StageDev& st, const Epi& ep) {
+  Smem* sm = RECUR_SMEM();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  constexpr int kElems = (kRows * TN * 8 + kConsumers - 1) / kConsumers;
+  const int ncta = TN * 8, total = kRows * ncta;
+  float pb[kElems], pe[kElems], pg[kElems];
+  int pidx[kElems];
+#pragma unroll
+  for (int q = 0; q < kElems; ++q) {
+    const int i = threadIdx.x + q * kConsumers;
+    pb[q] = 0.f; pe[q] = 0.f; pg[q] = 1.f; pidx[q] = -1;
+    if (i < total) {
+      const int m = i / ncta, nl = i - m * ncta;
+      const int n = col_of(st, cx.rank, nl);
+      if (ep.bias) pb[q] = ep.bias[n];
+      if (m < ep.rows) {
+        pidx[q] = m * ep.ld + n;
+        if (ep.ext) pe[q] = ep.ext[pidx[q]];
+        if (ep.gate) pg[q] = ep.gate[pidx[q]];
+      }
+    }
+  }
+  float acs[TN][4], ach[TN][4];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) { acs[j][0] = acs[j][1] = acs[j][2] = acs[j][3] = 0.f; ach[j][0] = ach[j][1] = ach[j][2] = ach[j][3] = 0.f; }
+  stamp(cx, 2);
+  for (int c = 0; c < st.nchunk; ++c) {
+    const int kcount = min(st.kc, st.K8 - c * st.kc);
+    const int slot = cx.pipe.slot;
+    mbar_wait(smem_u32(&sm->full[slot]), cx.pipe.phase);
+    const float* ring = sm->ring[slot];
+#pragma unroll 2
+    for (int kl = warp; kl < kcount; kl += 8) {
+      const int k0 = (c * st.kc + kl) << 3;
+      const float2 lo = *reinterpret_cast<const float2*>(sm->abuf + g * kLda + k0 + 2 * t);
+      const float2 hi = *reinterpret_cast<const float2*>(sm->abuf + (g + 8) * kLda + k0 + 2 * t);
+      uint32_t ah[4], al[4];
+      split_tf32(lo.x, ah[0], al[0]); split_tf32(hi.x, ah[1], al[1]);
+      split_tf32(lo.y, ah[2], al[2]); split_tf32(hi.y, ah[3], al[3]);
+      const float* bp = ring + ((size_t)kl * TN * 32 + lane) * 2;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const float2 b = *reinterpret_cast<const float2*>(bp + j * 64);
+        uint32_t bh[2], bl[2];
+        split_tf32(b.x, bh[0], bl[0]); split_tf32(b.y, bh[1], bl[1]);
+        mma_tf32(acs[j], al, bh);
+        mma_tf32(ach[j], ah, bh);
+        mma_tf32(acs[j], ah, bl);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&sm->empty[slot]));
+    if (++cx.pipe.slot == kRing) { cx.pipe.slot = 0; cx.pipe.phase ^= 1u; }
+  }
+  stamp(cx, 3);
+  float* red = sm->red + (size_t)warp * total;
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    *reinterpret_cast<float2*>(red + g * ncta + j * 8 + 2 * t) = make_float2(acs[j][0] + ach[j][0], acs[j][1] + ach[j][1]);
+    *reinterpret_cast<float2*>(red + (g + 8) * ncta + j * 8 + 2 * t) = make_float2(acs[j][2] + ach[j][2], acs[j][3] + ach[j][3]);
+  }
+  consumer_sync();
+#pragma unroll
+  for (int q = 0; q < kElems; ++q) {
+    const int i = threadIdx.x + q * kConsumers;
+    if (i < total) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += sm->red[(size_t)w * total + i];
+      v += pb[q];
+      v += pe[q];
+      if (ep.relu) v = fmaxf(v, 0.f);
+      v = pg[q] > 0.f ? v : 0.f;
+      if (pidx[q] >= 0) {
+        if (ep.out) ep.out[pidx[q]] = v;
+        if (ep.out2) ep.out2[pidx[q]] = v;
+      }
+      sm->tile[i] = v;
+    }
+  }
+  consumer_sync();
+}
+
 __device__ __noinline__ void run_stage(Ctx& cx, const StageDev& st, const Epi& ep) {
+  if (cx.mma) {
+    switch (st.ncta >> 3) {
+      case 1: stage_tn_mma<1>(cx, st, ep); break;
+      case 2: stage_tn_mma<2>(cx, st, ep); break;
+      case 3: stage_tn_mma<3>(cx, st, ep); break;
+      case 4: stage_tn_mma<4>(cx, st, ep); break;
+      case 5: stage_tn_mma<5>(cx, st, ep); break;
+      case 6: stage_tn_mma<6>(cx, st, ep); break;
+      case 7: stage_tn_mma<7>(cx, st, ep); break;
+      case 8: stage_tn_mma<8>(cx, st, ep); break;
+      default: stage_tn_mma<9>(cx, st, ep); break;
+    }
+    return;
+  }
   switch (st.ncta >> 3) {
     case 1: stage_tn<1>(cx, st, ep); break;
     case 2: stage_tn<2>(cx, st, ep); break;
@@ -646,6 +758,7 @@ struct FwdArgs {
   const float *emb, *box0, *pred; const long long* edges; const unsigned char* ind;
   float *objv, *boxes, *saved;
   unsigned long long* prof;
+  int mma;
 };
 
 // per-CTA partial sums of a 4-wide product, exchanged through global memory and added in rank order
@@ -665,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_fwd_kernel(const __grid_con
   const int steps = d.T - 1;
   if (threadIdx.x >= kConsumers) { producer_loop(model, a.tab, rank, steps, true); return; }
 
-  Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, (blockIdx.x == 0) ? a.prof : nullptr};
+  Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, (blockIdx.x == 0) ? a.prof : nullptr, a.mma};
   const Saved sv = saved_layout(d, a.NC);
   const int O = d.O, E = d.E, H = d.H, De = d.De, N2 = d.N2(), Dout = d.Dout;
   for (int i = threadIdx.x; i < O * 4; i += kConsumers) sm->box[i] = a.box0[(size_t)clip * O * 4 + i];
@@ -818,6 +931,7 @@ struct BwdArgs {
   float* z;                                   // Z buffer (z_layout)
   float *d_emb, *d_box0, *d_pred;             // [nc][O][Kx], [nc][O][4], [nc][T][E][Dp]
   float *dw0box, *dwb2, *dbb2;                // per-chain partial sums [nc][De][4], [nc][4][H], [nc][4]
+  int mma;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) recur_bwd_kernel(const __grid_constant__ BwdArgs a) {
@@ -829,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_bwd_kernel(const __grid_con
   const int steps = d.T - 1;
   if (threadIdx.x >= kConsumers) { producer_loop(model, a.tab, rank, steps, false); return; }
 
-  Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, nullptr};
+  Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, nullptr, a.mma};
   const Saved sv = saved_layout(d, a.NC);
   const Zbuf zz = z_layout(d, a.NC);
   const int O = d.O, E = d.E, H = d.H, De = d.De, N2 = d.N2(), Dout = d.Dout, Dpo = d.Dpo;
@@ -1119,6 +1233,12 @@ __global__ void __launch_bounds__(256) recur_bgrad_kernel(const __grid_constant_
 using namespace ag2v;
 using namespace ag2v::recur;
 
+static int g_recur_core = 0;
+// Product core of the recurrence kernels: 0 = fp32 FFMA register tiles (default), 1 = 3xTF32 mma.sync.  Process-wide;
+// the packed weights are laid out for the core that is active when ag2v_recur_pack runs, so switch before packing.
+extern "C" int ag2v_recur_set_core(int core) { g_recur_core = core ? 1 : 0; return 0; }
+extern "C" int ag2v_recur_get_core(void) { return g_recur_core; }
+
 static_assert(sizeof(Smem) <= 227 * 1024, "recurrence kernel: shared-memory image exceeds 227 KB");
 
 static int dims_check(const Dims& d) {
@@ -1185,6 +1305,7 @@ extern "C" int ag2v_recur_pack(int O, int E, int T, int Kx, int De, int Dp, int 
   AG2V_REQUIRE(plan_ok(p), "recur_pack: cluster size %d does not fit these widths", CS);
   PackArgs pa;
   pa.njobs = 0;
+  pa.mma = g_recur_core;
   auto push = [&](const Stage& s) {
     PackJob& j = pa.job[pa.njobs++];
     j.W = params[s.src]; j.ld = s.ld; j.trans = s.trans; j.N = s.N; j.K = s.K; j.ncta = s.ncta; j.CS = CS; j.nseg = s.nseg; j.off = s.off;
@@ -1283,6 +1404,7 @@ extern "C" int ag2v_recur_fwd(int O, int E, int T, int Kx, int De, int Dp, int H
   for (int i = 0; i < n_models; ++i) AG2V_REQUIRE(a.model[i], "recur_fwd: packed model %d is null", i);
   a.emb = emb; a.box0 = box0; a.pred = pred; a.edges = edges; a.ind = ind; a.objv = objv; a.boxes = boxes; a.saved = saved;
   a.prof = g_recur_prof;
+  a.mma = g_recur_core;
   return launch_cluster(recur_fwd_kernel, a, NC, CS, stream);
 }
 
@@ -1308,6 +1430,7 @@ extern "C" int ag2v_recur_bwd(int O, int E, int T, int Kx, int De, int Dp, int H
   a.d = d; a.tab = to_table(p.b, p.nb); a.small = p.sm; a.NC = NC; a.chain0 = chain0; a.model = pack;
   a.saved = saved; a.boxes = boxes; a.d_objv = d_objv; a.d_boxes = d_boxes; a.edges = edges; a.ind = ind; a.z = z;
   a.d_emb = d_emb; a.d_box0 = d_box0; a.d_pred = d_pred; a.dw0box = dw0box; a.dwb2 = dwb2; a.dbb2 = dbb2;
+  a.mma = g_recur_core;
   return launch_cluster(recur_bwd_kernel, a, nchains, CS, stream);
 }
 

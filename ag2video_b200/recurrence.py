@@ -25,6 +25,8 @@ L.register('ag2v_recur_cluster_fits', c_i, _D10 + [c_i])
 L.register('ag2v_recur_max_active_clusters', c_i, [c_i])
 L.register('ag2v_recur_num_params', c_i, [c_i])
 L.register('ag2v_recur_set_profile', c_i, [c_p])
+L.register('ag2v_recur_set_core', c_i, [c_i])
+L.register('ag2v_recur_get_core', c_i, [])
 L.register('ag2v_recur_pack_floats', c_sz, _D10 + [c_i])
 L.register('ag2v_recur_saved_floats', c_sz, _D10 + [c_i])
 L.register('ag2v_recur_z_floats', c_sz, _D10 + [c_i])
@@ -98,7 +100,7 @@ def _packed(module, dims, cs):
         return pack
     cache = _cache_of(module)
     cache.forward_begin()
-    return cache.get('recur%d' % cs, params, build)
+    return cache.get('recur%d.%d' % (cs, L.lib().ag2v_recur_get_core()), params, build)
 
 
 def recur_bytes(dims, nc):

@@ -67,6 +67,8 @@ int ag2v_recur_cluster_size(int O, int E, int T, int Kx, int De, int Dp, int H, 
 int ag2v_recur_cluster_fits(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int CS);
 int ag2v_recur_max_active_clusters(int CS);
 int ag2v_recur_num_params(int NL);
+int ag2v_recur_set_core(int core);      /* 0 = fp32 FFMA register tiles (default), 1 = 3xTF32 mma.sync; set before ag2v_recur_pack */
+int ag2v_recur_get_core(void);
 int ag2v_recur_set_profile(unsigned long long* buf);   /* debug timeline of CTA 0, see k1r_recur.cu */
 size_t ag2v_recur_pack_floats(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int CS);
 size_t ag2v_recur_saved_floats(int O, int E, int T, int Kx, int De, int Dp, int H, int Dout, int Dpo, int NL, int NC);

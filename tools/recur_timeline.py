@@ -13,6 +13,8 @@ from ag2video_b200.networks import Acts2LayoutModel  # noqa: E402
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+if len(sys.argv) > 3:
+    L.lib().ag2v_recur_set_core(int(sys.argv[3]))
 m = Acts2LayoutModel(make_opt(64)).cuda()
 b = {k: v.cuda() for k, v in synthetic_batch(B=B, F=T, image_size=8, seed=1, with_images=False, pad_to=(11, 6)).items() if v is not None}
 for _ in range(3):
