@@ -366,6 +366,7 @@ struct Ctx {
   int scount;
   unsigned long long* prof;     // optional timeline of CTA 0 (tools/recur_timeline.py), else null
   int mma;                      // product core: 0 = fp32 FFMA register tiles, 1 = 3xTF32 mma.sync fragments
+  int a_pending;                // an operand load is in flight: the stage waits for it after its epilogue prefetch
 };
 
 __device__ __forceinline__ void stamp(Ctx& cx, int what) {
@@ -416,20 +417,19 @@ __device__ __forceinline__ void a_wait(Ctx& cx) {
   cx.aphase ^= 1u;
 }
 __device__ __noinline__ void load_rows(Ctx& cx, const float* src, int ld, int M, int K) {
+  // issue only: the consumer of the operand (run_stage, or a caller that edits it in place) calls a_finish()
   stamp(cx, 1);
   if (threadIdx.x < 32) {
     a_begin(cx, (uint32_t)(M * K) * 4u);
     for (int m = threadIdx.x; m < M; m += 32)
       bulk_g2s(smem_u32(RECUR_SMEM()->abuf + m * kLda), src + (size_t)m * ld, (uint32_t)K * 4u, smem_u32(&RECUR_SMEM()->abar));
   }
-  a_wait(cx);
+  cx.a_pending = 1;
+}
+__device__ __forceinline__ void a_finish(Ctx& cx) {
+  if (cx.a_pending) { a_wait(cx); cx.a_pending = 0; }
 }
 
-// one GEMM stage for the consumers: tile[m][nl] = f(m, nl, sum_k abuf[m][k] * B(k, col(nl)))
-// fp32 FFMA register tiles (exact fp32 products; legacy mma.sync has ~400 cycles of dependent-issue latency on
-// sm_100, measured with tools/recur_timeline.py, which a 16-row problem cannot hide): a warp owns one k-slice
-// (k4 = warp, warp + 8, ...), a lane owns rows {mg, mg+4, mg+8, mg+12} x columns {ng + 8j}; operands come as
-// LDS.128 along k (A: 4 rows, conflict-free with the row stride kLda = 8 mod 32; B: packed, 128 B per (k4, j)).
 // Epilogue of a stage, applied to every element of the CTA's [16 x ncta] tile after the 8 k-slices are summed:
 //   v = sum (+ bias[n]) (+ sum_j box[m][j] * w4[n][j]) (+ ext[m*ld+n]);  relu;  gate[m*ld+n] > 0 ? v : 0;
 //   rows m < rows are stored to out / out2 (global, leading dimension ld); the tile keeps v for CTA-local post phases.
@@ -486,6 +486,7 @@ __device__ __noinline__ void stage_tn(Ctx& cx, const StageDev& st, const Epi& ep
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  a_finish(cx);
   stamp(cx, 2);
   const float* arow = sm->abuf + mg * kLda;
   for (int c = 0; c < st.nchunk; ++c) {
@@ -576,6 +577,7 @@ __device__ __noinline__ void stage_tn_mma(Ctx& cx, const StageDev& st, const Epi
   float acs[TN][4], ach[TN][4];
 #pragma unroll
   for (int j = 0; j < TN; ++j) { acs[j][0] = acs[j][1] = acs[j][2] = acs[j][3] = 0.f; ach[j][0] = ach[j][1] = ach[j][2] = ach[j][3] = 0.f; }
+  a_finish(cx);
   stamp(cx, 2);
   for (int c = 0; c < st.nchunk; ++c) {
     const int kcount = min(st.kc, st.K8 - c * st.kc);
@@ -778,7 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_fwd_kernel(const __grid_con
   const int steps = d.T - 1;
   if (threadIdx.x >= kConsumers) { producer_loop(model, a.tab, rank, steps, true); return; }
 
-  Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, (blockIdx.x == 0) ? a.prof : nullptr, a.mma};
+  Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, (blockIdx.x == 0) ? a.prof : nullptr, a.mma, 0};
   const Saved sv = saved_layout(d, a.NC);
   const int O = d.O, E = d.E, H = d.H, De = d.De, N2 = d.N2(), Dout = d.Dout;
   for (int i = threadIdx.x; i < O * 4; i += kConsumers) sm->box[i] = a.box0[(size_t)clip * O * 4 + i];
@@ -807,6 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_fwd_kernel(const __grid_con
     {  // u0 = relu(P + box W0[:, Kx:]^T) (model.py:136-137): 4 FMAs per element, every CTA builds the whole operand
        // for itself and keeps its own columns for the backward
       load_rows(cx, p0, De, O, De);
+      a_finish(cx);
       const float* wbox = model + a.small.w0box;
       float* u0 = a.saved + sv.u0 + ct * O * De;
       for (int i = threadIdx.x; i < O * De; i += kConsumers) {
@@ -943,7 +946,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_bwd_kernel(const __grid_con
   const int steps = d.T - 1;
   if (threadIdx.x >= kConsumers) { producer_loop(model, a.tab, rank, steps, false); return; }
 
-  Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, nullptr, a.mma};
+  Ctx cx{sm, model, rank, CS, {0, 0u}, 0u, {0u, 0u}, 0, nullptr, a.mma, 0};
   const Saved sv = saved_layout(d, a.NC);
   const Zbuf zz = z_layout(d, a.NC);
   const int O = d.O, E = d.E, H = d.H, De = d.De, N2 = d.N2(), Dout = d.Dout, Dpo = d.Dpo;
@@ -967,6 +970,7 @@ __global__ void __launch_bounds__(kThreads, 1) recur_bwd_kernel(const __grid_con
     int s = 0;
     {  // box_net[2]^T for every CTA: zb1 = (gB Wb2) * [hb > 0], built in place of hb; d Wb2 columns owned by this CTA
       load_rows(cx, a.saved + sv.hb + ct * O * H, H, O, H);
+      a_finish(cx);
       const float* wb2 = model + a.small.wb2;
       for (int i = threadIdx.x; i < 4 * wH; i += kConsumers) {      // acc1[j][c] += sum_m gB[m][j] * hb[m][rank*wH + c]
         const int j = i / wH, c = i - j * wH;

@@ -10,6 +10,8 @@ int conv3x3_check(const ConvParams& p, int epi);
 int conv3x3_mma(const ConvParams& p, int epi, int round_out, int precise, cudaStream_t stream);
 int conv3x3_tc(const ConvParams& p, int epi, int round_out, cudaStream_t stream);   // may return AG2V_ERR_UNSUPPORTED
 bool conv3x3_tc_supported(const ConvParams& p, int epi);
+bool conv3x3_tc_stat_geometry(const ConvParams& p, int groups, int* mtiles, int* tiles_per_group);
+int conv_stats_reduce(const float* part, int tiles_per_group, int Nout, int groups, double* sums, cudaStream_t stream);
 }  // namespace ag2v
 
 using namespace ag2v;
@@ -59,4 +61,42 @@ extern "C" int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nou
   ConvParams p{};
   p.B = B; p.Hh = Hh; p.Ww = Ww; p.Cin = Cin; p.Nout = Nout; p.C = Nout / 2;
   return conv3x3_tc_supported(p, epilogue) ? 1 : 0;
+}
+
+// ---- BN statistics fused into the producing convolution's epilogue (north_star; normalization.py:99 consumes them) ----
+// 1 if y = conv3x3(x) * scale + bias (+ res) on a dense NHWC [B,Hh,Ww,*] pair can also emit the per-channel sums of y per
+// statistics group (B / groups consecutive images): tcgen05 kernel, no split-K, tiles not straddling groups.
+// mtiles / tiles_per_group size the scratch: stat_part = mtiles * 2 * Nout floats.
+extern "C" int ag2v_conv3x3_stats_info(int B, int Hh, int Ww, int Cin, int Nout, int groups, int* mtiles, int* tiles_per_group) {
+  ConvParams p{};
+  p.B = B; p.Hh = Hh; p.Ww = Ww; p.Cin = Cin; p.Nout = Nout;
+  int mt = 0, tpg = 0;
+  if (!conv3x3_tc_supported(p, EPI_BIAS) || ag2v_conv3x3_splitk_floats(B, Hh, Ww, Cin, Nout) != 0 ||
+      !conv3x3_tc_stat_geometry(p, groups, &mt, &tpg))
+    return 0;
+  if (mtiles) *mtiles = mt;
+  if (tiles_per_group) *tiles_per_group = tpg;
+  return 1;
+}
+
+// The EPI_BIAS convolution of ag2v_conv3x3 (dense NHWC input and output) that also writes stat_part; then
+// sums[g][0][c] = sum y, sums[g][1][c] = sum y^2 over group g in double (the layout ag2v_bn_finalize reads).
+extern "C" int ag2v_conv3x3_bias_stats(const float* in, int B, int Hh, int Ww, int Cin, const float* wpk, const float* bias,
+                                       int Nout, float* out, int round_out, long long group_pixels, const float* scale,
+                                       const float* res, int groups, float* stat_part, double* sums, cudaStream_t stream) {
+  ConvParams p{};
+  p.in = in; p.in_sb = (long long)Hh * Ww * Cin; p.in_sy = (long long)Ww * Cin; p.in_sx = Cin;
+  p.B = B; p.Hh = Hh; p.Ww = Ww; p.Cin = Cin; p.wpk = wpk; p.bias = bias; p.Nout = Nout;
+  p.out = out; p.out_sb = (long long)Hh * Ww * Nout; p.out_sy = (long long)Ww * Nout; p.out_sx = Nout;
+  p.slope = 1.f; p.group_pixels = group_pixels; p.scale = scale; p.res = res;
+  p.stat_part = stat_part;
+  AG2V_REQUIRE(stat_part && sums, "conv3x3_bias_stats: null statistics buffers");
+  int rc = conv3x3_check(p, EPI_BIAS);
+  if (rc) return rc;
+  int mt = 0, tpg = 0;
+  if (!ag2v_conv3x3_stats_info(B, Hh, Ww, Cin, Nout, groups, &mt, &tpg))
+    return fail(AG2V_ERR_UNSUPPORTED, "conv3x3_bias_stats: shape %dx%dx%d %d->%d (groups %d) has no fused statistics", B, Hh, Ww, Cin, Nout, groups);
+  rc = conv3x3_tc(p, EPI_BIAS, round_out, stream);
+  if (rc) return rc;
+  return conv_stats_reduce(stat_part, tpg, Nout, groups, sums, stream);
 }

@@ -43,6 +43,9 @@ struct ConvParams {
   const float* gate;
   // split-K workspace (caller-provided, may be null): ksplit * P * Nout floats
   float* splitk_ws; size_t splitk_ws_floats;
+  // EPI_BIAS, tcgen05 kernel, no split-K: per-M-tile column sums of the OUTPUT for the batch norm that consumes it
+  // (normalization.py:99): stat_part[mtile][0][n] = sum over the tile's pixels of out[p, n], [mtile][1][n] = sum of squares
+  float* stat_part;
 };
 
 __host__ __device__ inline int gb8_col(int c, int is_beta) { return 16 * (c >> 3) + 8 * is_beta + (c & 7); }

@@ -42,7 +42,8 @@ struct TcCfg {
   static constexpr int kAccStages = 2;
   static constexpr int kAccCols = MT * BN;
   static constexpr int kTmemCols = kAccStages * kAccCols;      // 256 or 512
-  static constexpr int kBytes = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStatBytes = 4 * 2 * BN * 4;             // [epilogue warp][sum | sum of squares][BN] staging of the fused BN statistics
+  static constexpr int kBytes = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -133,6 +134,24 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, float (&v)[3
     for (int j = 0; j < 32; j += 4)
       if (j < ncols) *reinterpret_cast<float4*>(orow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   }
+}
+
+// Column sums over the 32 lanes of a warp for 32 columns at once (lane j ends up with the sum of column j): a
+// butterfly in which every round halves the columns a lane still carries - 31 shuffles instead of 32 x 5.
+template <int STEP>
+__device__ __forceinline__ void col_sum_round(float (&v)[32], int lane) {
+  const bool up = (lane & STEP) != 0;
+#pragma unroll
+  for (int i = 0; i < STEP; ++i) {
+    const float lo = v[i], hi = v[i + STEP];
+    const float send = up ? lo : hi, keep = up ? hi : lo;
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, STEP);
+  }
+}
+__device__ __forceinline__ float col_sum32(float (&v)[32], int lane) {
+  col_sum_round<16>(v, lane); col_sum_round<8>(v, lane); col_sum_round<4>(v, lane);
+  col_sum_round<2>(v, lane); col_sum_round<1>(v, lane);
+  return v[0];
 }
 
 // work item w -> (column tile, first M tile); column tile fastest so that CTAs running side by
@@ -233,6 +252,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else {
     // ---- epilogue: warps 2..5, TMEM lane quarter = warp % 4 --------------------
     const int q = warp & 3;
+    float* stat_s = reinterpret_cast<float*>(tc_smem_raw + (bars - raw) + 256);    // [4][2][BN]
+    const bool stats = (EPI == EPI_BIAS) && p.stat_part != nullptr;
     const int m = q * 32 + lane;                                       // accumulator row = pixel within the tile
     const int xt = m % gm.Wt, yt = (m / gm.Wt) % gm.Ht, bt = m / (gm.Wt * gm.Ht);
     uint32_t a_it = 0;
@@ -274,6 +295,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               epilogue_chunk<EPI, ROUND_OUT>(p, v, n, pp, xpix, orow);
             }
           }
+          if (EPI == EPI_BIAS && stats) {
+            // BN statistics of what was just stored (v holds the final values): per-column sums over this warp's
+            // 32 pixels by warp shuffles, staged per warp; pixels / columns outside the problem contribute zero
+            float w2[32];
+            const int ncols = n < p.Nout ? min(32, p.Nout - n) : 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (!valid || j >= ncols) v[j] = 0.f;
+              w2[j] = v[j] * v[j];
+            }
+            const float s1 = col_sum32(v, lane), s2 = col_sum32(w2, lane);
+            stat_s[(q * 2 + 0) * BN + ch * 32 + lane] = s1;
+            stat_s[(q * 2 + 1) * BN + ch * 32 + lane] = s2;
+          }
+        }
+        if (EPI == EPI_BIAS && stats) {
+          // the four epilogue warps (128 threads, named barrier 2) combine their quarters in warp order
+          asm volatile("bar.sync 2, 128;\n" ::: "memory");
+          const int et = threadIdx.x - 64;
+          for (int i = et; i < 2 * BN; i += 128) {
+            const int which = i / BN, col = i - which * BN;
+            if (n0 + col < p.Nout && mt0 + mt < gm.mtiles) {
+              const float s = ((stat_s[(0 * 2 + which) * BN + col] + stat_s[(1 * 2 + which) * BN + col]) +
+                               stat_s[(2 * 2 + which) * BN + col]) + stat_s[(3 * 2 + which) * BN + col];
+              p.stat_part[((size_t)(mt0 + mt) * 2 + which) * p.Nout + n0 + col] = s;
+            }
+          }
+          asm volatile("bar.sync 2, 128;\n" ::: "memory");
         }
       }
     }
@@ -355,6 +404,50 @@ bool conv3x3_tc_supported(const ConvParams& p, int epi) {
   if (p.in_sx % 4 || p.in_sy % 4 || p.in_sb % 4) return false;
   if (p.out_sx % 4 || p.out_sy % 4 || p.out_sb % 4) return false;
   return tma_encode_fn() != nullptr;
+}
+
+// Geometry of the fused BN statistics: M tiles of the launch and how many consecutive tiles make up one statistics
+// group (a group = B / groups consecutive images); false when a tile would straddle two groups.
+bool conv3x3_tc_stat_geometry(const ConvParams& p, int groups, int* mtiles, int* tiles_per_group) {
+  TcGeom g;
+  if (groups < 1 || p.B % groups || !tc_geometry(p, &g)) return false;
+  const int Bg = p.B / groups;
+  if (Bg % g.Bt) return false;
+  *mtiles = g.mtiles;
+  *tiles_per_group = (Bg / g.Bt) * g.tiles_y * g.tiles_x;
+  return true;
+}
+
+// sums[g][0][c] = sum over the group's tiles of part[tile][0][c] (and [1] = squares), in double, fixed order:
+// warp w of a block adds tiles w, w + 8, ... for 32 channels, the 8 warps are combined in warp order.
+__global__ void __launch_bounds__(256) conv_stats_reduce_kernel(const float* __restrict__ part, int tiles_per_group, int Nout,
+                                                                double* __restrict__ sums) {
+  __shared__ double red[8][2][32];
+  const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < Nout) {
+    for (int t = warp; t < tiles_per_group; t += 8) {
+      const float* src = part + ((size_t)(g * tiles_per_group + t) * 2) * Nout + c;
+      s1 += (double)src[0];
+      s2 += (double)src[Nout];
+    }
+  }
+  red[warp][0][lane] = s1; red[warp][1][lane] = s2;
+  __syncthreads();
+  if (warp == 0 && c < Nout) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += red[w][0][lane]; b += red[w][1][lane]; }
+    sums[((size_t)g * 2 + 0) * Nout + c] = a;
+    sums[((size_t)g * 2 + 1) * Nout + c] = b;
+  }
+}
+
+int conv_stats_reduce(const float* part, int tiles_per_group, int Nout, int groups, double* sums, cudaStream_t stream) {
+  conv_stats_reduce_kernel<<<dim3(ceil_div(Nout, 32), groups), 256, 0, stream>>>(part, tiles_per_group, Nout, sums);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
 }
 
 // Split the reduction (9 taps x Cin/32 chunks) over CTAs when the output tiles alone cannot fill

@@ -47,9 +47,12 @@ L.register('ag2v_conv3x3', c_i, [c_p, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p,
                                  c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_i, c_ll, c_i, c_p, c_p, c_p, c_p, c_sz, c_i, c_p])
 L.register('ag2v_conv3x3_splitk_floats', c_sz, [c_i] * 5)
 L.register('ag2v_conv3x3_tc_supported', c_i, [c_i] * 6)
+L.register('ag2v_conv3x3_stats_info', c_i, [c_i] * 6 + [c_p, c_p])
+L.register('ag2v_conv3x3_bias_stats', c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_ll, c_p, c_p, c_i, c_p, c_p, c_p])
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_SPADE, EPI_GATE, EPI_ACCUM = 0, 1, 2, 3, 4
 NHIDDEN = 128                      # "Yes, hardcoded" (normalization.py:84)
+FUSE_STATS = True                  # BN statistics of a block convolution's output come out of its epilogue (tests flip this)
 CONV_IMPL = 0                      # 0 auto, 1 mma.sync, 2 tcgen05, 3 mma.sync 3xTF32 (validation; tests flip this)
 
 
@@ -216,7 +219,7 @@ class _SegNearestFn(torch.autograd.Function):
 class _SpadeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, seg, token, w_sh, b_sh, w_g, b_g, w_b, b_b, mod, shared, slope, groups=1, next_scale=None,
-                round_out=False, upsample=False):
+                round_out=False, upsample=False, pre_sums=None):
         L.need_cuda(x, seg, w_sh)
         lib = L.lib()
         dev = x.device
@@ -244,11 +247,16 @@ class _SpadeFn(torch.autograd.Function):
         count = float(Pg)
         if training:
             Ps = Pg // 4 if upsample else Pg       # statistics of up(x) are those of x (every element appears 4 times)
-            part = torch.empty(G * lib.ag2v_chan_partial_floats(Ps, C, 2), device=dev, dtype=torch.float32)
-            sums = torch.empty(G * 2 * C, device=dev, dtype=torch.float64)
-            with _Timed('k3_bn_stats', 4.0 * G * Ps * C, (r, C)):
-                L.check(lib.ag2v_bn_stats(L.ptr(x), Ps, C, G, L.ptr(part), L.ptr(sums), L.stream()))
             dist, world = _world()
+            if pre_sums is not None and pre_sums.numel() == G * 2 * C:
+                # the convolution that produced x left its per-group sums behind (fused into its epilogue); the
+                # all-reduce below works in place and two layers may normalise the same x, so take a private copy
+                sums = pre_sums.clone() if world > 1 else pre_sums
+            else:
+                part = torch.empty(G * lib.ag2v_chan_partial_floats(Ps, C, 2), device=dev, dtype=torch.float32)
+                sums = torch.empty(G * 2 * C, device=dev, dtype=torch.float64)
+                with _Timed('k3_bn_stats', 4.0 * G * Ps * C, (r, C)):
+                    L.check(lib.ag2v_bn_stats(L.ptr(x), Ps, C, G, L.ptr(part), L.ptr(sums), L.stream()))
             pending = None
             if world > 1:
                 # SyncBN: the sums travel while the shared convolution (which does not need them) runs
@@ -342,7 +350,7 @@ class _SpadeFn(torch.autograd.Function):
                 dseg = buf
             _conv(dactv, a_strides, B, r, rw, NHIDDEN, pkt['w1t'], None, Lc, buf, seg_strides, EPI_ACCUM)
         dtoken = torch.zeros(1, device=dev) if (shared is not None and ctx.needs_input_grad[2]) else None
-        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None, dscale, None, None
+        return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None, dscale, None, None, None
 
 
 _PACK_EPOCH = [0]
@@ -408,7 +416,7 @@ class _SnConvFn(torch.autograd.Function):
     from the SPADE layer that produced ``x`` (SPADE.forward(next_scale=...)), not from here."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, scale, res, conv, groups):
+    def forward(ctx, x, weight, bias, scale, res, conv, groups, want_stats=False):
         L.need_cuda(x, weight)
         dev = x.device
         B, Cin, r, rw = x.shape
@@ -421,15 +429,31 @@ class _SnConvFn(torch.autograd.Function):
         Pg = B * r * rw // groups
         _cache_of(conv).forward_begin()
         wpk = _packed_cl(conv, weight, False)
-        _conv(x, (r * rw * Cin, rw * Cin, Cin), B, r, rw, Cin, wpk, bias, Nout, out, (r * rw * Nout, rw * Nout, Nout), EPI_BIAS,
-              group_pixels=Pg if groups > 1 else 0, scale=scale, res=res)
+        sums = None
+        lib = L.lib()
+        mt, tpg = L.ctypes.c_int(0), L.ctypes.c_int(0)
+        if (want_stats and FUSE_STATS and CONV_IMPL in (0, 2)
+                and lib.ag2v_conv3x3_stats_info(B, r, rw, Cin, Nout, groups, L.ctypes.byref(mt), L.ctypes.byref(tpg))):
+            # the batch norm that consumes this output gets its sums from the epilogue: no extra pass over the tensor
+            part = torch.empty(mt.value * 2 * Nout, device=dev, dtype=torch.float32)
+            sums = torch.empty(groups * 2 * Nout, device=dev, dtype=torch.float64)
+            with _Timed('conv3x3', 2.0 * 9 * B * r * rw * Cin * Nout, ('epi0+stats', r, Cin, Nout)):
+                L.check(lib.ag2v_conv3x3_bias_stats(L.ptr(x), B, r, rw, Cin, L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), 0,
+                                                    Pg if groups > 1 else 0, L.ptr(scale), L.ptr(res), groups, L.ptr(part),
+                                                    L.ptr(sums), L.stream()))
+        else:
+            _conv(x, (r * rw * Cin, rw * Cin, Cin), B, r, rw, Cin, wpk, bias, Nout, out, (r * rw * Nout, rw * Nout, Nout), EPI_BIAS,
+                  group_pixels=Pg if groups > 1 else 0, scale=scale, res=res)
         ctx.save_for_backward(x, weight, scale)
         ctx.meta = (B, Cin, r, rw, Nout, groups, bias is not None, res is not None)
         ctx.conv = conv
-        return out
+        if sums is None:
+            return out, None
+        ctx.mark_non_differentiable(sums)
+        return out, sums
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dsums=None):
         x, weight, scale = ctx.saved_tensors
         B, Cin, r, rw, Nout, G, has_bias, has_res = ctx.meta
         _cache_of(ctx.conv).backward_seen()
@@ -458,21 +482,25 @@ class _SnConvFn(torch.autograd.Function):
                                       CONV_IMPL, L.stream()))
         dw = torch.empty_like(weight, memory_format=torch.channels_last)
         L.check(lib.ag2v_unpack_dw3x3_cl(L.ptr(wpart), nsplit, Nout, Cin, 0, L.ptr(dw), None, L.stream()))
-        return dx, dw, dbias, None, (dy if has_res else None), None, None
+        return dx, dw, dbias, None, (dy if has_res else None), None, None, None
 
 
-def sn_conv3x3(conv, x, groups=1, res=None):
+def sn_conv3x3(conv, x, groups=1, res=None, stats=True):
     """``conv(x) (+ res)`` for a spectrally normalised 3x3 nn.Conv2d in sigma mode on the tcgen05
     implicit-GEMM kernel; ``x`` must come from ``SPADE.forward(..., next_scale=scale, round_out=True)``."""
     entry = conv.__dict__['_ag2v_sn_entry']
-    return _SnConvFn.apply(x, getattr(conv, entry.name + '_orig'), conv.bias, entry.scale_g, res, conv, int(groups))
+    y, sums = _SnConvFn.apply(x, getattr(conv, entry.name + '_orig'), conv.bias, entry.scale_g, res, conv, int(groups),
+                              bool(stats and conv.training))
+    if sums is not None:
+        y._ag2v_stats = (sums, int(groups))       # per-group [sum | sum of squares] of y, read by the SPADE that normalises y
+    return y
 
 
 def plain_conv3x3(conv, x):
     """``conv(x)`` for a plain (not spectrally normalised) 3x3 / stride 1 / padding 1 ``nn.Conv2d`` with channels_last
     weights on the tcgen05 implicit-GEMM kernel, forward, input and weight gradient - the generator's ``fc``
     (spade_generator.py:16,56).  ``x``: float32 channels_last, already rounded to TF32 (e.g. ``SharedSeg.nearest``)."""
-    return _SnConvFn.apply(x, conv.weight, conv.bias, None, None, conv, 1)
+    return _SnConvFn.apply(x, conv.weight, conv.bias, None, None, conv, 1, False)[0]
 
 
 def plain_conv3x3_usable(conv, x):
@@ -635,9 +663,12 @@ class SPADE(nn.Module):
         shared = segmap if isinstance(segmap, SharedSeg) else None
         seg = shared.seg if shared is not None else segmap
         token = shared.token if shared is not None else None
+        pre = getattr(x, '_ag2v_stats', None)          # left by sn_conv3x3 on its output: (sums, groups)
+        pre_sums = pre[0] if (pre is not None and pre[1] == int(groups) and self.training) else None
         return _SpadeFn.apply(x, seg, token, self.mlp_shared[0].weight, self.mlp_shared[0].bias,
                               self.mlp_gamma.weight, self.mlp_gamma.bias, self.mlp_beta.weight, self.mlp_beta.bias,
-                              self, shared, float(self.fused_slope), int(groups), next_scale, bool(round_out), bool(upsample))
+                              self, shared, float(self.fused_slope), int(groups), next_scale, bool(round_out), bool(upsample),
+                              pre_sums)
 
 
 class SPADEResnetBlock(nn.Module):

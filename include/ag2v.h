@@ -288,6 +288,13 @@ int ag2v_conv3x3(const float* in, long long in_sb, long long in_sy, long long in
 /* split-K scratch (floats) that lets low-resolution layers use the whole chip; 0 = none needed */
 size_t ag2v_conv3x3_splitk_floats(int B, int Hh, int Ww, int Cin, int Nout);
 int ag2v_conv3x3_tc_supported(int B, int Hh, int Ww, int Cin, int Nout, int epilogue);
+/* BN statistics fused into the producing convolution's epilogue (the SPADE / batch norm that consumes y needs
+ * sum y and sum y^2 per channel and statistics group, normalization.py:99): warp-shuffle column sums per M tile in the
+ * tcgen05 epilogue + a fixed-order reduction over tiles.  stat_part: mtiles * 2 * Nout floats of scratch. */
+int ag2v_conv3x3_stats_info(int B, int Hh, int Ww, int Cin, int Nout, int groups, int* mtiles, int* tiles_per_group);
+int ag2v_conv3x3_bias_stats(const float* in, int B, int Hh, int Ww, int Cin, const float* wpk, const float* bias,
+                            int Nout, float* out, int round_out, long long group_pixels, const float* scale,
+                            const float* res, int groups, float* stat_part, double* sums, ag2v_stream_t stream);
 
 /* SPADE backward, element-wise: pass 1 produces d(gamma|beta) [P,2C], dxhat and the
  * per-channel sums [groups][5][C] (sum g, sum g*xhat, sum dxhat, sum dxhat*xhat, sum dout*out);

@@ -184,3 +184,46 @@ def test_plain_conv3x3_fc_shape_forward_and_gradients_tol1e3():
     errs = {n: max_rel(a, b) for n, a, b in zip(('y', 'dx', 'dw', 'db'), got, want)}
     print('plain_conv3x3 512->1024 @8x8: ' + ' '.join('%s %.1e' % kv for kv in errs.items()))
     assert max(errs.values()) <= TOL, errs
+
+
+@pytest.mark.parametrize('B,r,Cin,Nout,groups,with_res', [(6, 256, 64, 64, 3, True), (6, 128, 128, 256, 3, False),
+                                                         (6, 64, 256, 256, 3, True), (2, 256, 128, 64, 1, False),
+                                                         (4, 32, 512, 512, 2, True)])
+def test_conv_epilogue_bn_statistics_tol1e5(B, r, Cin, Nout, groups, with_res):
+    """BN statistics fused into the tcgen05 convolution epilogue (warp-shuffle column sums per M tile + fixed-order
+    reduction): per-group sum / sum of squares of the OUTPUT against torch on the same output (1e-5), the output itself
+    bit-identical to the plain launch, and bitwise reproducible."""
+    import ctypes
+    import ag2video_b200.spade as sp
+    from ag2video_b200 import _lib as L
+    lib = L.lib()
+    mt, tpg = ctypes.c_int(0), ctypes.c_int(0)
+    if not lib.ag2v_conv3x3_stats_info(B, r, r, Cin, Nout, groups, ctypes.byref(mt), ctypes.byref(tpg)):
+        pytest.skip('this shape runs split-K: statistics stay in their own kernel')
+    g = torch.Generator().manual_seed(B * r + Cin)
+    x = torch.randn(B, Cin, r, r, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Nout, Cin, 3, 3, generator=g) / (3.0 * Cin ** 0.5)).cuda()
+    bias = torch.randn(Nout, generator=g).cuda()
+    scale = (torch.rand(groups, generator=g) + 0.5).cuda()
+    res = torch.randn(B, Nout, r, r, generator=g).cuda().contiguous(memory_format=torch.channels_last) if with_res else None
+    wpk, _ = sp._pack(w, None, None, None, False)
+    Pg = B * r * r // groups
+    outs = []
+    for _ in range(2):
+        out = torch.full((B, Nout, r, r), float('nan'), device='cuda').contiguous(memory_format=torch.channels_last)
+        part = torch.empty(mt.value * 2 * Nout, device='cuda')
+        sums = torch.empty(groups * 2 * Nout, device='cuda', dtype=torch.float64)
+        L.check(lib.ag2v_conv3x3_bias_stats(L.ptr(x), B, r, r, Cin, L.ptr(wpk), L.ptr(bias), Nout, L.ptr(out), 0,
+                                            Pg if groups > 1 else 0, L.ptr(scale), L.ptr(res), groups, L.ptr(part), L.ptr(sums), L.stream()))
+        outs.append((out, sums))
+    (out, sums), (out2, sums2) = outs
+    assert torch.equal(out, out2) and torch.equal(sums, sums2)
+    plain = torch.empty_like(out, memory_format=torch.channels_last)
+    sp._conv(x, (r * r * Cin, r * Cin, Cin), B, r, r, Cin, wpk, bias, Nout, plain, (r * r * Nout, r * Nout, Nout), sp.EPI_BIAS,
+             group_pixels=Pg if groups > 1 else 0, scale=scale, res=res)
+    assert torch.equal(out, plain)
+    og = out.double().view(groups, B // groups, Nout, r, r)
+    want = torch.stack([og.sum(dim=(1, 3, 4)), (og * og).sum(dim=(1, 3, 4))], dim=1).reshape(-1)
+    err = max_rel(sums, want)
+    print('fused BN statistics B=%d r=%d %d->%d groups=%d: %.1e' % (B, r, Cin, Nout, groups, err))
+    assert err <= 1e-5

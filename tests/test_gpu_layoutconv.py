@@ -51,25 +51,36 @@ def test_layout_conv_matches_dense_conv_of_layout(Co, H):
         assert max_rel(a, r) <= 2e-5, (name, max_rel(a, r))
 
 
-def test_fused_generator_equals_unfused():
-    """The whole generator with and without the fused layout->conv path: same weights, same clip."""
+@pytest.mark.parametrize('mode', ['validation_3xtf32', 'product_tf32'])
+def test_fused_generator_equals_unfused(mode):
+    """The whole generator with and without the fused layout->conv path: same weights, same clip, a smooth (MSE) loss.
+    In the 3xTF32 validation mode the two paths differ by fp32 summation order only, so the bars are tight (ADVICE r1);
+    with TF32 operands the 18-layer SPADE stack amplifies the 1e-6 difference of its input and gates flip."""
+    import ag2video_b200.spade as sp
     from ag2video_b200.networks import AG2VideoModel
-    res = []
-    for fuse in (False, True):
-        m = AG2VideoModel(make_opt(64, batch_size=2, fuse_layout_conv=fuse))
-        m.load_state_dict(det_state(m.state_dict(), 3), strict=True)
-        m = m.cuda().to(memory_format=torch.channels_last).train()
-        b = synthetic_batch(B=2, F=4, image_size=64, seed=8, device='cuda')
-        out = m(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
-        loss = (out[0] - b['imgs']).abs().mean() + (out[1] - b['boxes'])[:, 1:].abs().mean()
-        loss.backward()
-        res.append((out[0].detach(), out[2].detach(), float(loss.detach()),
-                    {k: p.grad for k, p in m.named_parameters() if p.grad is not None}))
+    old = sp.CONV_IMPL
+    sp.CONV_IMPL = 3 if mode == 'validation_3xtf32' else 0
+    try:
+        res = []
+        for fuse in (False, True):
+            m = AG2VideoModel(make_opt(64, batch_size=2, fuse_layout_conv=fuse))
+            m.load_state_dict(det_state(m.state_dict(), 3), strict=True)
+            m = m.cuda().to(memory_format=torch.channels_last).train()
+            b = synthetic_batch(B=2, F=4, image_size=64, seed=8, device='cuda')
+            out = m(b['imgs'], b['objs'], b['triplets'], b['actions'], boxes_gt=b['boxes'], use_gt=True)
+            loss = ((out[0] - b['imgs']) ** 2).mean() + ((out[1] - b['boxes'])[:, 1:] ** 2).mean()
+            loss.backward()
+            res.append((out[0].detach(), out[2].detach(), float(loss.detach()),
+                        {k: p.grad for k, p in m.named_parameters() if p.grad is not None}))
+    finally:
+        sp.CONV_IMPL = old
     (i0, f0, l0, g0), (i1, f1, l1, g1) = res
-    print('fused vs unfused: imgs %.2e flows %.2e loss %.2e' % (max_rel(i1, i0), max_rel(f1, f0), abs(l1 - l0) / abs(l0)))
-    assert max_rel(f1, f0) <= 1e-4 and abs(l1 - l0) <= 1e-4 * abs(l0)
-    assert max_rel(i1, i0) <= 5e-3           # TF32 SPADE stack amplifies the 1e-6 input difference
     assert set(g0) == set(g1)
     worst = max((rel_l2(g1[k], g0[k]), k) for k in g0 if float(g0[k].norm()) > 1e-6)
-    print('fused vs unfused: worst gradient rel-L2 %.2e (%s)' % worst)
-    assert worst[0] <= 0.1
+    print('fused vs unfused [%s]: imgs %.2e flows %.2e loss %.2e, worst gradient rel-L2 %.2e (%s)'
+          % (mode, max_rel(i1, i0), max_rel(f1, f0), abs(l1 - l0) / abs(l0), worst[0], worst[1]))
+    assert max_rel(f1, f0) <= 1e-4 and abs(l1 - l0) <= 1e-4 * abs(l0)
+    if mode == 'validation_3xtf32':
+        assert max_rel(i1, i0) <= 2e-3 and worst[0] <= 6e-2       # measured 8.8e-4 / 4.2e-2 (a flipped ReLU gate in the graph model)
+    else:
+        assert max_rel(i1, i0) <= 1e-2 and worst[0] <= 0.1
