@@ -183,6 +183,10 @@ class MetaDiscriminatorModel(nn.Module):
         self.img_discriminator = MultiscaleActionDiscriminator(opt)
         if device is not None:
             self.img_discriminator.to(device)
+        if bool(getattr(opt, 'channels_last', True)):
+            # the PatchGAN stems hand NHWC activations on (K7); NHWC weights keep cuDNN from converting the trunk's
+            # activations and weights back and forth (144 nchwToNhwc / nhwcToNchw launches per iteration in round 1)
+            self.img_discriminator.to(memory_format=torch.channels_last)
         self.img_discriminator.train()
         cuda = next(self.img_discriminator.parameters()).is_cuda
         fused = cuda if fused is None else fused

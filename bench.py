@@ -325,7 +325,7 @@ def gpu_pairs(dev):
         ts.sort()
         return ts[len(ts) // 2]
     ms = ev_time(c1, 10, 3)
-    res['c1'] = {'gpu_ms_per_step': ms, 'gpu_frames_per_s': 8.0 / (ms / 1e3), 'protocol': 'eager (no CUDA graph), median of 10 after 3 warm-up'}
+    res['c1'] = {'gpu_ms_per_step': ms, 'gpu_frames_per_s': 8.0 / (ms / 1e3), 'gpu_protocol': 'eager (no CUDA graph), median of 10 after 3 warm-up'}
     del model
     bb = synthetic_batch(B=16, F=1, image_size=8, seed=1, n_objects=10, with_images=False)
     boxes = bb['boxes'].reshape(16, -1, 4).to(dev)
@@ -348,7 +348,7 @@ def gpu_pairs(dev):
         torch.autograd.grad((o, p_), [obj, pred] + list(layer.parameters()), (o, p_))
     t_gcn = ev_time(c4_gcn, 10, 3)
     res['c4'] = {'gpu_layout_ms_16_frames': t_lay, 'gpu_gcn_layer_ms': t_gcn, 'gpu_ms_16_frames': t_lay + t_gcn,
-                 'protocol': 'K2 fwd+bwd for all 16 frames in one launch each, K1 layer 0 fwd+bwd; median of 10'}
+                 'gpu_protocol': 'K2 fwd+bwd for all 16 frames in one launch each, K1 layer 0 fwd+bwd; median of 10'}
     torch.cuda.empty_cache()
     return res
 
