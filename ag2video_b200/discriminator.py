@@ -49,10 +49,22 @@ class NLayerActionDiscriminator(nn.Module):
         for n, layers in enumerate(seq):
             self.add_module('model%d' % n, nn.Sequential(*layers))
 
+    @staticmethod
+    def _level(sub, x):
+        """One level of the trunk.  [Sequential(conv, InstanceNorm2d), LeakyReLU(0.2)] (discriminator.py:373-380) runs as
+        conv (library, NHWC) -> instance norm + LeakyReLU on the grouped batch-norm kernels (one group per image)."""
+        first = sub[0]
+        if (x.is_cuda and isinstance(first, nn.Sequential) and len(first) == 2 and isinstance(first[1], nn.InstanceNorm2d)
+                and not first[1].affine and not first[1].track_running_stats and len(sub) == 2
+                and isinstance(sub[1], nn.LeakyReLU) and first[0].out_channels % 4 == 0):
+            from .spade import instance_norm_act
+            return instance_norm_act(first[0](x), first[1].eps, sub[1].negative_slope)
+        return sub(x)
+
     def forward(self, x):
         outs = []
         for sub in self.children():
-            x = sub(x)
+            x = self._level(sub, x)
             outs.append(x)
         return outs
 
@@ -60,7 +72,7 @@ class NLayerActionDiscriminator(nn.Module):
         """Levels 1.. given the output of model0 (the stem evaluated elsewhere)."""
         outs = [y]
         for sub in list(self.children())[1:]:
-            y = sub(y)
+            y = self._level(sub, y)
             outs.append(y)
         return outs
 
@@ -186,7 +198,12 @@ class MetaDiscriminatorModel(nn.Module):
         if bool(getattr(opt, 'channels_last', True)):
             # the PatchGAN stems hand NHWC activations on (K7); NHWC weights keep cuDNN from converting the trunk's
             # activations and weights back and forth (144 nchwToNhwc / nhwcToNchw launches per iteration in round 1)
-            self.img_discriminator.to(memory_format=torch.channels_last)
+            # (the stems keep torch's layout: their 3 image channels go through a library convolution that is
+            # faster on NCHW weights, the layout channels through K7)
+            for name, D in self.img_discriminator.named_children():
+                if name.startswith('discriminator'):
+                    for sub in list(D.children())[1:]:
+                        sub.to(memory_format=torch.channels_last)
         self.img_discriminator.train()
         cuda = next(self.img_discriminator.parameters()).is_cuda
         fused = cuda if fused is None else fused

@@ -528,7 +528,7 @@ class _BnActFn(torch.autograd.Function):
     on weight_orig; it is folded into eps (BN(s x; eps) == BN(x; eps / s^2)), never multiplied in."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, in_scale, running_mean, running_var, training, momentum, eps, slope, groups):
+    def forward(ctx, x, weight, bias, in_scale, running_mean, running_var, training, momentum, eps, slope, groups, sync=True):
         L.need_cuda(x, weight, bias)
         lib = L.lib()
         dev = x.device
@@ -548,7 +548,7 @@ class _BnActFn(torch.autograd.Function):
             part = torch.empty(G * lib.ag2v_chan_partial_floats(Pg, C, 2), device=dev, dtype=torch.float32)
             sums = torch.empty(G * 2 * C, device=dev, dtype=torch.float64)
             L.check(lib.ag2v_bn_stats(L.ptr(x), Pg, C, G, L.ptr(part), L.ptr(sums), L.stream()))
-            dist, world = _world()
+            dist, world = _world() if sync else (None, 1)
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
                 count = float(Pg * world)
@@ -562,13 +562,13 @@ class _BnActFn(torch.autograd.Function):
         L.check(lib.ag2v_bn_act_fwd(L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(w), L.ptr(b), Pg, C, G, float(slope), L.ptr(y),
                                     L.stream()))
         ctx.save_for_backward(x, y, mean, rstd, w, sc)
-        ctx.meta = (C, Pg, G, count, training, slope, eps)
+        ctx.meta = (C, Pg, G, count, training, slope, eps, bool(sync))
         return y
 
     @staticmethod
     def backward(ctx, dout):
         x, y, mean, rstd, w, sc = ctx.saved_tensors
-        C, Pg, G, count, training, slope, eps = ctx.meta
+        C, Pg, G, count, training, slope, eps, sync = ctx.meta
         lib = L.lib()
         dev = x.device
         dout = _cl(dout.float())
@@ -589,19 +589,35 @@ class _BnActFn(torch.autograd.Function):
                 dscale = (eps * (r * r * s[:, 3]).sum(dim=1) / s_.view(G) ** 3).float()
             else:            # y = (s x - rm) r0 w + b with r0 = rstd / s:  dy/ds = x r0 w,  x = xhat / rstd + mean
                 dscale = ((r / s_) * (s[:, 3] / r + m * s[:, 2])).sum(dim=1).float()
-        if training:
+        if training and sync:
             dist, world = _world()
             if world > 1:
                 dist.all_reduce(sums, group=_sync_group['group'])
         L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
                                       int(training), Pg, C, G, 0, 0, None, L.stream()))
-        return dx, db[C:], db[:C], dscale, None, None, None, None, None, None, None
+        return dx, db[C:], db[:C], dscale, None, None, None, None, None, None, None, None
 
 
 def bn_act(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5, slope=1.0, groups=1,
-           in_scale=None):
+           in_scale=None, sync=True):
     return _BnActFn.apply(x, weight, bias, in_scale, running_mean, running_var, bool(training), float(momentum), float(eps),
-                          float(slope), int(groups))
+                          float(slope), int(groups), bool(sync))
+
+
+_IN_CONST = {}
+
+
+def instance_norm_act(x, eps=1e-5, slope=1.0):
+    """``leaky_relu(instance_norm(x), slope)`` (nn.InstanceNorm2d(affine=False, track_running_stats=False) followed by
+    nn.LeakyReLU: the PatchGAN trunk, discriminator.py:373-380) on the grouped batch-norm kernels: one statistics group
+    per image, never synchronised across ranks (the statistics are per sample by definition), NHWC in and out."""
+    N, C = x.shape[:2]
+    key = (C, str(x.device))
+    if key not in _IN_CONST:
+        _IN_CONST[key] = (torch.ones(C, device=x.device), torch.zeros(C, device=x.device))
+    one, zero = _IN_CONST[key]
+    scratch_m, scratch_v = torch.zeros(C, device=x.device), torch.ones(C, device=x.device)      # running stats are not tracked
+    return bn_act(x, one, zero, scratch_m, scratch_v, True, 0.0, eps, slope=slope, groups=N, sync=False)
 
 
 class _ParamFreeNorm(nn.Module):
