@@ -71,7 +71,10 @@ extern "C" int ag2v_conv3x3_stats_info(int B, int Hh, int Ww, int Cin, int Nout,
   ConvParams p{};
   p.B = B; p.Hh = Hh; p.Ww = Ww; p.Cin = Cin; p.Nout = Nout;
   int mt = 0, tpg = 0;
-  if (!conv3x3_tc_supported(p, EPI_BIAS) || ag2v_conv3x3_splitk_floats(B, Hh, Ww, Cin, Nout) != 0 ||
+  // Cin < 128: the main loop of a work item (9 * Cin / 32 steps) is shorter than the epilogue with the column sums in
+  // it, and the kernel becomes epilogue-bound (measured on B200, r=256, 64 -> 64: 94 us fused against 51 us + 30 us
+  // for the separate statistics pass; 128 -> 64: 79 us against 90 us) - those layers keep the separate pass.
+  if (Cin < 128 || !conv3x3_tc_supported(p, EPI_BIAS) || ag2v_conv3x3_splitk_floats(B, Hh, Ww, Cin, Nout) != 0 ||
       !conv3x3_tc_stat_geometry(p, groups, &mt, &tpg))
     return 0;
   if (mtiles) *mtiles = mt;

@@ -186,7 +186,7 @@ def test_plain_conv3x3_fc_shape_forward_and_gradients_tol1e3():
     assert max(errs.values()) <= TOL, errs
 
 
-@pytest.mark.parametrize('B,r,Cin,Nout,groups,with_res', [(6, 256, 64, 64, 3, True), (6, 128, 128, 256, 3, False),
+@pytest.mark.parametrize('B,r,Cin,Nout,groups,with_res', [(6, 256, 128, 64, 3, True), (6, 128, 128, 256, 3, False),
                                                          (6, 64, 256, 256, 3, True), (2, 256, 128, 64, 1, False),
                                                          (4, 32, 512, 512, 2, True)])
 def test_conv_epilogue_bn_statistics_tol1e5(B, r, Cin, Nout, groups, with_res):
