@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--no-cudnn-benchmark', action='store_true', help='keep cuDNN heuristics for the out-of-path convolutions')
     ap.add_argument('--generator-only', action='store_true', help='generator fwd+bwd+Adam with an L1 surrogate loss (no discriminator / graph step)')
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--skip-peak', action='store_true', help='do not measure the cuBLAS TF32 peak (ncu launch lists); fractions then use bf16 / 2')
     return ap.parse_args()
 
 
@@ -420,7 +421,13 @@ def run_ours(args):
         pairs['c1']['gpu_over_cpu'] = pairs['c1']['gpu_frames_per_s'] / pairs['c1']['cpu_frames_per_s']
         pairs['c4']['gpu_over_cpu'] = pairs['c4']['cpu_ms_16_frames'] / pairs['c4']['gpu_ms_16_frames']
         cpu_base['pairs'] = pairs
-    tf32 = measure_tf32_peak(dev) if rank == 0 else None
+    tf32 = None
+    if rank == 0:
+        if args.skip_peak:
+            half = peaks()['bf16_tflops_sustained'] / 2.0
+            tf32 = {'tf32_tflops': half, 'tf32_tflops_sustained': half, 'how': 'not measured (--skip-peak): half of the bf16 sustained peak'}
+        else:
+            tf32 = measure_tf32_peak(dev)
 
     torch.manual_seed(0)
     opt = make_opt(args.size, batch_size=args.batch, frames_per_action=args.frames)

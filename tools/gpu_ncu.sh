@@ -4,10 +4,8 @@
 tag=${1:-ncu}
 out=gpurun_out/$tag
 mkdir -p $out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --print-units base --launch-skip ${SKIP:-27000} -c ${COUNT:-11000} \
-    --csv --log-file $out/launches_raw.csv python bench.py --steps 1 --warmup 0 --no-graph --no-cpu-baseline > $out/bench_under_ncu.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --print-units base --launch-skip ${SKIP:-17000} -c ${COUNT:-8500} \
+    --csv --log-file $out/launches_raw.csv python bench.py --steps 1 --warmup 0 --no-graph --no-cpu-baseline --skip-peak > $out/bench_under_ncu.log 2>&1
 python tools/launch_list.py $out/launches_raw.csv > $out/launches_step.csv 2> $out/launch_list.err
 gzip -f $out/launches_raw.csv
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'layout_sconv|layout_fwd_kernel|layout_bwd_kernel|layout_tables' -c 24 \
-    -o $out/k7_k2 python tools/ncu_targets.py disc > $out/ncu_targets.log 2>&1
-head -40 $out/launches_step.csv | cut -c1-150; tail -3 $out/launch_list.err; tail -3 $out/ncu_targets.log; ls -la $out
+head -30 $out/launches_step.csv | cut -c1-150; tail -3 $out/launch_list.err; ls -la $out

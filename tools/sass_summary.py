@@ -30,7 +30,7 @@ def main():
     print('%-86s %6s ' % ('kernel', 'instr') + ' '.join('%8s' % p.replace('[A-Z]*', '*') for p in PATTERNS))
     total = [0] * len(PATTERNS)
     for name, body in sorted(zip(names, blocks)):
-        lines = [l for l in body.splitlines() if re.search(r'/\*[0-9a-f]{4}\*/', l)]
+        lines = [l for l in body.splitlines() if re.search(r'/\*[0-9a-f]{4,}\*/', l)]
         ops = [re.sub(r'^\s*/\*[0-9a-f]+\*/\s*(@!?U?P\d+\s+)?', '', l).split('(')[0].split()[0] if l.strip() else '' for l in lines]
         counts = [sum(1 for o in ops if re.match(p + r'(\.|$|\s|;)', o)) for p in PATTERNS]
         total = [a + b for a, b in zip(total, counts)]
