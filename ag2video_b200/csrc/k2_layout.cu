@@ -235,6 +235,70 @@ layout_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ wx_g
   if (lane == 0) dvecs[task] = acc * scale[n];
 }
 
+// ---- gradient with respect to the boxes (autograd of layout.py:98-130 through grid_sample's grid gradient) ----
+// w(ix) is piecewise linear in the source coordinate ix = 7 * (lin - p0) / extent: slope +1 while only the upper tap
+// is inside the 8-wide source (floor(ix) == -1), -1 while only the lower tap is (floor(ix) == 7), 0 elsewhere; torch
+// computes the same from the tap values of the constant image.  d ix / d p0 = -7 / extent, d ix / d extent =
+// -7 (lin - p0) / extent^2 (the chain of sub, div, *2 - 1 and the (g + 1) / 2 * 7 unnormalisation).
+__device__ __forceinline__ float axis_slope(float lin, float p0, float extent) {
+  float g = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(lin, p0), extent), 2.f), 1.f);
+  float ix = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), 7.f);
+  float fl = floorf(ix);
+  float s = 0.f;
+  if (fl >= -1.f && fl <= 6.f) s += 1.f;
+  if (fl >= 0.f && fl <= 7.f) s -= 1.f;
+  return s;
+}
+
+// One block per (n, o).  Only the border pixels of the object's window (slope != 0 along x or y) contribute; for each
+// of them G = scale * sum_d dout[n,d,y,x] * v[n,o,d].  Thread-strided pixels and a fixed reduction tree: deterministic.
+__global__ void __launch_bounds__(256)
+layout_dboxes_kernel(const float* __restrict__ dout, size_t dout_nstride, const float* __restrict__ vecs,
+                     const float* __restrict__ boxes, const float* __restrict__ lin_x, const float* __restrict__ lin_y,
+                     const float* __restrict__ wx_g, const float* __restrict__ wy_g, const int4* __restrict__ range,
+                     const float* __restrict__ scale, int O, int D, int H, int W, float* __restrict__ dboxes) {
+  extern __shared__ float v_s[];
+  __shared__ float red[8][4];
+  const int no = blockIdx.x, n = no / O;
+  const int4 rg = range[no];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rg.y > rg.x && rg.w > rg.z) {                              // illegal objects have an empty window: zero gradient
+    for (int d = threadIdx.x; d < D; d += blockDim.x) v_s[d] = vecs[(size_t)no * D + d];
+    __syncthreads();
+    const float4 bx = *reinterpret_cast<const float4*>(boxes + (size_t)no * 4);
+    const float sc = scale[n];
+    const float* wx = wx_g + (size_t)no * W;
+    const float* wy = wy_g + (size_t)no * H;
+    // one pixel further than the support on each side: w can be exactly 0 where the slope is not
+    const int xa = max(rg.x - 1, 0), xb = min(rg.y + 1, W), ya = max(rg.z - 1, 0), yb = min(rg.w + 1, H);
+    const int cols = xb - xa, total = cols * (yb - ya);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int y = ya + i / cols, x = xa + i % cols;
+      const float sx = axis_slope(lin_x[x], bx.x, bx.z), sy = axis_slope(lin_y[y], bx.y, bx.w);
+      if (sx == 0.f && sy == 0.f) continue;
+      const float* src = dout + (size_t)n * dout_nstride + (size_t)y * W + x;
+      float g = 0.f;
+      for (int d = 0; d < D; ++d) g = fmaf(src[(size_t)d * H * W], v_s[d], g);
+      g *= sc;
+      const float gx = 7.f * g * wy[y] * sx, gy = 7.f * g * wx[x] * sy;      // dL / d(normalised X), dL / d(normalised Y)
+      acc[0] -= gx / bx.z;
+      acc[2] -= gx * (lin_x[x] - bx.x) / (bx.z * bx.z);
+      acc[1] -= gy / bx.w;
+      acc[3] -= gy * (lin_y[y] - bx.y) / (bx.w * bx.w);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = warp_sum(acc[k]);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 4; ++k) red[threadIdx.x >> 5][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+    dboxes[(size_t)no * 4 + threadIdx.x] = s;
+  }
+}
+
 struct LayoutWs {
   float* wx; float* wy; int4* range; float* scale;
 };
@@ -375,4 +439,23 @@ extern "C" int ag2v_boxes_to_layout_bwd_strided(const float* dout, long long dou
                                                 float* dvecs, cudaStream_t stream) {
   AG2V_REQUIRE(dout_batch_stride >= (long long)D * H * W, "boxes_to_layout_bwd_strided: batch stride smaller than D*H*W");
   return layout_bwd_impl(dout, (size_t)dout_batch_stride, boxes, valid, lin_x, lin_y, N, O, D, H, W, avg, recompute, workspace, dvecs, stream);
+}
+
+// dboxes [N,O,4] = gradient of sum(dout * boxes_to_layout(vecs, boxes)) with respect to the xywh boxes, what autograd
+// gives the reference through grid_sample (layout.py:55-57).  `workspace` is the buffer the forward call filled.
+// dout[n] starts at dout + n * dout_batch_stride floats.  Objects the forward dropped get zero.
+extern "C" int ag2v_boxes_to_layout_dboxes(const float* dout, long long dout_batch_stride, const float* vecs,
+                                           const float* boxes, const float* lin_x, const float* lin_y, int N, int O,
+                                           int D, int H, int W, void* workspace, float* dboxes, cudaStream_t stream) {
+  int rc = layout_check(N, O, D, H, W);
+  if (rc) return rc;
+  if (N == 0 || O == 0) return AG2V_OK;
+  AG2V_REQUIRE(dout && vecs && boxes && lin_x && lin_y && workspace && dboxes, "boxes_to_layout_dboxes: null pointer");
+  AG2V_REQUIRE(dout_batch_stride >= (long long)D * H * W, "boxes_to_layout_dboxes: batch stride smaller than D*H*W");
+  AG2V_REQUIRE(D * sizeof(float) <= 48 * 1024, "boxes_to_layout_dboxes: D=%d too large", D);
+  LayoutWs ws = layout_ws_carve(workspace, N, O, H, W);
+  layout_dboxes_kernel<<<N * O, 256, D * sizeof(float), stream>>>(dout, (size_t)dout_batch_stride, vecs, boxes, lin_x, lin_y,
+                                                                   ws.wx, ws.wy, ws.range, ws.scale, O, D, H, W, dboxes);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
 }

@@ -83,6 +83,72 @@ dense_compose_bwd_kernel(const float* __restrict__ dout, const float* __restrict
   }
 }
 
+// ---- gradients of masks_to_layout with respect to the masks and the boxes (autograd of layout.py:66-95) ----
+// G[o, i] = sum_d v[o, d] * dout[d, i]: the gradient arriving at the sampled plane S[o]
+__global__ void __launch_bounds__(256)
+mask_plane_grad_kernel(const float* __restrict__ dout, const float* __restrict__ vecs, int O, int D, int HW,
+                       float* __restrict__ G) {
+  const int o = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) acc = fmaf(dout[(size_t)d * HW + i], vecs[(size_t)o * D + d], acc);
+    G[(size_t)o * HW + i] = acc;
+  }
+}
+
+// One block per object: scatters G through the four taps into dmasks (atomics: several pixels share a tap, the
+// summation order is not fixed, as in torch's grid_sampler backward) and reduces the grid gradient to dboxes.
+// grid gradient as grid_sampler_2d_backward: gix = sum over taps of (+-) value * y-weight, scaled by (M - 1) / 2.
+__global__ void __launch_bounds__(256)
+mask_sample_bwd_kernel(const float* __restrict__ G, const float* __restrict__ boxes, const float* __restrict__ masks,
+                       const float* __restrict__ lin_x, const float* __restrict__ lin_y, int M, int H, int W,
+                       float* __restrict__ dmasks, float* __restrict__ dboxes) {
+  __shared__ float red[8][4];
+  const int o = blockIdx.x;
+  const float4 bx = *reinterpret_cast<const float4*>(boxes + (size_t)o * 4);
+  const float* mk = masks + (size_t)o * M * M;
+  float* dm = dmasks ? dmasks + (size_t)o * M * M : nullptr;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    const float g = G[(size_t)o * H * W + i];
+    const float gxn = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(lin_x[x], bx.x), bx.z), 2.f), 1.f);
+    const float gyn = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(lin_y[y], bx.y), bx.w), 2.f), 1.f);
+    const Taps t = make_taps(gxn, gyn, M, M);
+    const bool a = t.in_y0 && t.in_x0, b = t.in_y0 && t.in_x1, c = t.in_y1 && t.in_x0, d = t.in_y1 && t.in_x1;
+    if (!(a || b || c || d)) continue;
+    if (dm) {
+      if (a) atomicAdd(dm + t.y0 * M + t.x0, g * t.nw);
+      if (b) atomicAdd(dm + t.y0 * M + t.x0 + 1, g * t.ne);
+      if (c) atomicAdd(dm + (t.y0 + 1) * M + t.x0, g * t.sw);
+      if (d) atomicAdd(dm + (t.y0 + 1) * M + t.x0 + 1, g * t.se);
+    }
+    if (dboxes) {
+      const float nw = a ? mk[t.y0 * M + t.x0] : 0.f, ne = b ? mk[t.y0 * M + t.x0 + 1] : 0.f;
+      const float sw = c ? mk[(t.y0 + 1) * M + t.x0] : 0.f, se = d ? mk[(t.y0 + 1) * M + t.x0 + 1] : 0.f;
+      // the separable weights back out of the products: nw = wx0 * wy0, ne = wx1 * wy0, sw = wx0 * wy1 (wx0 + wx1 = 1)
+      const float wy0 = t.nw + t.ne, wy1 = t.sw + t.se, wx0 = t.nw + t.sw, wx1 = t.ne + t.se;
+      const float gix = g * ((ne - nw) * wy0 + (se - sw) * wy1) * (float)(M - 1);   // dL / d(normalised X) = gix * (M-1)/2 * 2
+      const float giy = g * ((sw - nw) * wx0 + (se - ne) * wx1) * (float)(M - 1);
+      acc[0] -= gix / bx.z;
+      acc[2] -= gix * (lin_x[x] - bx.x) / (bx.z * bx.z);
+      acc[1] -= giy / bx.w;
+      acc[3] -= giy * (lin_y[y] - bx.y) / (bx.w * bx.w);
+    }
+  }
+  if (!dboxes) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = warp_sum(acc[k]);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 4; ++k) red[threadIdx.x >> 5][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+    dboxes[(size_t)o * 4 + threadIdx.x] = s;
+  }
+}
+
 // test mode (layout.py:185-197): objects in ascending order of their sampled mass
 // paint the pixels where their clean mask > 0.5 and nothing has painted before.
 __global__ void mask_order_kernel(const float* __restrict__ vecs, const float* __restrict__ S, int O, int D, int HW,
@@ -173,6 +239,76 @@ __global__ void crop_bwd_kernel(const float* __restrict__ dout, const int* __res
   }
 }
 
+// backend='jj' of crop_bbox (bilinear.py:134-189 bilinear_sample): coordinates stay in [0, 1] and are scaled by the
+// source size, taps are CLAMPED to the image (no zero padding), weights are the distances to the clamped taps, and the
+// four products are summed in the reference's order w1*v1 + w2*v2 + w3*v3 + w4*v4 (v2 is the tap BELOW, v3 to the right).
+struct TapsJJ { int x0, x1, y0, y1; float w1, w2, w3, w4; };
+
+__device__ __forceinline__ TapsJJ make_taps_jj(float X, float Y, int Wsrc, int Hsrc) {
+  TapsJJ t;
+  X = __fmul_rn(X, (float)Wsrc); Y = __fmul_rn(Y, (float)Hsrc);
+  const float x0 = fminf(fmaxf(floorf(X), 0.f), (float)(Wsrc - 1)), x1 = fminf(fmaxf(__fadd_rn(x0, 1.f), 0.f), (float)(Wsrc - 1));
+  const float y0 = fminf(fmaxf(floorf(Y), 0.f), (float)(Hsrc - 1)), y1 = fminf(fmaxf(__fadd_rn(y0, 1.f), 0.f), (float)(Hsrc - 1));
+  t.w1 = __fmul_rn(__fsub_rn(x1, X), __fsub_rn(y1, Y)); t.w2 = __fmul_rn(__fsub_rn(x1, X), __fsub_rn(Y, y0));
+  t.w3 = __fmul_rn(__fsub_rn(X, x0), __fsub_rn(y1, Y)); t.w4 = __fmul_rn(__fsub_rn(X, x0), __fsub_rn(Y, y0));
+  // NaN coordinates: fmaxf / fminf return the non-NaN operand, so the taps stay inside the image (the weights are NaN,
+  // as in the reference)
+  t.x0 = (int)x0; t.x1 = (int)x1; t.y0 = (int)y0; t.y1 = (int)y1;
+  return t;
+}
+
+__device__ __forceinline__ void crop_coords_jj(const float* box, float wsx, float wex, float wsy, float wey, float* X, float* Y) {
+  const float x1 = __fadd_rn(box[0], box[2]), y1 = __fadd_rn(box[1], box[3]);       // xywh_to_points, no [-1, 1] remap
+  *X = __fadd_rn(__fmul_rn(wsx, box[0]), __fmul_rn(wex, x1));
+  *Y = __fadd_rn(__fmul_rn(wsy, box[1]), __fmul_rn(wey, y1));
+}
+
+__global__ void crop_jj_fwd_kernel(const float* __restrict__ feats, const int* __restrict__ frame,
+                                   const float* __restrict__ boxes, const float* __restrict__ ws_x,
+                                   const float* __restrict__ we_x, const float* __restrict__ ws_y,
+                                   const float* __restrict__ we_y, int n_crops, int C, int H, int W, int HH, int WW,
+                                   float* __restrict__ out) {
+  const long long total = (long long)n_crops * HH * WW;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(q % WW), i = (int)((q / WW) % HH), n = (int)(q / ((long long)WW * HH));
+    float X, Y;
+    crop_coords_jj(boxes + (size_t)n * 4, ws_x[j], we_x[j], ws_y[i], we_y[i], &X, &Y);
+    const TapsJJ t = make_taps_jj(X, Y, W, H);
+    const float* src = feats + (size_t)frame[n] * C * H * W;
+    for (int c = 0; c < C; ++c) {
+      const float* pl = src + (size_t)c * H * W;
+      float acc = __fmul_rn(t.w1, pl[t.y0 * W + t.x0]);
+      acc = __fadd_rn(acc, __fmul_rn(t.w2, pl[t.y1 * W + t.x0]));
+      acc = __fadd_rn(acc, __fmul_rn(t.w3, pl[t.y0 * W + t.x1]));
+      acc = __fadd_rn(acc, __fmul_rn(t.w4, pl[t.y1 * W + t.x1]));
+      out[(((size_t)n * C + c) * HH + i) * WW + j] = acc;
+    }
+  }
+}
+
+__global__ void crop_jj_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ frame,
+                                   const float* __restrict__ boxes, const float* __restrict__ ws_x,
+                                   const float* __restrict__ we_x, const float* __restrict__ ws_y,
+                                   const float* __restrict__ we_y, int n_crops, int C, int H, int W, int HH, int WW,
+                                   float* __restrict__ dfeats) {
+  const long long total = (long long)n_crops * HH * WW;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(q % WW), i = (int)((q / WW) % HH), n = (int)(q / ((long long)WW * HH));
+    float X, Y;
+    crop_coords_jj(boxes + (size_t)n * 4, ws_x[j], we_x[j], ws_y[i], we_y[i], &X, &Y);
+    const TapsJJ t = make_taps_jj(X, Y, W, H);
+    float* dst = dfeats + (size_t)frame[n] * C * H * W;
+    for (int c = 0; c < C; ++c) {
+      const float g = dout[(((size_t)n * C + c) * HH + i) * WW + j];
+      float* pl = dst + (size_t)c * H * W;
+      atomicAdd(pl + t.y0 * W + t.x0, g * t.w1);
+      atomicAdd(pl + t.y1 * W + t.x0, g * t.w2);
+      atomicAdd(pl + t.y0 * W + t.x1, g * t.w3);
+      atomicAdd(pl + t.y1 * W + t.x1, g * t.w4);
+    }
+  }
+}
+
 static int blocks_for(long long n, int per = 256, int cap = 148 * 16) {
   long long b = ceil_div_ll(n, per);
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -242,6 +378,47 @@ extern "C" int ag2v_crop_bbox_bwd(const float* dout, const int* frame, const flo
   AG2V_REQUIRE(dout && frame && boxes && ws_x && we_x && ws_y && we_y && dfeats, "crop_bbox_bwd: null pointer");
   crop_bwd_kernel<<<blocks_for((long long)n_crops * HH * WW), 256, 0, stream>>>(dout, frame, boxes, ws_x, we_x, ws_y,
                                                                               we_y, n_crops, C, H, W, HH, WW, dfeats);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// Gradients of masks_to_layout (train mode) with respect to the masks [O,M,M] and the xywh boxes [O,4]; either output
+// may be null.  G = workspace [O,H,W]; dmasks must be zero-initialised by the caller.
+extern "C" int ag2v_masks_to_layout_bwd_inputs(const float* dout, const float* vecs, const float* boxes, const float* masks,
+                                               const float* lin_x, const float* lin_y, int O, int D, int M, int H, int W,
+                                               float* G, float* dmasks, float* dboxes, cudaStream_t stream) {
+  AG2V_REQUIRE(O >= 0 && D > 0 && M > 1 && H > 0 && W > 0, "masks_to_layout_bwd_inputs: bad sizes");
+  if (O == 0 || (!dmasks && !dboxes)) return AG2V_OK;
+  AG2V_REQUIRE(dout && vecs && boxes && masks && lin_x && lin_y && G, "masks_to_layout_bwd_inputs: null pointer");
+  dim3 grid(blocks_for(H * W, 256, 64), O);
+  mask_plane_grad_kernel<<<grid, 256, 0, stream>>>(dout, vecs, O, D, H * W, G);
+  AG2V_LAUNCH_CHECK();
+  mask_sample_bwd_kernel<<<O, 256, 0, stream>>>(G, boxes, masks, lin_x, lin_y, M, H, W, dmasks, dboxes);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// crop_bbox(backend='jj') (bilinear.py:127-128, :134-189): same arguments as ag2v_crop_bbox_fwd / _bwd
+extern "C" int ag2v_crop_bbox_jj_fwd(const float* feats, const int* frame, const float* boxes, const float* ws_x,
+                                     const float* we_x, const float* ws_y, const float* we_y, int n_crops, int C,
+                                     int H, int W, int HH, int WW, float* out, cudaStream_t stream) {
+  AG2V_REQUIRE(n_crops >= 0 && C > 0 && H > 0 && W > 0 && HH > 0 && WW > 0, "crop_bbox_jj: bad sizes");
+  if (n_crops == 0) return AG2V_OK;
+  AG2V_REQUIRE(feats && frame && boxes && ws_x && we_x && ws_y && we_y && out, "crop_bbox_jj: null pointer");
+  crop_jj_fwd_kernel<<<blocks_for((long long)n_crops * HH * WW), 256, 0, stream>>>(feats, frame, boxes, ws_x, we_x, ws_y,
+                                                                                 we_y, n_crops, C, H, W, HH, WW, out);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+extern "C" int ag2v_crop_bbox_jj_bwd(const float* dout, const int* frame, const float* boxes, const float* ws_x,
+                                     const float* we_x, const float* ws_y, const float* we_y, int n_crops, int C,
+                                     int H, int W, int HH, int WW, float* dfeats, cudaStream_t stream) {
+  AG2V_REQUIRE(n_crops >= 0 && C > 0 && H > 0 && W > 0 && HH > 0 && WW > 0, "crop_bbox_jj_bwd: bad sizes");
+  if (n_crops == 0) return AG2V_OK;
+  AG2V_REQUIRE(dout && frame && boxes && ws_x && we_x && ws_y && we_y && dfeats, "crop_bbox_jj_bwd: null pointer");
+  crop_jj_bwd_kernel<<<blocks_for((long long)n_crops * HH * WW), 256, 0, stream>>>(dout, frame, boxes, ws_x, we_x, ws_y,
+                                                                                 we_y, n_crops, C, H, W, HH, WW, dfeats);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

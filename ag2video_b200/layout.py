@@ -43,22 +43,30 @@ class _BoxesToLayoutFn(torch.autograd.Function):
         with L.timed('k2_layout_fwd', 4.0 * N * D * H * W, (N, D, H)):
             L.check(lib.ag2v_boxes_to_layout_fwd(L.ptr(vecs), L.ptr(boxes), L.ptr(valid), L.ptr(lin_x), L.ptr(lin_y),
                                                  N, O, D, H, W, int(avg), L.ptr(ws), L.ptr(out), L.stream()))
-        ctx.save_for_backward(ws)
+        ctx.save_for_backward(ws, vecs, boxes)
         ctx.dims = (N, O, D, H, W, int(avg))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (ws,) = ctx.saved_tensors
+        ws, vecs, boxes = ctx.saved_tensors
         N, O, D, H, W, avg = ctx.dims
         dout = L.f32c(dout)
-        dvecs = torch.zeros(N, O, D, device=dout.device, dtype=torch.float32)
-        with L.timed('k2_layout_bwd', 4.0 * N * D * H * W, (N, D, H)):
-            L.check(L.lib().ag2v_boxes_to_layout_bwd(L.ptr(dout), None, None, None, None, N, O, D, H, W, avg, 0,
-                                                     L.ptr(ws), L.ptr(dvecs), L.stream()))
-        # boxes are data on the training path (meta_models.py:53 passes ground truth
-        # or detached predictions), so no gradient is produced for them.
-        return dvecs, None, None, None, None, None
+        dvecs = dboxes = None
+        if ctx.needs_input_grad[0]:
+            dvecs = torch.zeros(N, O, D, device=dout.device, dtype=torch.float32)
+            with L.timed('k2_layout_bwd', 4.0 * N * D * H * W, (N, D, H)):
+                L.check(L.lib().ag2v_boxes_to_layout_bwd(L.ptr(dout), None, None, None, None, N, O, D, H, W, avg, 0,
+                                                         L.ptr(ws), L.ptr(dvecs), L.stream()))
+        # boxes are data on the training path (meta_models.py:53 passes ground truth or detached predictions);
+        # a caller that does differentiate them gets what autograd gives the reference through grid_sample
+        if ctx.needs_input_grad[1]:
+            dev = dout.device
+            dboxes = torch.zeros(N, O, 4, device=dev, dtype=torch.float32)
+            L.check(L.lib().ag2v_boxes_to_layout_dboxes(L.ptr(dout), D * H * W, L.ptr(vecs), L.ptr(boxes),
+                                                        L.ptr(_linspace(W, dev)), L.ptr(_linspace(H, dev)), N, O, D, H, W,
+                                                        L.ptr(ws), L.ptr(dboxes), L.stream()))
+        return dvecs, dboxes, None, None, None, None
 
 
 def _pooling_flag(pooling):
@@ -83,6 +91,7 @@ def boxes_to_layout(vecs, boxes, H, W=None, pooling='sum'):
     return _BoxesToLayoutFn.apply(vecs.unsqueeze(0), boxes.unsqueeze(0), None, int(H), int(W), avg)
 
 
+L.register('ag2v_boxes_to_layout_dboxes', L.c_i, [L.c_p, ctypes.c_longlong] + [L.c_p] * 4 + [L.c_i] * 5 + [L.c_p] * 2 + [L.c_p])
 L.register('ag2v_boxes_to_layout_fwd_strided', L.c_i, [L.c_p] * 5 + [L.c_i] * 6 + [L.c_p] * 2 + [ctypes.c_longlong, L.c_p])
 L.register('ag2v_boxes_to_layout_bwd_strided', L.c_i, [L.c_p, ctypes.c_longlong] + [L.c_p] * 4 + [L.c_i] * 7 + [L.c_p] * 2 + [L.c_p])
 
@@ -140,6 +149,7 @@ def layout_cat(img, vecs, boxes, valid, H, W=None):
 
 L.register('ag2v_masks_to_layout_fwd', L.c_i, [L.c_p] * 5 + [L.c_i] * 6 + [L.c_p] * 3 + [L.c_p])
 L.register('ag2v_masks_to_layout_bwd', L.c_i, [L.c_p] * 2 + [L.c_i] * 4 + [L.c_p] + [L.c_p])
+L.register('ag2v_masks_to_layout_bwd_inputs', L.c_i, [L.c_p] * 6 + [L.c_i] * 5 + [L.c_p] * 3 + [L.c_p])
 
 
 class _MasksToLayoutFn(torch.autograd.Function):
@@ -156,20 +166,33 @@ class _MasksToLayoutFn(torch.autograd.Function):
         L.check(L.lib().ag2v_masks_to_layout_fwd(L.ptr(vecs), L.ptr(boxes), L.ptr(masks), L.ptr(_linspace(W, dev)),
                                                  L.ptr(_linspace(H, dev)), O, D, M, H, W, int(test_mode), L.ptr(S),
                                                  L.ptr(order), L.ptr(out), L.stream()))
-        ctx.save_for_backward(S)
-        ctx.dims = (O, D, H, W, bool(test_mode))
+        ctx.save_for_backward(S, vecs, boxes, masks)
+        ctx.dims = (O, D, M, H, W, bool(test_mode))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (S,) = ctx.saved_tensors
-        O, D, H, W, test_mode = ctx.dims
+        S, vecs, boxes, masks = ctx.saved_tensors
+        O, D, M, H, W, test_mode = ctx.dims
         if test_mode:
             raise RuntimeError('masks_to_layout(test_mode=True) is an inference-only compositing path')
-        dvecs = torch.zeros(O, D, device=dout.device, dtype=torch.float32)
-        L.check(L.lib().ag2v_masks_to_layout_bwd(L.ptr(L.f32c(dout)), L.ptr(S), O, D, H, W, L.ptr(dvecs), L.stream()))
-        # masks come from data or from a frozen mask head on this path: no gradient for them or the boxes
-        return dvecs, None, None, None, None, None
+        dev = dout.device
+        dout = L.f32c(dout)
+        dvecs = dboxes = dmasks = None
+        if ctx.needs_input_grad[0]:
+            dvecs = torch.zeros(O, D, device=dev, dtype=torch.float32)
+            L.check(L.lib().ag2v_masks_to_layout_bwd(L.ptr(dout), L.ptr(S), O, D, H, W, L.ptr(dvecs), L.stream()))
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            # what autograd gives the reference through F.grid_sample (layout.py:87-91): mask taps and grid gradient
+            if ctx.needs_input_grad[1]:
+                dboxes = torch.zeros(O, 4, device=dev, dtype=torch.float32)
+            if ctx.needs_input_grad[2]:
+                dmasks = torch.zeros(O, M, M, device=dev, dtype=torch.float32)
+            G = torch.empty(max(O, 1), H, W, device=dev, dtype=torch.float32)
+            L.check(L.lib().ag2v_masks_to_layout_bwd_inputs(L.ptr(dout), L.ptr(vecs), L.ptr(boxes), L.ptr(masks),
+                                                            L.ptr(_linspace(W, dev)), L.ptr(_linspace(H, dev)), O, D, M, H, W,
+                                                            L.ptr(G), L.ptr(dmasks), L.ptr(dboxes), L.stream()))
+        return dvecs, dboxes, dmasks, None, None, None
 
 
 def masks_to_layout(vecs, boxes, masks, H, W=None, pooling='sum', test_mode=False):

@@ -124,6 +124,12 @@ int ag2v_boxes_to_layout_bwd_strided(const float* dout, long long dout_batch_str
                                      const uint8_t* valid, const float* lin_x, const float* lin_y, int N, int O, int D,
                                      int H, int W, int avg, int recompute, void* workspace, float* dvecs,
                                      ag2v_stream_t stream);
+/* dboxes [N,O,4]: gradient with respect to the xywh boxes - autograd of _boxes_to_grid and grid_sample's grid
+ * gradient (layout.py:55-57, :119-128); only the border pixels of each object's window contribute.  `workspace` is the
+ * buffer the forward filled; dropped objects get zero. */
+int ag2v_boxes_to_layout_dboxes(const float* dout, long long dout_batch_stride, const float* vecs, const float* boxes,
+                                const float* lin_x, const float* lin_y, int N, int O, int D, int H, int W,
+                                void* workspace, float* dboxes, ag2v_stream_t stream);
 
 /* ---- K4: layout fused into its consumer convolution ----------
  * conv3x3(layout)[co,p] = sum_o sum_k U[o,k,co] * m_o(p+k) with U[o,k,:] = W[:,:,k] v[o,:]: the
@@ -213,6 +219,12 @@ int ag2v_masks_to_layout_fwd(const float* vecs, const float* boxes, const float*
                              int* order, float* out, ag2v_stream_t stream);
 int ag2v_masks_to_layout_bwd(const float* dout, const float* S, int O, int D, int H, int W, float* dvecs,
                              ag2v_stream_t stream);
+/* Gradients of the same call (train mode) with respect to the masks [O,M,M] and the xywh boxes [O,4] - what autograd
+ * gives the reference through F.grid_sample (layout.py:87-91); either output may be null.  G = scratch [O,H,W];
+ * dmasks must be zero-initialised (atomics, like torch's grid_sampler backward). */
+int ag2v_masks_to_layout_bwd_inputs(const float* dout, const float* vecs, const float* boxes, const float* masks,
+                                    const float* lin_x, const float* lin_y, int O, int D, int M, int H, int W, float* G,
+                                    float* dmasks, float* dboxes, ag2v_stream_t stream);
 
 /* crop_bbox (models/bilinear.py:102-131 with tensor_linspace :192-221) over a flat
  * list of crops: feats [NF,C,H,W] NCHW, frame[n] = source image of crop n, boxes
@@ -224,6 +236,14 @@ int ag2v_crop_bbox_fwd(const float* feats, const int* frame, const float* boxes,
 int ag2v_crop_bbox_bwd(const float* dout, const int* frame, const float* boxes, const float* ws_x,
                        const float* we_x, const float* ws_y, const float* we_y, int n_crops, int C, int H, int W,
                        int HH, int WW, float* dfeats, ag2v_stream_t stream);
+/* crop_bbox(backend='jj') (models/bilinear.py:127-128 -> bilinear_sample :134-189): coordinates in [0,1] scaled by the
+ * source size, taps clamped to the image, the reference's weight and summation order.  Arguments as above. */
+int ag2v_crop_bbox_jj_fwd(const float* feats, const int* frame, const float* boxes, const float* ws_x,
+                          const float* we_x, const float* ws_y, const float* we_y, int n_crops, int C, int H, int W,
+                          int HH, int WW, float* out, ag2v_stream_t stream);
+int ag2v_crop_bbox_jj_bwd(const float* dout, const int* frame, const float* boxes, const float* ws_x,
+                          const float* we_x, const float* ws_y, const float* we_y, int n_crops, int C, int H, int W,
+                          int HH, int WW, float* dfeats, ag2v_stream_t stream);
 
 /* ---- K3: SPADE ---------------------------------------------------------------
  * Pieces of SPADE.forward (models/spade_models/networks/normalization.py:96-110),

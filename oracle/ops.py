@@ -174,15 +174,38 @@ def remove_dummy_objects(objs, vocab):
     return (first != 0) & (first != image_id)
 
 
-def crop_bbox(feats, bbox, HH, WW=None):
-    """models/bilinear.py:102-131 ('cudnn' backend) with tensor_linspace
-    (bilinear.py:192-221) and xywh_to_points (models/metrics.py:20-24)."""
+def _sample_clamped(feats, X, Y):
+    """models/bilinear.py:134-189 (bilinear_sample, the 'jj' backend): X, Y [N,HH,WW] in [0,1] scaled by the image
+    size; the four taps are clamped into the image and weighted by their distance to the UNclamped coordinate;
+    summed as w1*v1 + w2*v2 + w3*v3 + w4*v4 with v2 the tap below and v3 the tap to the right."""
+    N, C, H, W = feats.shape
+    X, Y = X * W, Y * H
+    xa = X.floor().clamp(0, W - 1)
+    xb = (xa + 1).clamp(0, W - 1)
+    ya = Y.floor().clamp(0, H - 1)
+    yb = (ya + 1).clamp(0, H - 1)
+    n = torch.arange(N).view(N, 1, 1)
+
+    def tap(yy, xx):                       # feats[n, :, yy, xx] -> [N,C,HH,WW]
+        return feats[n, :, yy.long(), xx.long()].permute(0, 3, 1, 2)
+
+    def wgt(a, b):
+        return (a * b).unsqueeze(1)
+
+    return (wgt(xb - X, yb - Y) * tap(ya, xa) + wgt(xb - X, Y - ya) * tap(yb, xa)
+            + wgt(X - xa, yb - Y) * tap(ya, xb) + wgt(X - xa, Y - ya) * tap(yb, xb))
+
+
+def crop_bbox(feats, bbox, HH, WW=None, backend='cudnn'):
+    """models/bilinear.py:102-131 with tensor_linspace (bilinear.py:192-221) and xywh_to_points
+    (models/metrics.py:20-24); backend 'cudnn' (grid_sample) or 'jj' (bilinear_sample)."""
     WW = HH if WW is None else WW
     N = feats.shape[0]
     pts = bbox.clone()
     pts[:, 2] = bbox[:, 0] + bbox[:, 2]
     pts[:, 3] = bbox[:, 1] + bbox[:, 3]
-    pts = 2 * pts - 1
+    if backend == 'cudnn':
+        pts = 2 * pts - 1
     x0, y0, x1, y1 = pts[:, 0], pts[:, 1], pts[:, 2], pts[:, 3]
 
     def lerp(a, b, steps):
@@ -192,6 +215,8 @@ def crop_bbox(feats, bbox, HH, WW=None):
 
     X = lerp(x0, x1, WW).view(N, 1, WW).expand(N, HH, WW)
     Y = lerp(y0, y1, HH).view(N, HH, 1).expand(N, HH, WW)
+    if backend == 'jj':
+        return _sample_clamped(feats, X, Y)
     return F.grid_sample(feats, torch.stack([X, Y], dim=3), align_corners=True)
 
 

@@ -471,6 +471,44 @@ def cater_case():
     save('cater.pt', out)
 
 
+def inputgrads_case():
+    """The gradients the reference's autograd produces for inputs that are data on the training path - boxes of
+    boxes_to_layout, masks and boxes of masks_to_layout - and crop_bbox with the 'jj' sampling backend
+    (bilinear.py:127-128).  All from the reference's own functions."""
+    from models.bilinear import crop_bbox
+    out = {}
+    boxes_a = torch.tensor([[0.10, 0.20, 0.30, 0.25], [0.00, 0.00, 0.00, 0.00], [0.55, 0.40, 0.219, 0.292],
+                            [0.85, 0.80, 0.30, 0.30], [0.50, 0.50, 0.02, 0.02], [-0.10, 0.30, 0.40, 0.20]])
+    for name, D, H, W, pooling in [('sum32', 8, 32, None, 'sum'), ('rect', 5, 24, 40, 'sum'), ('avg64', 16, 64, None, 'avg')]:
+        vecs = det_tensor('ig.layout.%s' % name, (boxes_a.shape[0], D), 2).requires_grad_()
+        boxes = boxes_a.clone().requires_grad_()
+        res = boxes_to_layout(vecs, boxes, H, W, pooling=pooling)
+        cot = det_tensor('ig.layout.cot.%s' % name, res.shape, 2)
+        (res * cot).sum().backward()
+        out['layout_' + name] = dict(vecs=vecs.detach(), boxes=boxes.detach(), H=H, W=W, pooling=pooling, cot=cot,
+                                     dvecs=vecs.grad.clone(), dboxes=boxes.grad.clone())
+    g = torch.Generator().manual_seed(19)
+    boxes_m = torch.tensor([[0.10, 0.20, 0.30, 0.25], [0.25, 0.30, 0.40, 0.40], [0.55, 0.10, 0.219, 0.292],
+                            [0.05, 0.60, 0.50, 0.30]])
+    for name, M, H in [('m5', 5, 32), ('m16', 16, 48)]:
+        masks = (torch.rand(4, M, M, generator=g) * (torch.rand(4, M, M, generator=g) > 0.3).float()).requires_grad_()
+        vecs = det_tensor('ig.masks.%s' % name, (4, 6), 3).requires_grad_()
+        boxes = boxes_m.clone().requires_grad_()
+        res = masks_to_layout(vecs, boxes, masks, H)
+        cot = det_tensor('ig.masks.cot.%s' % name, res.shape, 3)
+        (res * cot).sum().backward()
+        out['masks_' + name] = dict(vecs=vecs.detach(), boxes=boxes.detach(), masks=masks.detach(), H=H, cot=cot,
+                                    dvecs=vecs.grad.clone(), dboxes=boxes.grad.clone(), dmasks=masks.grad.clone())
+    feats = det_tensor('ig.jj.feats', (5, 3, 20, 28), 4).requires_grad_()
+    bbox = torch.tensor([[0.10, 0.20, 0.30, 0.25], [0.0, 0.0, 1.0, 1.0], [0.55, 0.40, 0.219, 0.292],
+                         [0.85, 0.80, 0.30, 0.30], [-0.10, 0.30, 0.40, 0.20]])       # two boxes leave the image: clamped taps
+    crops = crop_bbox(feats, bbox, 8, 6, backend='jj')
+    cot = det_tensor('ig.jj.cot', crops.shape, 4)
+    (crops * cot).sum().backward()
+    out['crop_jj'] = dict(feats=feats.detach(), bbox=bbox, HH=8, WW=6, crops=crops.detach(), cot=cot, dfeats=feats.grad.clone())
+    save('input_grads.pt', out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['gconv', 'gconv_edge', 'gconv_net', 'layout', 'masks', 'crop', 'spade', 'block',
                              'acts2layout', 'generator', 'losses']

@@ -101,3 +101,33 @@ def test_crop_bbox_batch_config4_golden_tol1e5():
     sum((a * k).sum() for a, k in zip(crops, cots)).backward()
     assert max_rel(imgs.grad[:, :, :, ::8, ::8], c['dimgs_pick']) <= TOL
     assert abs(float(imgs.grad.norm()) - c['dimgs_norm']) <= TOL * c['dimgs_norm']
+
+
+# ---- gradients for inputs that are data on the training path, and the 'jj' sampling backend ------------------
+@pytest.mark.parametrize('name', ['masks_m5', 'masks_m16'])
+def test_masks_to_layout_mask_and_box_gradients_golden_tol1e5(name):
+    """dmasks / dboxes as the reference's autograd produces them through F.grid_sample (tests/golden/input_grads.pt)."""
+    from ag2video_b200.layout import masks_to_layout
+    c = golden('input_grads.pt')[name]
+    vecs, boxes, masks = (c[k].cuda().requires_grad_() for k in ('vecs', 'boxes', 'masks'))
+    out = masks_to_layout(vecs, boxes, masks, c['H'])
+    (out * c['cot'].cuda()).sum().backward()
+    errs = (max_rel(vecs.grad, c['dvecs']), max_rel(boxes.grad, c['dboxes']), max_rel(masks.grad, c['dmasks']))
+    print('masks_to_layout %s: dvecs %.2e dboxes %.2e dmasks %.2e' % ((name,) + errs))
+    assert max(errs) <= TOL
+    # only the inputs that ask for a gradient get one
+    v2 = c['vecs'].cuda().requires_grad_()
+    masks_to_layout(v2, c['boxes'].cuda(), c['masks'].cuda(), c['H']).sum().backward()
+    assert v2.grad is not None
+
+
+def test_crop_bbox_jj_backend_golden_tol1e5():
+    from ag2video_b200.bilinear import crop_bbox
+    c = golden('input_grads.pt')['crop_jj']
+    feats = c['feats'].cuda().requires_grad_()
+    crops = crop_bbox(feats, c['bbox'].cuda(), c['HH'], c['WW'], backend='jj')
+    assert max_rel(crops, c['crops']) <= TOL
+    (crops * c['cot'].cuda()).sum().backward()
+    assert max_rel(feats.grad, c['dfeats']) <= TOL
+    with pytest.raises(ValueError):
+        crop_bbox(feats, c['bbox'].cuda(), 8, backend='other')

@@ -84,3 +84,44 @@ def test_linearity_and_determinism_full_size():
     assert max_rel(lhs, rhs) <= 1e-5
     # checksum: sum over pixels equals sum_o v[o,d] * (sum wy)(sum wx)
     assert torch.isfinite(lhs).all()
+
+
+@pytest.mark.parametrize('name', ['layout_sum32', 'layout_rect', 'layout_avg64'])
+def test_boxes_to_layout_box_gradient_golden_tol1e5(name):
+    """dboxes as the reference's autograd produces it through _boxes_to_grid and grid_sample's grid gradient
+    (tests/golden/input_grads.pt); an all-zero box (dropped by the forward) gets zero."""
+    from ag2video_b200.layout import boxes_to_layout
+    c = golden('input_grads.pt')[name]
+    vecs, boxes = c['vecs'].cuda().requires_grad_(), c['boxes'].cuda().requires_grad_()
+    out = boxes_to_layout(vecs, boxes, c['H'], c['W'], pooling=c['pooling'])
+    (out * c['cot'].cuda()).sum().backward()
+    e_v, e_b = max_rel(vecs.grad, c['dvecs']), max_rel(boxes.grad, c['dboxes'])
+    print('boxes_to_layout %s: dvecs %.2e dboxes %.2e' % (name, e_v, e_b))
+    assert e_v <= TOL and e_b <= TOL
+    assert float(boxes.grad[1].abs().max()) == 0.0
+
+
+def test_boxes_to_layout_box_gradient_full_size_vs_oracle_tol1e5():
+    """D=128, 64x64, 30 (clip, frame) samples of CATER boxes through the batched entry: dboxes of every sample
+    against the CPU oracle's autograd."""
+    from ag2video_b200.layout import boxes_to_layout_batched
+    batch = synthetic_batch(B=2, F=15, image_size=8, seed=12, with_images=False)
+    B, F, O = batch['boxes'].shape[:3]
+    g = torch.Generator().manual_seed(3)
+    vecs = torch.randn(B * F, O, 128, generator=g)
+    cot = torch.randn(B * F, 128, 64, 64, generator=g)
+    boxes = batch['boxes'].reshape(B * F, O, 4).clone()
+    valid = torch.stack([oops.remove_dummy_objects(batch['objs'][i], cater_vocab()) for i in range(B)])
+    valid = valid.unsqueeze(1).expand(B, F, O).reshape(B * F, O)
+    bg = boxes.cuda().requires_grad_()
+    out = boxes_to_layout_batched(vecs.cuda(), bg, valid.cuda(), 64)
+    (out * cot.cuda()).sum().backward()
+    worst = 0.0
+    for n in range(B * F):
+        br = boxes[n][valid[n]].clone().requires_grad_()
+        ref = oops.boxes_to_layout(vecs[n][valid[n]], br, 64)
+        (ref * cot[n:n + 1]).sum().backward()
+        worst = max(worst, max_rel(bg.grad[n][valid[n].cuda()], br.grad))
+        assert float(bg.grad[n][~valid[n].cuda()].abs().max() if (~valid[n]).any() else 0.0) == 0.0
+    print('boxes_to_layout dboxes, 30 samples of 64x64 D=128 vs CPU oracle: %.2e' % worst)
+    assert worst <= TOL

@@ -318,3 +318,34 @@ def test_k2b_config4_oracle_matches_reference():
     crops, flat = oops.crop_bbox_batch(b['imgs'], b['objs'], b['boxes'], 32, vocab=cater_vocab())
     for got, want, gf, wf in zip(crops, g['crop']['crops'], flat, g['crop']['objs_flat']):
         assert max_rel(got, want) <= TOL and torch.equal(gf, wf)
+
+
+# ---- gradients for inputs that are data on the training path, and the 'jj' sampling backend ------------------
+@pytest.mark.parametrize('name', ['layout_sum32', 'layout_rect', 'layout_avg64'])
+def test_boxes_to_layout_box_gradient_matches_reference(name):
+    c = golden('input_grads.pt')[name]
+    vecs, boxes = c['vecs'].clone().requires_grad_(), c['boxes'].clone().requires_grad_()
+    out = oops.boxes_to_layout(vecs, boxes, c['H'], c['W'], pooling=c['pooling'])
+    (out * c['cot']).sum().backward()
+    assert max_rel(vecs.grad, c['dvecs']) <= TOL and max_rel(boxes.grad, c['dboxes']) <= TOL
+    assert float(c['dboxes'].abs().max()) > 0
+
+
+@pytest.mark.parametrize('name', ['masks_m5', 'masks_m16'])
+def test_masks_to_layout_input_gradients_match_reference(name):
+    c = golden('input_grads.pt')[name]
+    vecs, boxes, masks = (c[k].clone().requires_grad_() for k in ('vecs', 'boxes', 'masks'))
+    out = oops.masks_to_layout(vecs, boxes, masks, c['H'])
+    (out * c['cot']).sum().backward()
+    assert max_rel(vecs.grad, c['dvecs']) <= TOL and max_rel(boxes.grad, c['dboxes']) <= TOL
+    assert max_rel(masks.grad, c['dmasks']) <= TOL
+
+
+def test_crop_bbox_jj_backend_matches_reference():
+    """bilinear_sample (bilinear.py:134-189): clamped taps, two boxes reach outside the image."""
+    c = golden('input_grads.pt')['crop_jj']
+    feats = c['feats'].clone().requires_grad_()
+    crops = oops.crop_bbox(feats, c['bbox'], c['HH'], c['WW'], backend='jj')
+    assert max_rel(crops, c['crops']) <= TOL
+    (crops * c['cot']).sum().backward()
+    assert max_rel(feats.grad, c['dfeats']) <= TOL
