@@ -81,7 +81,10 @@ class GraphTripleConv(nn.Module):
         super().__init__()
         assert pooling in ['sum', 'avg'], 'Invalid pooling "%s"' % pooling
         if mlp_normalization != 'none':
-            raise NotImplementedError('the fused layer covers mlp_normalization="none" (the reference default)')
+            # layers.py:13-14 puts BatchNorm1d(hidden) behind a Linear that sees [B, T, features] (graph.py:67-68):
+            # BatchNorm1d reads dim 1 (T) as channels, so the reference itself raises for 'batch' unless T == hidden
+            raise NotImplementedError('mlp_normalization=%r: the reference\'s batched graph layer cannot run it either '
+                                      '(BatchNorm1d on [B, T, features]); only "none" exists' % (mlp_normalization,))
         self.return_new_p_vecs = return_new_p_vecs
         self.hidden_dim = hidden_dim
         self.num_attributes = num_attributes
