@@ -76,6 +76,25 @@ def _world():
     return None, 1
 
 
+def _allreduce_sums(sums, dist, overlap=False):
+    """Sum the per-channel double sums over the data-parallel ranks (sync_batchnorm/batchnorm.py:74-83, :105-145), in
+    place.  One kernel of this library over NVLink peer memory (csrc/k8_peer.cu) where the ranks share a node, the
+    group's own all-reduce otherwise.  overlap=True returns an object whose .wait() orders the current stream after the
+    exchange, so that work which does not need the sums can be enqueued in between."""
+    from . import peer
+    group = _sync_group['group']
+    ex = peer.get(group)
+    if ex is not None and sums.numel() <= ex.cap:
+        if overlap:
+            return ex.allreduce_async(sums)
+        ex.allreduce(sums)
+        return None
+    if overlap:
+        return dist.all_reduce(sums, group=group, async_op=True)
+    dist.all_reduce(sums, group=group)
+    return None
+
+
 def _cl(t):
     return t.contiguous(memory_format=torch.channels_last)
 
@@ -260,7 +279,7 @@ class _SpadeFn(torch.autograd.Function):
             pending = None
             if world > 1:
                 # SyncBN: the sums travel while the shared convolution (which does not need them) runs
-                pending = dist.all_reduce(sums, group=_sync_group['group'], async_op=True)
+                pending = _allreduce_sums(sums, dist, overlap=True)
             count = float(Pg * world)
         _cache_of(mod).forward_begin()
         pk = mod._packed(w_sh, b_sh, w_g, b_g, w_b, b_b)
@@ -318,7 +337,7 @@ class _SpadeFn(torch.autograd.Function):
             dist, world = _world()
             if world > 1:              # db (local sums) is already extracted; the BN backward needs global sums:
                 # they travel while the gamma / beta weight and input gradients (which do not need them) run
-                pending = dist.all_reduce(sums, group=_sync_group['group'], async_op=True)
+                pending = _allreduce_sums(sums, dist, overlap=True)
         a_strides = (r * rw * NHIDDEN, rw * NHIDDEN, NHIDDEN)
         # gamma / beta convolutions: weight gradient, then input gradient gated by the ReLU of actv
         dw_g, dw_b = _wgrad(dgb, 2 * C, actv, a_strides, NHIDDEN, B, r, rw, True, w_g, w_b)
@@ -550,7 +569,7 @@ class _BnActFn(torch.autograd.Function):
             L.check(lib.ag2v_bn_stats(L.ptr(x), Pg, C, G, L.ptr(part), L.ptr(sums), L.stream()))
             dist, world = _world() if sync else (None, 1)
             if world > 1:
-                dist.all_reduce(sums, group=_sync_group['group'])
+                _allreduce_sums(sums, dist)
                 count = float(Pg * world)
             L.check(lib.ag2v_bn_finalize(L.ptr(sums), count, 0.0, C, G, eps, momentum, L.ptr(sc), L.ptr(running_mean),
                                          L.ptr(running_var), L.ptr(mean), L.ptr(rstd), L.stream()))
@@ -592,7 +611,7 @@ class _BnActFn(torch.autograd.Function):
         if training and sync:
             dist, world = _world()
             if world > 1:
-                dist.all_reduce(sums, group=_sync_group['group'])
+                _allreduce_sums(sums, dist)
         L.check(lib.ag2v_spade_bwd_dx(L.ptr(x), L.ptr(dx), L.ptr(mean), L.ptr(rstd), L.ptr(sums), float(count),
                                       int(training), Pg, C, G, 0, 0, None, L.stream()))
         return dx, db[C:], db[:C], dscale, None, None, None, None, None, None, None, None

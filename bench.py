@@ -626,6 +626,8 @@ def run_ours(args):
             sys.stderr.flush()
             os._exit(0)
 
+    from ag2video_b200 import peer
+    peer_status = peer.status()          # 'peer': csrc/k8_peer.cu over NVLink windows; 'group': NCCL all-reduce
     if rank != 0:
         shutdown()
         return
@@ -634,7 +636,8 @@ def run_ours(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 GEMMs / f32 elsewhere', 'data': 'synthetic',
         'config': bench_config(args),
-        'impl_detail': {'conv_impl': args.conv_impl, 'step_execution': mode, 'native_so_sha256': so_sha256()},
+        'impl_detail': {'conv_impl': args.conv_impl, 'step_execution': mode, 'native_so_sha256': so_sha256(),
+                        'syncbn_collective': peer_status},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),

@@ -357,6 +357,22 @@ int ag2v_double_to_float(const double* src, int n, int groups, long long group_s
  * operands are rounded where they are produced; this covers the externally produced segmap) */
 int ag2v_round_tf32(const float* src, float* dst, long long n, ag2v_stream_t stream);
 
+/* ---- K8: SyncBN statistics over NVLink peer memory ------------------------------------------------------------
+ * Replaces the exchange of the per-channel sums between the replicas of SynchronizedBatchNorm
+ * (models/spade_models/networks/sync_batchnorm/batchnorm.py:74-83 forward, :105-145 backward; there a master / slave
+ * queue between device threads, comm.py).  One process per GPU: each rank allocates a window, sends its 64-byte CUDA IPC
+ * handle to the others over any host channel and maps theirs; ag2v_peer_allreduce_f64 is then ONE kernel per rank that
+ * stores the rank's vector into every window, publishes a sequence number and sums the `world` rows in rank order
+ * (bit-identical totals on all ranks).  seq = 1, 2, ... per window set, the same on all ranks; cap even, <= 32768. */
+size_t ag2v_peer_window_bytes(int world, int cap);
+int ag2v_peer_window_alloc(int world, int cap, void** window);
+int ag2v_peer_window_free(void* window);
+int ag2v_peer_window_export(void* window, unsigned char* handle64);
+int ag2v_peer_window_import(const unsigned char* handle64, void** window);
+int ag2v_peer_window_close(void* window);
+int ag2v_peer_allreduce_f64(double* vec, int n, void* const* windows, int rank, int world, int cap, unsigned seq,
+                            ag2v_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

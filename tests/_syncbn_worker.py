@@ -54,5 +54,10 @@ if __name__ == '__main__':
     import ag2video_b200.spade as sp
     sp.set_sync_bn(True)
     torch.save(run(slice(rank, rank + 1)), os.path.join(outdir, 'rank%d.pt' % rank))
+    from ag2video_b200 import peer
+    if os.environ.get('AG2V_EXPECT_PEER') == '1':         # tests/test_gpu_peer.py: the sums must have travelled by peer memory
+        assert peer.status()['collective'] == 'peer', peer.status()
+    else:
+        assert peer.status()['collective'] == 'group', peer.status()
     dist.barrier()
     dist.destroy_process_group()
