@@ -4,6 +4,8 @@
 // One process per GPU.  Every rank owns one window of device memory that all ranks of the node map (CUDA IPC):
 //     data  [kSlots][world][cap] doubles     slot = call number % kSlots, one row per SOURCE rank
 //     flags [kSlots][kMaxChunks][kMaxWorld]  u32, the call number of the last complete row chunk
+//     calls, tickets                         u32, the number of exchanges this rank has finished (device-side, so that
+//                                            a launch captured in a CUDA graph numbers itself correctly on every replay)
 // An exchange is ONE kernel per rank: every CTA owns a chunk of the vector, stores its chunk into the row `rank` of
 // EVERY rank's window (16-byte stores over NVLink / NVSwitch), publishes the call number with a system-scope release
 // store per destination, spins (acquire) until all `world` rows of its own window carry that number, and sums the rows
@@ -28,6 +30,9 @@ constexpr int kThreads = 256;
 
 __host__ __device__ inline size_t data_doubles(int world, int cap) { return (size_t)kSlots * world * cap; }
 __host__ __device__ inline size_t window_bytes(int world, int cap) {
+  return data_doubles(world, cap) * sizeof(double) + (size_t)kSlots * kMaxChunks * kMaxWorld * sizeof(unsigned) + 64;
+}
+__host__ __device__ inline size_t counter_offset(int world, int cap) {
   return data_doubles(world, cap) * sizeof(double) + (size_t)kSlots * kMaxChunks * kMaxWorld * sizeof(unsigned);
 }
 
@@ -35,7 +40,6 @@ struct Args {
   void* win[kMaxWorld];                // window base of every rank, as mapped in THIS process
   double* vec;                         // in: this rank's sums; out: the totals (in place)
   int n, cap, rank, world;
-  unsigned seq;                        // call number, >= 1, identical on all ranks
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -54,7 +58,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 __global__ void __launch_bounds__(kThreads) exchange_kernel(const Args a) {
   const int chunk = blockIdx.x, tid = threadIdx.x;
-  const int slot = a.seq % kSlots;
+  // call number: 1 + the exchanges already finished on this window set.  Launches on one window set are stream-ordered,
+  // every CTA of this launch reads the same value, and the last CTA to leave bumps it for the next launch.
+  unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.win[a.rank]) + counter_offset(a.world, a.cap));
+  const unsigned seq = *reinterpret_cast<volatile unsigned*>(counter) + 1u;
+  const int slot = seq % kSlots;
   const int i0 = chunk * kChunk + 2 * tid;                       // this thread's pair of doubles
   const size_t row = ((size_t)slot * a.world + a.rank) * a.cap;  // where this rank's row lives in every window
   double2 mine = make_double2(0.0, 0.0);
@@ -73,15 +81,15 @@ __global__ void __launch_bounds__(kThreads) exchange_kernel(const Args a) {
   if (tid < a.world) {
     unsigned* f = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.win[tid]) + flag_off) +
                   ((size_t)slot * kMaxChunks + chunk) * kMaxWorld + a.rank;
-    st_release_sys(f, a.seq);
+    st_release_sys(f, seq);
     // now wait for row `tid` of the own window
     const unsigned* g = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(a.win[a.rank]) + flag_off) +
                         ((size_t)slot * kMaxChunks + chunk) * kMaxWorld + tid;
     const unsigned long long t0 = globaltimer_ns();
     unsigned spins = 0;
-    while (ld_acquire_sys(g) != a.seq) {
+    while (ld_acquire_sys(g) != seq) {
       if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 20000000000ull) {
-        printf("ag2v peer exchange: rank %d waited 20 s for rank %d (call %u, chunk %d)\n", a.rank, tid, a.seq, chunk);
+        printf("ag2v peer exchange: rank %d waited 20 s for rank %d (call %u, chunk %d)\n", a.rank, tid, seq, chunk);
         __trap();
       }
     }
@@ -96,6 +104,15 @@ __global__ void __launch_bounds__(kThreads) exchange_kernel(const Args a) {
     }
     a.vec[i0] = s.x;
     if (i0 + 1 < a.n) a.vec[i0 + 1] = s.y;
+  }
+  __syncthreads();                       // every thread of this CTA has read `counter`
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(counter + 1, 1u) == gridDim.x - 1) {           // last CTA of this launch
+      counter[1] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(counter) = seq;
+    }
   }
 }
 
@@ -151,15 +168,16 @@ extern "C" int ag2v_peer_window_close(void* window) {
 }
 
 // In-place sum of vec[0..n) (doubles) over the `world` ranks of a node.  windows[r] = rank r's window as mapped in this
-// process (windows[rank] = the own allocation).  seq = 1, 2, 3, ... counted per window set, identical on all ranks; all
-// ranks must issue the same calls in the same order.  Asynchronous on `stream`; the result is bit-identical on all ranks.
+// process (windows[rank] = the own allocation).  All ranks must issue the same calls on a window set in the same order,
+// and the calls on one window set must be ordered on the device (one stream, or event dependencies): the call number
+// is counted in the window itself, so the launch can be captured in a CUDA graph and replayed.  Asynchronous on
+// `stream`; the result is bit-identical on all ranks.
 extern "C" int ag2v_peer_allreduce_f64(double* vec, int n, void* const* windows, int rank, int world, int cap,
-                                       unsigned seq, cudaStream_t stream) {
+                                       cudaStream_t stream) {
   AG2V_REQUIRE(vec && windows, "peer_allreduce: null pointer");
   AG2V_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "peer_allreduce: rank %d of %d", rank, world);
   AG2V_REQUIRE(ag2v_peer_window_bytes(world, cap) > 0, "peer_allreduce: bad cap %d", cap);
   AG2V_REQUIRE(n >= 0 && n <= cap, "peer_allreduce: n=%d exceeds the window capacity %d", n, cap);
-  AG2V_REQUIRE(seq >= 1, "peer_allreduce: call numbers start at 1");
   AG2V_REQUIRE(((uintptr_t)vec & 7) == 0, "peer_allreduce: vec must be 8-byte aligned");
   if (n == 0 || world == 1) return AG2V_OK;
   Args a{};
@@ -167,7 +185,7 @@ extern "C" int ag2v_peer_allreduce_f64(double* vec, int n, void* const* windows,
     AG2V_REQUIRE(windows[r], "peer_allreduce: window of rank %d is null", r);
     a.win[r] = windows[r];
   }
-  a.vec = vec; a.n = n; a.cap = cap; a.rank = rank; a.world = world; a.seq = seq;
+  a.vec = vec; a.n = n; a.cap = cap; a.rank = rank; a.world = world;
   exchange_kernel<<<ceil_div(n, kChunk), kThreads, 0, stream>>>(a);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;

@@ -25,8 +25,7 @@ L.register('ag2v_peer_window_free', L.c_i, [L.c_p])
 L.register('ag2v_peer_window_export', L.c_i, [L.c_p, ctypes.c_char_p])
 L.register('ag2v_peer_window_import', L.c_i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)])
 L.register('ag2v_peer_window_close', L.c_i, [L.c_p])
-L.register('ag2v_peer_allreduce_f64', L.c_i, [L.c_p, L.c_i, ctypes.POINTER(ctypes.c_void_p), L.c_i, L.c_i, L.c_i,
-                                              ctypes.c_uint, L.c_p])
+L.register('ag2v_peer_allreduce_f64', L.c_i, [L.c_p, L.c_i, ctypes.POINTER(ctypes.c_void_p), L.c_i, L.c_i, L.c_i, L.c_p])
 
 CAP = 16384            # doubles per call: 5 * C * groups of the widest SPADE layer (C = 1024) with room to spare
 CHANNELS = 2           # 0: calls on the caller's stream; 1: calls overlapped with other work on a side stream
@@ -46,7 +45,7 @@ class PeerExchange:
         self.group, self.cap = group, int(cap)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         lib = L.lib()
-        self.own, self.windows, self.seq = [], [], [0] * CHANNELS
+        self.own, self.windows = [], []
         self._imported = []
         handles = []
         for _ in range(CHANNELS):
@@ -93,9 +92,9 @@ class PeerExchange:
         n = vec.numel()
         if n > self.cap:
             raise ValueError('peer all-reduce: %d values exceed the window capacity %d' % (n, self.cap))
-        self.seq[channel] += 1
+        # the call number lives in the window (device side): the launch is CUDA-graph capturable
         L.check(L.lib().ag2v_peer_allreduce_f64(L.ptr(vec), n, self.windows[channel], self.rank, self.world, self.cap,
-                                                self.seq[channel], L.stream()))
+                                                L.stream()))
         return vec
 
     def allreduce_async(self, vec):

@@ -362,15 +362,16 @@ int ag2v_round_tf32(const float* src, float* dst, long long n, ag2v_stream_t str
  * (models/spade_models/networks/sync_batchnorm/batchnorm.py:74-83 forward, :105-145 backward; there a master / slave
  * queue between device threads, comm.py).  One process per GPU: each rank allocates a window, sends its 64-byte CUDA IPC
  * handle to the others over any host channel and maps theirs; ag2v_peer_allreduce_f64 is then ONE kernel per rank that
- * stores the rank's vector into every window, publishes a sequence number and sums the `world` rows in rank order
- * (bit-identical totals on all ranks).  seq = 1, 2, ... per window set, the same on all ranks; cap even, <= 32768. */
+ * stores the rank's vector into every window, publishes its call number and sums the `world` rows in rank order
+ * (bit-identical totals on all ranks).  The call number is counted in the window on the device, so a captured launch
+ * replays correctly; calls on one window set must be device-ordered and identical on all ranks.  cap even, <= 32768. */
 size_t ag2v_peer_window_bytes(int world, int cap);
 int ag2v_peer_window_alloc(int world, int cap, void** window);
 int ag2v_peer_window_free(void* window);
 int ag2v_peer_window_export(void* window, unsigned char* handle64);
 int ag2v_peer_window_import(const unsigned char* handle64, void** window);
 int ag2v_peer_window_close(void* window);
-int ag2v_peer_allreduce_f64(double* vec, int n, void* const* windows, int rank, int world, int cap, unsigned seq,
+int ag2v_peer_allreduce_f64(double* vec, int n, void* const* windows, int rank, int world, int cap,
                             ag2v_stream_t stream);
 
 #ifdef __cplusplus

@@ -10,6 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 SIZES = [1, 2, 7, 511, 512, 513, 2048, 5 * 1024 + 3, 16384, 6, 6, 6, 6, 6, 6]      # the tail cycles through all slots
+GRAPH_SIZES = [2048, 640, 10240]
+GRAPH_REPLAYS = 6
 
 
 def contribution(rank, call, n):
@@ -37,7 +39,26 @@ def main():
             ex.allreduce(v)
         res.append(v.cpu())
     torch.cuda.synchronize()
-    torch.save(res, os.path.join(out, 'peer%d.pt' % rank))
+    # the same launches captured in a CUDA graph and replayed (how bench.py runs the training step): the call number is
+    # counted on the device, so every replay is a new exchange
+    bufs = [torch.zeros(n, dtype=torch.float64, device='cuda') for n in GRAPH_SIZES]
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            ex.allreduce(bufs[0])
+            pending = ex.allreduce_async(bufs[1])
+            ex.allreduce(bufs[2])
+            pending.wait()
+        replays = []
+        for rep in range(GRAPH_REPLAYS):
+            for k, n in enumerate(GRAPH_SIZES):
+                bufs[k].copy_(contribution(rank, 100 + 10 * rep + k, n))
+            g.replay()
+            replays.append([b.cpu() for b in bufs])
+    torch.cuda.synchronize()
+    torch.save(dict(eager=res, graph=replays), os.path.join(out, 'peer%d.pt' % rank))
     dist.barrier()
     ex.close()
     dist.destroy_process_group()

@@ -37,13 +37,21 @@ def test_peer_allreduce_bit_exact_and_identical_on_all_ranks(world, tmp_path):
     import _peer_worker as w
     _spawn('_peer_worker.py', world, tmp_path)
     got = [torch.load(os.path.join(str(tmp_path), 'peer%d.pt' % r), weights_only=False) for r in range(world)]
-    for call, n in enumerate(w.SIZES):
+    def total(call, n):
         want = torch.zeros(n, dtype=torch.float64)
         for r in range(world):                       # rank order, as the kernel sums
             want = want + w.contribution(r, call, n)
+        return want
+
+    for call, n in enumerate(w.SIZES):
         for r in range(world):
-            assert got[r][call].shape == (n,)
-            assert torch.equal(got[r][call], want), 'call %d (n=%d) rank %d' % (call, n, r)
+            assert got[r]['eager'][call].shape == (n,)
+            assert torch.equal(got[r]['eager'][call], total(call, n)), 'call %d (n=%d) rank %d' % (call, n, r)
+    # CUDA-graph replays: every replay is a fresh exchange of that replay's inputs
+    for rep in range(w.GRAPH_REPLAYS):
+        for k, n in enumerate(w.GRAPH_SIZES):
+            for r in range(world):
+                assert torch.equal(got[r]['graph'][rep][k], total(100 + 10 * rep + k, n)), 'replay %d vector %d rank %d' % (rep, k, r)
 
 
 def test_syncbn_over_peer_memory_equals_one_process_tol1e5(tmp_path):
