@@ -362,6 +362,53 @@ __global__ void __launch_bounds__(kSnThreads) specnorm_sigma_bwd_kernel(const __
   }
 }
 
+// sigma mode backward for ONE weight of the list, straight from the gradients of its 1/sigma scales (so that the weight's
+// gradient is complete as soon as its own layer has run its backward - the gradient all-reduce of the data-parallel path
+// can then start layer by layer instead of after a batched kernel at the end of the backward pass):
+//   dW = sum_it coef_it u_it v_it^T,  coef_it = - (dscale_g[it] + sum_j dscale_img[it * ipg + j]) / sigma_it^2
+// (scale = 1 / sigma per frame group; dscale_img is the gradient of the per-image copy of it).
+__global__ void __launch_bounds__(kSnThreads) specnorm_scale_bwd_one_kernel(const __grid_constant__ SnParams P, int ti,
+                                                                            const float* __restrict__ dscale_g,
+                                                                            const float* __restrict__ dscale_img, int ipg) {
+  __shared__ float coef[64];
+  if (threadIdx.x < P.iters) {
+    const int it = threadIdx.x;
+    float d = dscale_g ? dscale_g[it] : 0.f;
+    if (dscale_img)
+      for (int j = 0; j < ipg; ++j) d += dscale_img[it * ipg + j];
+    const float sg = P.sigma[it * P.it_sigma + ti];
+    coef[it] = -d / (sg * sg);
+  }
+  __syncthreads();
+  const SnTensor& T = P.t[ti];
+  const int K = T.cin * T.taps;
+  const long long total = (long long)T.co * K;
+  for (int item = P.itemC[ti] + blockIdx.x; item < P.itemC[ti + 1]; item += gridDim.x) {
+    const long long i0 = (long long)(item - P.itemC[ti]) * kSnChunk;
+    const long long i1 = i0 + kSnChunk < total ? i0 + kSnChunk : total;
+    if ((K & 3) == 0) {
+      for (long long i = i0 + 4 * threadIdx.x; i < i1; i += 4 * kSnThreads) {
+        const int r = (int)(i / K), p = (int)(i - (long long)r * K);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < P.iters; ++it) {
+          const float cu = coef[it] * P.usave[it * P.it_u + T.roff + r];
+          const float4 v4 = *reinterpret_cast<const float4*>(P.vphys + it * P.it_v + T.koff + p);
+          o.x = fmaf(cu, v4.x, o.x); o.y = fmaf(cu, v4.y, o.y); o.z = fmaf(cu, v4.z, o.z); o.w = fmaf(cu, v4.w, o.w);
+        }
+        *reinterpret_cast<float4*>(T.out + i) = o;
+      }
+    } else {
+      for (long long i = i0 + threadIdx.x; i < i1; i += kSnThreads) {
+        const int r = (int)(i / K), p = (int)(i - (long long)r * K);
+        float o = 0.f;
+        for (int it = 0; it < P.iters; ++it)
+          o = fmaf(coef[it] * P.usave[it * P.it_u + T.roff + r], P.vphys[it * P.it_v + T.koff + p], o);
+        T.out[i] = o;
+      }
+    }
+  }
+}
+
 static int fill_params(SnParams& P, int n, const void* const* w, void* const* out, const void* const* g,
                        void* const* u, void* const* v, const int* co, const int* cin, const int* taps,
                        const int* cl, float* save, size_t save_floats, float* scratch, size_t scratch_floats,
@@ -484,6 +531,31 @@ extern "C" int ag2v_spectral_norm_sigma_bwd(int n, const float* dsigma, void* co
   P.eps = 0.f;
   const int items = P.itemC[n];
   specnorm_sigma_bwd_kernel<<<items < 4 * sm_count() ? items : 4 * sm_count(), kSnThreads, 0, stream>>>(P, dsigma);
+  AG2V_LAUNCH_CHECK();
+  return AG2V_OK;
+}
+
+// grad_w = gradient of weight `only` of the list (geometry arrays and `save` describe the WHOLE list of the forward call)
+// from the gradients of its scales: dscale_g [iters] (per frame group) and / or dscale_img [iters * images_per_group]
+// (per image); either may be null.  One launch per weight, issued by that weight's own autograd node.
+extern "C" int ag2v_spectral_norm_scale_bwd_one(int n, int only, const float* dscale_g, const float* dscale_img,
+                                                int images_per_group, void* grad_w, const int* co, const int* cin,
+                                                const int* taps, const int* channels_last, int iters, const float* save,
+                                                size_t save_floats, cudaStream_t stream) {
+  if (int rc = check_arch()) return rc;
+  AG2V_REQUIRE(only >= 0 && only < n && grad_w, "spectral norm: weight %d of %d / null gradient", only, n);
+  AG2V_REQUIRE(dscale_g || dscale_img, "spectral norm: no scale gradient");
+  AG2V_REQUIRE(!dscale_img || images_per_group >= 1, "spectral norm: images_per_group=%d", images_per_group);
+  void* outs[kSnMax];
+  for (int i = 0; i < n && i < kSnMax; ++i) outs[i] = grad_w;        // only entry `only` is written
+  SnParams P;
+  if (int rc = fill_params(P, n, nullptr, outs, nullptr, nullptr, nullptr, co, cin, taps, channels_last,
+                           const_cast<float*>(save), save_floats, nullptr, 0, true, iters, true)) return rc;
+  P.power_iter = 0;
+  P.eps = 0.f;
+  const int items = P.itemC[only + 1] - P.itemC[only];
+  specnorm_scale_bwd_one_kernel<<<items < 4 * sm_count() ? items : 4 * sm_count(), kSnThreads, 0, stream>>>(
+      P, only, dscale_g, dscale_img, images_per_group);
   AG2V_LAUNCH_CHECK();
   return AG2V_OK;
 }

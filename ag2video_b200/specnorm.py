@@ -33,7 +33,16 @@ L.register('ag2v_spectral_norm_sigma_fwd', L.c_i, [L.c_i, _pp, _pp, _pp, _ip, _i
                                                    L.c_i, L.c_f, L.c_p])
 L.register('ag2v_spectral_norm_sigma_bwd', L.c_i, [L.c_i, L.c_p, _pp, _ip, _ip, _ip, _ip, L.c_i, L.c_p, L.c_sz, L.c_p])
 
+L.register('ag2v_spectral_norm_scale_bwd_one', L.c_i, [L.c_i, L.c_i, L.c_p, L.c_p, L.c_i, L.c_p, _ip, _ip, _ip, _ip, L.c_i,
+                                                       L.c_p, L.c_sz, L.c_p])
+
 MAX_PER_LAUNCH = 48
+# Sigma mode, training: every weight gets its own autograd node for the 1/sigma scales (one small launch per weight in
+# the backward) instead of one batched node for all weights.  A batched node runs last, and autograd hands a leaf its
+# gradient only when ALL of its consumers have run - so with it every spectrally normalised weight (two thirds of the
+# generator's gradient bytes) would complete at the very end of the backward pass and the data-parallel gradient
+# all-reduce could not overlap anything (measured on 2 B200s: 1.1 ms of 52.7 ms exposed).
+PER_WEIGHT_SIGMA_GRAD = True
 
 
 def _ptr_array(tensors):
@@ -150,6 +159,32 @@ class _SpectralSigmaFn(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(dws)
 
 
+class _ScaleOfWeight(torch.autograd.Function):
+    """(weight_orig, 1/sigma per image [N], 1/sigma per group [G]) -> (scale [N,1,1,1], scale_g [G]) for ONE weight of a
+    batched sigma call: the values were computed by the batched forward kernel, this node only ties them to the weight.
+    Backward: dW = sum_g coef_g u_g v_g^T with coef_g = -(d scale_g[g] + sum of d scale over the images of g) / sigma_g^2."""
+
+    @staticmethod
+    def forward(ctx, w, inv_img, inv_g, save, geom, index, images_per_group):
+        ctx.save_for_backward(save)
+        ctx.info = (geom, index, images_per_group, inv_g.numel(), w)
+        return inv_img.detach().view(-1, 1, 1, 1), inv_g.detach()
+
+    @staticmethod
+    def backward(ctx, d_img, d_g):
+        (save,) = ctx.saved_tensors
+        (co, cin, taps, cl), index, ipg, iters, w = ctx.info
+        d_img = None if d_img is None else d_img.float().contiguous()
+        d_g = None if d_g is None else d_g.float().contiguous()
+        if d_img is None and d_g is None:
+            return (None,) * 7
+        dw = torch.empty_like(w)
+        L.check(L.lib().ag2v_spectral_norm_scale_bwd_one(len(co), index, L.ptr(d_g), L.ptr(d_img), ipg, L.ptr(dw), _int_array(co),
+                                                         _int_array(cin), _int_array(taps), _int_array(cl), iters, L.ptr(save),
+                                                         save.numel(), L.stream()))
+        return (dw,) + (None,) * 6
+
+
 def spectral_sigmas(weights, us, vs, iters, training=True, eps=1e-12):
     """sigma [iters, n] for lists of weight_orig / weight_u / weight_v."""
     outs = []
@@ -239,6 +274,8 @@ class SpectralNormGroup:
             raise RuntimeError('spectral norm sigma mode: modules disagree on training mode / eps')
         (training, eps), = modes
         trip = [e.tensors() for e in self.entries]
+        if PER_WEIGHT_SIGMA_GRAD and training and torch.is_grad_enabled():
+            return self._refresh_sigma_per_weight(trip, groups, images_per_group, eps)
         sigma = spectral_sigmas([t[0] for t in trip], [t[1] for t in trip], [t[2] for t in trip], groups, training, eps)
         inv = sigma.reciprocal()                                                     # [G, n]
         inv_img = inv.repeat_interleave(images_per_group, dim=0)                     # [N, n]
@@ -246,6 +283,40 @@ class SpectralNormGroup:
         for i, e in enumerate(self.entries):
             e.scale = inv_img[:, i].view(-1, 1, 1, 1)
             e.scale_g = inv_t[i]
+            e.fresh = False
+        return sigma
+
+    def _refresh_sigma_per_weight(self, trip, groups, images_per_group, eps):
+        """The batched forward kernel without an autograd node of its own; one _ScaleOfWeight node per weight."""
+        ws, us, vs = [t[0] for t in trip], [t[1] for t in trip], [t[2] for t in trip]
+        sigmas, chunks = [], []
+        with torch.no_grad():
+            for i in range(0, len(ws), MAX_PER_LAUNCH):
+                j = i + MAX_PER_LAUNCH
+                L.need_cuda(*ws[i:j])
+                geom = _geometry(ws[i:j])
+                save_n, fwd_n, _ = _sizes(*geom[:3])
+                dev = ws[i].device
+                save = torch.empty(groups * save_n, device=dev, dtype=torch.float32)
+                scratch = torch.empty(fwd_n, device=dev, dtype=torch.float32)
+                L.check(L.lib().ag2v_spectral_norm_sigma_fwd(len(ws[i:j]), _ptr_array(ws[i:j]), _ptr_array(us[i:j]), _ptr_array(vs[i:j]),
+                                                             _int_array(geom[0]), _int_array(geom[1]), _int_array(geom[2]),
+                                                             _int_array(geom[3]), groups, L.ptr(save), save.numel(), L.ptr(scratch),
+                                                             fwd_n, 1, float(eps), L.stream()))
+                n = len(ws[i:j])
+                n4 = (n + 3) & ~3
+                sigmas.append(save[:groups * n4].view(groups, n4)[:, :n])
+                chunks.append((save, geom))
+            sigma = sigmas[0].contiguous() if len(sigmas) == 1 else torch.cat(sigmas, dim=1)          # [G, n]
+            inv_t = sigma.reciprocal().t().contiguous()                                                # [n, G]
+            inv_img_t = inv_t.repeat_interleave(images_per_group, dim=1).contiguous()                  # [n, N]
+        for i, e in enumerate(self.entries):
+            save, geom = chunks[i // MAX_PER_LAUNCH]
+            if ws[i].requires_grad:
+                e.scale, e.scale_g = _ScaleOfWeight.apply(ws[i], inv_img_t[i], inv_t[i], save, geom, i % MAX_PER_LAUNCH,
+                                                          images_per_group)
+            else:
+                e.scale, e.scale_g = inv_img_t[i].view(-1, 1, 1, 1), inv_t[i]
             e.fresh = False
         return sigma
 

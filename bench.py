@@ -401,7 +401,10 @@ def run_ours(args):
     # the library convolutions outside the path (cuDNN): let it pick its algorithms during warm-up
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     sp.CONV_IMPL = args.conv_impl
-    if world > 1:
+    # AG2V_DIAG (comma list; diagnosis of the multi-GPU overhead only, reported in impl_detail, never a bench number):
+    #   nosyncbn = per-rank BN statistics, nograd = no gradient all-reduce
+    diag = [d for d in os.environ.get('AG2V_DIAG', '').split(',') if d]
+    if world > 1 and 'nosyncbn' not in diag:
         sp.set_sync_bn(True)
 
     cpu_base, pairs = None, None
@@ -444,7 +447,7 @@ def run_ours(args):
         from ag2video_b200.losses import LossModel
         from ag2video_b200.trainer import Trainer
         discriminator = MetaDiscriminatorModel(opt, dev)
-        trainer = Trainer(opt, model, discriminator, LossModel(opt, discriminator), world=world)
+        trainer = Trainer(opt, model, discriminator, LossModel(opt, discriminator), world=1 if 'nograd' in diag else world)
 
     # a small pool of distinct clips per rank in pinned host memory (disjoint seeds per rank = sharding by clip);
     # keys g_* = the long graph batch of the graph step (no images)
@@ -637,7 +640,7 @@ def run_ours(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 GEMMs / f32 elsewhere', 'data': 'synthetic',
         'config': bench_config(args),
         'impl_detail': {'conv_impl': args.conv_impl, 'step_execution': mode, 'native_so_sha256': so_sha256(),
-                        'syncbn_collective': peer_status},
+                        'syncbn_collective': peer_status, **({'DIAGNOSIS_ONLY': diag} if diag else {})},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),

@@ -195,6 +195,14 @@ int ag2v_spectral_norm_sigma_fwd(int n, const void* const* w, void* const* u, vo
 int ag2v_spectral_norm_sigma_bwd(int n, const float* dsigma, void* const* grad_w, const int* co, const int* cin,
                                  const int* taps, const int* channels_last, int iters, const float* save,
                                  size_t save_floats, ag2v_stream_t stream);
+/* The same gradient for ONE weight (`only`) of the list, straight from the gradients of its 1/sigma scales: dscale_g
+ * [iters] per frame group and / or dscale_img [iters * images_per_group] per image (either may be null); coefficients
+ * -(dscale) / sigma^2.  One launch per weight from that weight's own autograd node, so weight gradients complete layer
+ * by layer and the data-parallel gradient all-reduce overlaps the rest of the backward pass. */
+int ag2v_spectral_norm_scale_bwd_one(int n, int only, const float* dscale_g, const float* dscale_img,
+                                     int images_per_group, void* grad_w, const int* co, const int* cin, const int* taps,
+                                     const int* channels_last, int iters, const float* save, size_t save_floats,
+                                     ag2v_stream_t stream);
 
 /* K6 — 3x3 convolutions with 2-3 output channels at full resolution (the generator's conv_img
  * 64 -> 3 between LeakyReLU(0.2) and tanh, spade_models/networks/generator.py; the flow head
