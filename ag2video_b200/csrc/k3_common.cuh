@@ -46,6 +46,8 @@ struct ConvParams {
   // EPI_BIAS, tcgen05 kernel, no split-K: per-M-tile column sums of the OUTPUT for the batch norm that consumes it
   // (normalization.py:99): stat_part[mtile][0][n] = sum over the tile's pixels of out[p, n], [mtile][1][n] = sum of squares
   float* stat_part;
+  // tcgen05 kernel: {next work index, CTAs done} of the dynamic tile scheduler (set by the launcher)
+  unsigned* sched;
 };
 
 __host__ __device__ inline int gb8_col(int c, int is_beta) { return 16 * (c >> 3) + 8 * is_beta + (c & 7); }

@@ -163,8 +163,13 @@ __device__ __forceinline__ void tile_origin(const TcGeom& gm, int tile, int& x0,
   x0 = tx * gm.Wt; y0 = ty * gm.Ht; b0 = tile * gm.Bt;
 }
 
-// Persistent: grid = min(work items, SMs); every role walks the same static schedule
-// w = blockIdx.x, blockIdx.x + gridDim.x, ...
+// Persistent: grid = min(work items, SMs).  Work items are handed out DYNAMICALLY: the TMA lane takes the next index
+// from a global counter (p.sched[0]) and publishes it to the MMA lane and the four epilogue warps through a 4-deep
+// shared-memory ring (mbarriers sfull / sempty).  With a static schedule (w = blockIdx.x + k * gridDim.x) a CTA that
+// cannot be placed because another kernel holds its SM - NCCL's gradient all-reduce during the backward pass - keeps
+// its share of the tiles waiting and the whole convolution ends only after that other kernel; here the CTAs that run
+// take all the work and a late CTA finds the counter exhausted and leaves.  The last CTA to leave resets the counter.
+constexpr int TC_SCHED = 4;
 template <int MT, int BN, int EPI, bool ROUND_OUT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -178,6 +183,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t bar_full = bars, bar_empty = bars + 8 * S;            // smem ring
   const uint32_t bar_tfull = bars + 16 * S, bar_tempty = bar_tfull + 8 * AS;   // accumulator stages
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem_raw + (bars - raw) + 16 * S + 16 * AS);
+  static_assert(16 * S + 16 * AS + 8 <= 136, "barrier block layout");
+  const uint32_t bar_sfull = bars + 136, bar_sempty = bar_sfull + 8 * TC_SCHED;       // work-item ring
+  volatile int* sched_w = reinterpret_cast<volatile int*>(tc_smem_raw + (bars - raw) + 136 + 16 * TC_SCHED);   // 200..216 of 256
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.Cin / TC_BK;
   const int total = 9 * KC;
@@ -185,6 +193,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int a = 0; a < AS; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    for (int j = 0; j < TC_SCHED; ++j) { mbar_init(bar_sfull + 8 * j, 1); mbar_init(bar_sempty + 8 * j, 5); }   // MMA lane + 4 epilogue warps
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
@@ -197,7 +206,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       uint32_t g_it = 0;
-      for (int w = blockIdx.x; w < gm.work; w += gridDim.x) {
+      for (uint32_t j = 0;; ++j) {
+        int w = (int)atomicAdd(p.sched, 1u);
+        if (w >= gm.work) w = -1;
+        const uint32_t sl = j % TC_SCHED;
+        mbar_wait(bar_sempty + 8 * sl, ((j / TC_SCHED) & 1u) ^ 1u);     // all five readers are done with this ring slot
+        sched_w[sl] = w;
+        mbar_arrive(bar_sfull + 8 * sl);
+        if (w < 0) break;
         const int split = w % gm.ksplit, wt = w / gm.ksplit;
         const int n0 = (wt % gm.ntiles) * BN, mt0 = (wt / gm.ntiles) * MT;
         const int it0 = split * gm.its_per_split, it1 = min(total, it0 + gm.its_per_split);
@@ -223,7 +239,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       uint32_t g_it = 0, a_it = 0;
-      for (int w = blockIdx.x; w < gm.work; w += gridDim.x, ++a_it) {
+      for (;; ++a_it) {
+        const uint32_t sl = a_it % TC_SCHED;
+        mbar_wait(bar_sfull + 8 * sl, (a_it / TC_SCHED) & 1u);
+        const int w = sched_w[sl];
+        mbar_arrive(bar_sempty + 8 * sl);
+        if (w < 0) break;
         const uint32_t as = a_it % AS, aph = (a_it / AS) & 1u;
         const int split = w % gm.ksplit;
         const int it0 = split * gm.its_per_split, it1 = min(total, it0 + gm.its_per_split);
@@ -256,8 +277,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const bool stats = (EPI == EPI_BIAS) && p.stat_part != nullptr;
     const int m = q * 32 + lane;                                       // accumulator row = pixel within the tile
     const int xt = m % gm.Wt, yt = (m / gm.Wt) % gm.Ht, bt = m / (gm.Wt * gm.Ht);
-    uint32_t a_it = 0;
-    for (int w = blockIdx.x; w < gm.work; w += gridDim.x, ++a_it) {
+    for (uint32_t a_it = 0;; ++a_it) {
+      const uint32_t sl = a_it % TC_SCHED;
+      mbar_wait(bar_sfull + 8 * sl, (a_it / TC_SCHED) & 1u);
+      const int w = sched_w[sl];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sempty + 8 * sl);
+      if (w < 0) break;
       const uint32_t as = a_it % AS, aph = (a_it / AS) & 1u;
       const int split = w % gm.ksplit, wt = w / gm.ksplit;
       const int n0 = (wt % gm.ntiles) * BN, mt0 = (wt / gm.ntiles) * MT;
@@ -330,6 +356,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+  if (threadIdx.x == 0 && atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {    // every CTA has taken its last (exhausted) index
+    p.sched[0] = 0; p.sched[1] = 0;
+    __threadfence();
+  }
 }
 
 // Split-K finish: sum the partial tiles in split order (deterministic) and apply the epilogue.
@@ -470,8 +500,30 @@ static int launch_finish(const ConvParams& p, int ksplit, cudaStream_t stream) {
   return AG2V_OK;
 }
 
+// Work counters of the dynamic tile scheduler: {next index, CTAs done} pairs, zero between launches (the kernel resets
+// its pair).  Launches take the pairs round robin, so two launches that might overlap on different streams never share
+// one (a pair comes round again 256 launches later).  One pool per device, allocated on first use.
+static unsigned* sched_pair() {
+  constexpr int kPairs = 256, kMaxDev = 64;
+  static unsigned* pool[kMaxDev] = {};
+  static unsigned next[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  if (!pool[dev]) {
+    unsigned* q = nullptr;
+    if (cudaMalloc(&q, kPairs * 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+    if (cudaMemset(q, 0, kPairs * 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+    cudaDeviceSynchronize();
+    pool[dev] = q;
+  }
+  return pool[dev] + 2 * (next[dev]++ % kPairs);
+}
+
 template <int MT, int BN, int EPI, bool RO>
-static int launch_tc(const ConvParams& p, const TcGeom& g0, cudaStream_t stream) {
+static int launch_tc(const ConvParams& p0, const TcGeom& g0, cudaStream_t stream) {
+  ConvParams p = p0;
+  p.sched = sched_pair();
+  AG2V_REQUIRE(p.sched, "conv3x3_tc: cannot allocate the work counters");
   TcGeom g = g0;
   g.ntiles = ceil_div(p.Nout, BN);
   const int tiles = ceil_div(g.mtiles, MT) * g.ntiles;
