@@ -207,7 +207,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       uint32_t g_it = 0;
       for (uint32_t j = 0;; ++j) {
-        int w = (int)atomicAdd(p.sched, 1u);
+        int w = p.sched ? (int)atomicAdd(p.sched, 1u) : (int)(blockIdx.x + j * gridDim.x);     // null: static round robin
         if (w >= gm.work) w = -1;
         const uint32_t sl = j % TC_SCHED;
         mbar_wait(bar_sempty + 8 * sl, ((j / TC_SCHED) & 1u) ^ 1u);     // all five readers are done with this ring slot
@@ -356,7 +356,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
-  if (threadIdx.x == 0 && atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {    // every CTA has taken its last (exhausted) index
+  if (threadIdx.x == 0 && p.sched && atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {    // every CTA has taken its last (exhausted) index
     p.sched[0] = 0; p.sched[1] = 0;
     __threadfence();
   }
@@ -522,8 +522,9 @@ static unsigned* sched_pair() {
 template <int MT, int BN, int EPI, bool RO>
 static int launch_tc(const ConvParams& p0, const TcGeom& g0, cudaStream_t stream) {
   ConvParams p = p0;
-  p.sched = sched_pair();
-  AG2V_REQUIRE(p.sched, "conv3x3_tc: cannot allocate the work counters");
+  static const bool static_schedule = getenv("AG2V_TC_STATIC") && getenv("AG2V_TC_STATIC")[0] == '1';   // ablation only
+  p.sched = static_schedule ? nullptr : sched_pair();
+  AG2V_REQUIRE(static_schedule || p.sched, "conv3x3_tc: cannot allocate the work counters");
   TcGeom g = g0;
   g.ntiles = ceil_div(p.Nout, BN);
   const int tiles = ceil_div(g.mtiles, MT) * g.ntiles;

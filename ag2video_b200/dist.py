@@ -29,7 +29,15 @@ def init_from_env(backend=None):
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
         if backend == 'nccl':
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device('cuda', local))
+            kw = {}
+            if os.environ.get('AG2V_NCCL_HIGH_PRIORITY', '0') == '1':
+                # Ablation switch.  The compute stream is full of persistent kernels that hold every SM until they
+                # finish, so NCCL's CTAs only get an SM at a kernel boundary; a high-priority NCCL stream was tried to
+                # place them first - no measurable change on 2 B200s (52.9 vs 52.8 ms per step), so it stays off.
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.is_high_priority_stream = True
+                kw['pg_options'] = opts
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device('cuda', local), **kw)
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, local
@@ -66,6 +74,9 @@ class GradBuckets:
     """
 
     def __init__(self, params, bucket_mb=48, group=None, overlap=True):
+        bucket_mb = int(os.environ.get('AG2V_BUCKET_MB', bucket_mb))              # ablation switches
+        overlap = overlap and os.environ.get('AG2V_GRAD_OVERLAP', '1') != '0'
+        self.launched_by_hook = self.launched_at_end = 0
         self.group = group
         self.params = [p for p in params if p.requires_grad]
         self.buckets = []
@@ -98,6 +109,7 @@ class GradBuckets:
                 return
             self._ready[i] += 1
             if self._ready[i] == len(self.buckets[i]) and not self._launched[i]:
+                self.launched_by_hook += 1
                 self._launch(i)
         return hook
 
@@ -149,6 +161,7 @@ class GradBuckets:
             return
         for i in range(len(self.buckets)):
             if not self._launched[i]:
+                self.launched_at_end += 1
                 self._launch(i)
         for work, post in self._works:
             work.wait()

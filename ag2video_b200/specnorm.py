@@ -15,6 +15,7 @@ A module whose weight was not refreshed by the group since its last use (stand-a
 block) refreshes itself through the same kernel, so the per-call contract holds either way.
 """
 import ctypes
+import os
 
 import torch
 from torch.nn.utils.spectral_norm import SpectralNorm
@@ -37,12 +38,14 @@ L.register('ag2v_spectral_norm_scale_bwd_one', L.c_i, [L.c_i, L.c_i, L.c_p, L.c_
                                                        L.c_p, L.c_sz, L.c_p])
 
 MAX_PER_LAUNCH = 48
-# Sigma mode, training: every weight gets its own autograd node for the 1/sigma scales (one small launch per weight in
-# the backward) instead of one batched node for all weights.  A batched node runs last, and autograd hands a leaf its
-# gradient only when ALL of its consumers have run - so with it every spectrally normalised weight (two thirds of the
-# generator's gradient bytes) would complete at the very end of the backward pass and the data-parallel gradient
-# all-reduce could not overlap anything (measured on 2 B200s: 1.1 ms of 52.7 ms exposed).
-PER_WEIGHT_SIGMA_GRAD = True
+# Sigma mode, training: optionally every weight gets its own autograd node for the 1/sigma scales (one small launch per
+# weight in the backward) instead of one batched node for all weights.  A batched node runs last, and autograd hands a
+# leaf its gradient only when ALL of its consumers have run - so with it every spectrally normalised weight (two thirds
+# of the generator's gradient bytes) completes at the very end of the backward pass and its gradient bucket cannot be
+# all-reduced earlier.  Measured on 2 B200s the step time is the same either way (52.6 ms: NCCL's kernels do not get SMs
+# next to the persistent convolutions), so the cheaper batched node stays the default;
+# AG2V_SN_PER_WEIGHT_GRAD=1 selects the per-weight nodes.
+PER_WEIGHT_SIGMA_GRAD = os.environ.get('AG2V_SN_PER_WEIGHT_GRAD', '0') == '1'
 
 
 def _ptr_array(tensors):

@@ -631,6 +631,11 @@ def run_ours(args):
 
     from ag2video_b200 import peer
     peer_status = peer.status()          # 'peer': csrc/k8_peer.cu over NVLink windows; 'group': NCCL all-reduce
+    bucket_stats = None
+    if trainer is not None and getattr(trainer, 'buckets', None):
+        bucket_stats = {k: {'buckets': len(b.buckets), 'mb': round(sum(f.numel() for f in b.flat if f is not None) * 4 / 2**20, 1),
+                            'launched_by_hook': b.launched_by_hook, 'launched_at_end': b.launched_at_end}
+                        for k, b in trainer.buckets.items()}
     if rank != 0:
         shutdown()
         return
@@ -640,7 +645,7 @@ def run_ours(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 GEMMs / f32 elsewhere', 'data': 'synthetic',
         'config': bench_config(args),
         'impl_detail': {'conv_impl': args.conv_impl, 'step_execution': mode, 'native_so_sha256': so_sha256(),
-                        'syncbn_collective': peer_status, **({'DIAGNOSIS_ONLY': diag} if diag else {})},
+                        'syncbn_collective': peer_status, 'gradient_buckets': bucket_stats, **({'DIAGNOSIS_ONLY': diag} if diag else {})},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),

@@ -81,3 +81,38 @@ def test_specnorm_standalone_and_deterministic():
         res.append((m.weight.detach().clone(), m.weight_orig.grad.clone(), m.weight_u.clone()))
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+def test_sigma_mode_per_weight_gradient_nodes_equal_the_batched_node():
+    """Sigma mode (convolutions on weight_orig, outputs scaled by 1/sigma per frame group): the gradient of every
+    weight through its scales is the same whether ONE batched autograd node produces it for all weights or every
+    weight has its own node (specnorm.PER_WEIGHT_SIGMA_GRAD; one launch per weight, so gradients complete layer by
+    layer).  Same u, v, sigma and the same rank-1 sums: 1e-6."""
+    from ag2video_b200 import specnorm
+    torch.manual_seed(3)
+    root = nn.Sequential(spectral_norm(nn.Conv2d(16, 24, 3, padding=1)), spectral_norm(nn.Conv2d(24, 8, 3, padding=1, bias=False)),
+                         spectral_norm(nn.Conv2d(8, 8, 1))).cuda()
+    x = torch.randn(6, 16, 10, 10, device='cuda')                       # 3 frame groups of 2 images
+    cot = torch.randn(6, 8, 10, 10, device='cuda')
+    results = []
+    for per_weight in (False, True):
+        net = copy.deepcopy(root).train()
+        group = specnorm.SpectralNormGroup(net)
+        old = specnorm.PER_WEIGHT_SIGMA_GRAD
+        specnorm.PER_WEIGHT_SIGMA_GRAD = per_weight
+        try:
+            group.refresh_sigma(3, 2)
+            h = specnorm.conv_scaled(net[0], x)                          # per-image scale
+            z, scale_g = specnorm.conv_unscaled(net[1], torch.relu(h))   # per-group scale handed to the consumer
+            h = z * scale_g.repeat_interleave(2).view(-1, 1, 1, 1)
+            y = specnorm.conv_scaled(net[2], torch.relu(h))
+            group.end_sigma()
+            (y * cot).sum().backward()
+        finally:
+            specnorm.PER_WEIGHT_SIGMA_GRAD = old
+        results.append((y.detach(), [m.weight_orig.grad.clone() for m in net], [m.weight_u.clone() for m in net]))
+    (y0, g0, u0), (y1, g1, u1) = results
+    assert torch.equal(y0, y1) and all(torch.equal(a, b) for a, b in zip(u0, u1))
+    worst = max(max_rel(b, a) for a, b in zip(g0, g1))
+    print('per-weight vs batched sigma gradient: %.2e' % worst)
+    assert worst <= 1e-6
