@@ -106,6 +106,10 @@ class MultiscaleActionDiscriminator(nn.Module):
         self.pre_obj_vecs_net = nn.Sequential(nn.Linear(obj_in, emb, bias=False), nn.ReLU(),
                                               nn.Linear(emb, emb, bias=False), nn.ReLU())
         self.fc_objs_vecs = nn.Linear(gdim + opt.semantic_nc, gdim * 2)
+        # the spectral norms of the PatchGAN trunks (torch's pre-forward hooks: ~10 tiny launches per module and call)
+        # run as ONE launch for all trunks per forward call, with the hooks' per-call semantics (csrc/k5_specnorm.cu)
+        from .specnorm import SpectralNormGroup
+        self.__dict__['_sn'] = SpectralNormGroup(self)
 
     def get_obj_vecs(self, objs, layout_boxes, actions_data):
         """discriminator.py:273-313: [B,T,O,gconv_dim]; the object vectors are carried across frames.
@@ -163,6 +167,8 @@ class MultiscaleActionDiscriminator(nn.Module):
         vecs, boxes, valid, tables = cond
         H = self.image_size
         img = img.reshape(-1, *img.shape[2:])
+        if img.is_cuda:
+            self._sn.refresh()             # one power iteration per trunk convolution and call, like the hooks
         nets = [D for name, D in self.named_children() if name.startswith('discriminator')]
         result = []
         if not self.rank1_stem:
