@@ -196,6 +196,15 @@ class SharedSeg:
             self.grad = torch.zeros_like(self.seg, memory_format=torch.channels_last)
         return self.grad
 
+    def grad_buffer_for_full_cover(self):
+        """(buffer, fresh): for a contribution that covers EVERY element of the segmap.  The first such contribution
+        of a backward pass (the full-resolution SPADE layers run their backward first) can be written instead of
+        added, so the buffer is neither zero-filled nor read: fresh = True and the caller must overwrite all of it."""
+        if self.grad is None:
+            self.grad = torch.empty_like(self.seg, memory_format=torch.channels_last)
+            return self.grad, True
+        return self.grad, False
+
     def nearest(self, h, w):
         """``F.interpolate(seg, size=(h, w))`` (nearest, integer ratio) read from the shared copy;
         its gradient goes straight into the shared buffer instead of a full-resolution tensor of
@@ -362,12 +371,18 @@ class _SpadeFn(torch.autograd.Function):
         dw_sh, _ = _wgrad(dactv, NHIDDEN, seg, seg_strides, Lc, B, r, rw, False, w_sh, None)
         dseg = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            full = (Hs == r and Ws == rw)                  # this layer's segmap view is the whole segmap
+            fresh = False
             if shared is not None:
-                buf = shared.grad_buffer()
+                buf, fresh = shared.grad_buffer_for_full_cover() if full else (shared.grad_buffer(), False)
             else:
-                buf = torch.empty(B, Lc, Hs, Ws, device=dev, dtype=torch.float32, memory_format=torch.channels_last).zero_()
+                buf = torch.empty(B, Lc, Hs, Ws, device=dev, dtype=torch.float32, memory_format=torch.channels_last)
+                fresh = full
+                if not full:
+                    buf.zero_()
                 dseg = buf
-            _conv(dactv, a_strides, B, r, rw, NHIDDEN, pkt['w1t'], None, Lc, buf, seg_strides, EPI_ACCUM)
+            # the first full-resolution contribution writes (no zero fill, no read of the buffer), the others add
+            _conv(dactv, a_strides, B, r, rw, NHIDDEN, pkt['w1t'], None, Lc, buf, seg_strides, EPI_BIAS if fresh else EPI_ACCUM)
         dtoken = torch.zeros(1, device=dev) if (shared is not None and ctx.needs_input_grad[2]) else None
         return dx, dseg, dtoken, dw_sh, db_sh, dw_g, db[C:], dw_b, db[:C], None, None, None, None, dscale, None, None, None
 
