@@ -601,18 +601,26 @@ def run_ours(args):
                     'avg_launch_us': ms_ * 1e3 / n_, 'share_of_step': (ms_ / prof_steps) / step_ms}
         # every timed kernel family of the path, with its own bound (K1 / K2 / K4 / K7 / element-wise K3: HBM)
         roof_all = {k: entry(k, *v) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
-        # the dominant kernel = the (kernel, shape) with the largest share of the step
-        key = max(by_shape, key=lambda k: by_shape[k][1])
+        # The dominant kernel = the kernel with the largest share of the step (all its launches: algorithmic work of
+        # every launch / the sum of their durations); `dominant_shape` = its launch shape with the largest share, with
+        # the DRAM traffic of one such launch from the round's `ncu --set full` capture.
+        fam = max(agg, key=lambda k: agg[k][1])
+        roof = entry(fam, *agg[fam])
+        key = max((k for k in by_shape if k[0] == fam), key=lambda k: by_shape[k][1])
         w_, ms_, n_ = by_shape[key]
-        roof = entry(key[0], w_, ms_, n_)
+        shape = entry(key[0], w_, ms_, n_)
         batch_imgs = args.batch * (args.frames - 1)
         tr = ncu_traffic()
         tkey = ' '.join(str(k) for k in key + (batch_imgs,))
+        shape.update({'kernel': '%s (%d images)' % (' '.join(str(k) for k in key), batch_imgs), 'work_per_launch': w_ / n_,
+                      'traffic': tr['launches'].get(tkey)})
+        kernel_names = {'conv3x3': 'conv3x3_tc_kernel', 'wgrad3x3': 'wgrad3x3_tc_kernel'}
         roof.update({
-            'kernel': '%s (%d images)' % (' '.join(str(k) for k in key), batch_imgs),
-            'traffic': tr['launches'].get(tkey), 'traffic_basis': ('dram__bytes_read.sum + dram__bytes_write.sum of one launch, '
-                                                                  'ncu --set full: %s' % tr['source']) if tr['launches'].get(tkey) else None,
-            'work_per_launch': w_ / n_,
+            'kernel': '%s, all %d launches of a step (every shape)' % (kernel_names.get(fam, fam), round(agg[fam][2] / prof_steps)),
+            'dominant_shape': shape,
+            'traffic': shape['traffic'], 'traffic_basis': ('dominant_shape: dram__bytes_read.sum + dram__bytes_write.sum of one launch, '
+                                                          'ncu --set full: %s' % tr['source']) if shape['traffic'] else None,
+            'work_per_launch': agg[fam][0] / agg[fam][2],
             'peak_basis': ('cuBLAS TF32 8192^3 sustained, measured in this run (%.1f TFLOP/s; burst %.1f); MEASURED_PEAKS.json (%s) '
                            'holds bf16 only: %.1f sustained' % (tf32_peak, tf32['tf32_tflops'], pk['source'], pk['bf16_tflops_sustained'])),
             'frac_of_half_bf16_peak': roof['achieved'] / (pk['bf16_tflops_sustained'] / 2.0) if roof['bound'] == 'tensor' else None,
