@@ -55,7 +55,9 @@ def build(verbose=False, force=False):
                 print(log)
     newest = max(os.path.getmtime(o) for o in objs)
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
-        cmd = [NVCC, '-shared', '-o', LIB] + objs   # static cudart; the driver API is reached via cudaGetDriverEntryPoint
+        # static cudart; the driver API is reached via cudaGetDriverEntryPoint.  The arch flag at link time keeps nvcc's
+        # (empty) device-link stub on sm_100a instead of its default architecture.
+        cmd = [NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
