@@ -89,6 +89,14 @@ class GradBuckets:
                 cur, size = [], 0
         if cur:
             self.buckets.append(cur)
+        # AG2V_GRAD_ALLREDUCE=ce: the buckets live in a CUDA-IPC arena and are all-reduced by copy engines + a reduction
+        # kernel (peer.GradientExchange, csrc/k8_peer.cu) instead of NCCL; default: NCCL
+        self.ce = None
+        mode = os.environ.get('AG2V_GRAD_ALLREDUCE', 'nccl')
+        if mode in ('ce', 'ce-force') and self._active() and self.params and self.params[0].is_cuda and \
+                (dist.get_backend(group) == 'nccl' or mode == 'ce-force'):
+            from . import peer
+            self.ce = peer.GradientExchange([sum(p.numel() for p in b) for b in self.buckets], group)
         self.flat = [None] * len(self.buckets)
         self.views = [None] * len(self.buckets)
         self._ready = [0] * len(self.buckets)
@@ -117,7 +125,12 @@ class GradBuckets:
         if self.views[i] is None:
             bucket = self.buckets[i]
             n = sum(p.numel() for p in bucket)
-            self.flat[i] = torch.zeros(n, device=bucket[0].device, dtype=bucket[0].dtype)
+            if self.ce is not None:
+                if bucket[0].dtype != torch.float32:
+                    raise RuntimeError('copy-engine gradient exchange: float32 parameters only')
+                self.flat[i] = self.ce.bucket(i)                       # padded to whole slices; the pad stays zero
+            else:
+                self.flat[i] = torch.zeros(n, device=bucket[0].device, dtype=bucket[0].dtype)
             views, off = [], 0
             for p in bucket:
                 dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)
@@ -131,6 +144,8 @@ class GradBuckets:
         bucket, views = self.buckets[i], self._views(i)
         have = [(v, p.grad) for v, p in zip(views, bucket) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         missing = [v for v, p in zip(views, bucket) if p.grad is None]
+        if self.ce is not None:
+            self.ce.before_fill(i)             # nobody reads the previous contents of this bucket any more
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         if missing:
@@ -138,6 +153,10 @@ class GradBuckets:
         for v, p in zip(views, bucket):
             p.grad = v
         world = dist.get_world_size(self.group)
+        if self.ce is not None:
+            self.ce.exchange(i)                # on the exchange stream, after everything enqueued so far
+            self._launched[i] = True
+            return
         if dist.get_backend(self.group) == 'nccl':
             work = dist.all_reduce(self.flat[i], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             self._works.append((work, None))
@@ -152,6 +171,8 @@ class GradBuckets:
         rank keeps issuing the same sequence)."""
         for work, _ in self._works:
             work.wait()
+        if self.ce is not None:
+            self.ce.finish()
         self._works = []
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
@@ -167,6 +188,8 @@ class GradBuckets:
             work.wait()
             if post is not None:
                 post[0].div_(post[1])
+        if self.ce is not None:
+            self.ce.finish()
         self._works = []
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)

@@ -27,6 +27,12 @@ L.register('ag2v_peer_window_import', L.c_i, [ctypes.c_char_p, ctypes.POINTER(ct
 L.register('ag2v_peer_window_close', L.c_i, [L.c_p])
 L.register('ag2v_peer_allreduce_f64', L.c_i, [L.c_p, L.c_i, ctypes.POINTER(ctypes.c_void_p), L.c_i, L.c_i, L.c_i, L.c_p])
 
+L.register('ag2v_peer_alloc', L.c_i, [L.c_sz, ctypes.POINTER(ctypes.c_void_p)])
+L.register('ag2v_ce_flag_bytes', L.c_sz, [])
+L.register('ag2v_peer_memcpy', L.c_i, [L.c_p, L.c_p, L.c_sz, L.c_p])
+L.register('ag2v_ce_sync', L.c_i, [ctypes.POINTER(ctypes.c_void_p)] + [L.c_i] * 8 + [L.c_p])
+L.register('ag2v_ce_reduce', L.c_i, [L.c_p, L.c_p, L.c_i, ctypes.c_longlong, L.c_f, L.c_i, L.c_p])
+
 CAP = 16384            # doubles per call: 5 * C * groups of the widest SPADE layer (C = 1024) with room to spare
 CHANNELS = 2           # 0: calls on the caller's stream; 1: calls overlapped with other work on a side stream
 
@@ -145,3 +151,116 @@ def get(group=None):
     if ex is None and dist.get_rank(group) == 0:
         warnings.warn('SyncBN statistics travel by the process group\'s all-reduce, not by peer memory: %s' % why)
     return ex
+
+
+class _External:
+    """Device memory of this library seen as a 1-D float32 array (``torch.as_tensor`` maps it without a copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+
+
+class GradientExchange:
+    """All-reduce(avg) of gradient buckets with the copy engines doing the transport (csrc/k8_peer.cu, K8b).
+
+    Every rank owns one exportable arena: the flat buckets (what ``p.grad`` points into), a staging area of
+    (world - 1) slices per bucket, and a flag block.  ``bucket(i)`` is the torch view of flat bucket i;
+    ``before_fill(i)`` goes on the compute stream right before the bucket is overwritten; ``exchange(i)`` enqueues the
+    exchange of bucket i on the exchange stream (after everything enqueued so far on the current stream)."""
+
+    def __init__(self, sizes, group=None, reduce_ctas=64):
+        import torch.distributed as dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if len(sizes) > 64:
+            raise RuntimeError('gradient exchange: at most 64 buckets (got %d)' % len(sizes))
+        quantum = 4 * self.world                                  # slices of whole float4s
+        self.sizes = [(n + quantum - 1) // quantum * quantum for n in sizes]
+        self.slice = [n // self.world for n in self.sizes]
+        self.reduce_ctas = int(reduce_ctas)
+        self.flat_off, self.stage_off, off = [], [], 0
+        for n in self.sizes:
+            self.flat_off.append(off)
+            off += (n + 63) // 64 * 64
+        for sl in self.slice:
+            self.stage_off.append(off)
+            off += ((self.world - 1) * sl + 63) // 64 * 64
+        self.flag_off_bytes = off * 4
+        lib = L.lib()
+        total = self.flag_off_bytes + lib.ag2v_ce_flag_bytes()
+        ptr = ctypes.c_void_p()
+        L.check(lib.ag2v_peer_alloc(total, ctypes.byref(ptr)))
+        self.own = ptr
+        buf = ctypes.create_string_buffer(64)
+        L.check(lib.ag2v_peer_window_export(ptr, buf))
+        mine = dict(host=socket.gethostname(), handle=buf.raw, sizes=self.sizes)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        error, self._imported, self.base = None, [], [None] * self.world
+        if len({e['host'] for e in everyone}) != 1:
+            error = 'ranks on several hosts'
+        elif any(e['sizes'] != self.sizes for e in everyone):
+            error = 'ranks disagree on the bucket sizes'
+        else:
+            try:
+                for r, e in enumerate(everyone):
+                    if r == self.rank:
+                        self.base[r] = ptr.value
+                        continue
+                    q = ctypes.c_void_p()
+                    L.check(lib.ag2v_peer_window_import(e['handle'], ctypes.byref(q)))
+                    self._imported.append(q)
+                    self.base[r] = q.value
+            except RuntimeError as exc:
+                error = str(exc)
+        errors = [None] * self.world
+        dist.all_gather_object(errors, error, group=group)
+        errors = [e for e in errors if e]
+        if errors:
+            self.close()
+            raise RuntimeError('gradient exchange windows unavailable: ' + errors[0])
+        self.flags = (ctypes.c_void_p * self.world)(*[b + self.flag_off_bytes for b in self.base])
+        self.stream = torch.cuda.Stream()
+        self._keep = [_External(self.base[self.rank] + 4 * o, n) for o, n in zip(self.flat_off, self.sizes)]
+        self._buckets = [torch.as_tensor(e, device=torch.device('cuda', torch.cuda.current_device())) for e in self._keep]
+        dist.barrier(group=group)
+
+    def bucket(self, i):
+        return self._buckets[i]
+
+    def _sync(self, i, phase, bump, post, wait, back):
+        L.check(L.lib().ag2v_ce_sync(self.flags, self.rank, self.world, i, phase, bump, post, wait, back, L.stream()))
+
+    def before_fill(self, i):
+        """Count the exchange that starts with this refill and wait until no rank reads the bucket's previous
+        contents any more (phase C of the previous exchange).  On the current (compute) stream."""
+        self._sync(i, 2, 1, 0, 1, 1)
+
+    def exchange(self, i):
+        lib, me, W = L.lib(), self.rank, self.world
+        sl, fo, so = self.slice[i], self.flat_off[i], self.stage_off[i]
+        peers = [r for r in range(W) if r != me]
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            st = L.stream()
+            self._sync(i, 0, 0, 1, 1, 0)                                     # A: every rank's bucket is complete
+            for k, r in enumerate(peers):                                    # my slice of every peer's bucket -> staging
+                L.check(lib.ag2v_peer_memcpy(self.base[me] + 4 * (so + k * sl), self.base[r] + 4 * (fo + me * sl), 4 * sl, st))
+            L.check(lib.ag2v_ce_reduce(self.base[me] + 4 * (fo + me * sl), self.base[me] + 4 * so, W - 1, sl, 1.0 / W,
+                                       self.reduce_ctas, st))
+            self._sync(i, 1, 0, 1, 1, 0)                                     # B: every rank's slice is reduced
+            for r in peers:                                                  # the reduced slices of the others
+                L.check(lib.ag2v_peer_memcpy(self.base[me] + 4 * (fo + r * sl), self.base[r] + 4 * (fo + r * sl), 4 * sl, st))
+            self._sync(i, 2, 0, 1, 0, 0)                                     # C: I no longer read the peers' buckets
+
+    def finish(self):
+        """Order the current stream after every exchange enqueued so far."""
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    def close(self):
+        lib = L.lib()
+        for q in getattr(self, '_imported', []):
+            lib.ag2v_peer_window_close(q)
+        if getattr(self, 'own', None) is not None:
+            lib.ag2v_peer_window_free(self.own)
+        self._imported, self.own = [], None

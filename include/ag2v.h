@@ -382,6 +382,19 @@ int ag2v_peer_window_close(void* window);
 int ag2v_peer_allreduce_f64(double* vec, int n, void* const* windows, int rank, int world, int cap,
                             ag2v_stream_t stream);
 
+/* K8b: gradient all-reduce(avg) with the copy engines doing the transport between CUDA-IPC windows (replaces the NCCL
+ * all-reduce of the data-parallel step when selected; the reference's nn.DataParallel gathers gradients on device 0,
+ * torch/nn/parallel).  ag2v_peer_alloc: exportable device memory (export / import / close / free as for the windows).
+ * Per bucket: ag2v_ce_sync (post + wait on flags carrying the bucket's exchange count, kept on the device),
+ * ag2v_peer_memcpy (cudaMemcpyAsync between mapped windows), ag2v_ce_reduce (own = (own + staged copies) * scale), see
+ * csrc/k8_peer.cu.  Flag block = ag2v_ce_flag_bytes() bytes, zero-initialised, one per rank. */
+int ag2v_peer_alloc(size_t bytes, void** ptr);
+size_t ag2v_ce_flag_bytes(void);
+int ag2v_peer_memcpy(void* dst, const void* src, size_t bytes, ag2v_stream_t stream);
+int ag2v_ce_sync(void* const* flags, int rank, int world, int bucket, int phase, int bump, int post, int wait, int back,
+                 ag2v_stream_t stream);
+int ag2v_ce_reduce(float* own, const float* staged, int parts, long long n, float scale, int ctas, ag2v_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,24 @@ def test_syncbn_over_peer_memory_equals_one_process_tol1e5(tmp_path):
             worst = max(worst, max_rel(ranks[0][op]['grads'][k] + ranks[1][op]['grads'][k], v))
     print('SyncBN over peer memory, 2 ranks x 1 sample vs 1 process x 2 samples: %.2e' % worst)
     assert worst <= 1e-5
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_copy_engine_gradient_exchange_equals_the_mean_over_ranks(world, tmp_path):
+    """GradBuckets with the copy-engine exchange (K8b: cudaMemcpyAsync between IPC windows + one reduction kernel per
+    bucket) on a real backward with hooked bucket launches: every rank ends with the mean of the ranks' gradients
+    (1e-6: float sums in rank order, then * 1/world), identical bits on all ranks, a parameter without gradient gets
+    zeros; three eager steps and three replays of the step captured in a CUDA graph."""
+    import _gradex_worker as w
+    _spawn('_gradex_worker.py', world, tmp_path)
+    got = [torch.load(os.path.join(str(tmp_path), 'gradex%d.pt' % r), weights_only=False) for r in range(world)]
+    assert got[0]['hook'] > 0                      # buckets were exchanged from the backward hooks, not only at the end
+    for s in range(6):
+        for k, shape in enumerate(w.SHAPES):
+            want = sum(w.coefficient(r, s, k, shape) for r in range(world)) / world
+            if k == len(w.SHAPES) - 1:
+                want = torch.zeros(shape)
+            for r in range(world):
+                g = got[r]['results'][s][k]
+                assert torch.equal(g, got[0]['results'][s][k]), 'step %d parameter %d: rank %d differs from rank 0' % (s, k, r)
+                assert max_rel(g, want) <= 1e-6 or float(want.abs().max()) == 0 and float(g.abs().max()) == 0, (s, k, r)
