@@ -221,6 +221,7 @@ class GradientExchange:
             raise RuntimeError('gradient exchange windows unavailable: ' + errors[0])
         self.flags = (ctypes.c_void_p * self.world)(*[b + self.flag_off_bytes for b in self.base])
         self.stream = torch.cuda.Stream()
+        self._pending = False
         self._keep = [_External(self.base[self.rank] + 4 * o, n) for o, n in zip(self.flat_off, self.sizes)]
         self._buckets = [torch.as_tensor(e, device=torch.device('cuda', torch.cuda.current_device())) for e in self._keep]
         dist.barrier(group=group)
@@ -241,6 +242,7 @@ class GradientExchange:
         sl, fo, so = self.slice[i], self.flat_off[i], self.stage_off[i]
         peers = [r for r in range(W) if r != me]
         self.stream.wait_stream(torch.cuda.current_stream())
+        self._pending = True
         with torch.cuda.stream(self.stream):
             st = L.stream()
             self._sync(i, 0, 0, 1, 1, 0)                                     # A: every rank's bucket is complete
@@ -254,8 +256,11 @@ class GradientExchange:
             self._sync(i, 2, 0, 1, 0, 0)                                     # C: I no longer read the peers' buckets
 
     def finish(self):
-        """Order the current stream after every exchange enqueued so far."""
-        torch.cuda.current_stream().wait_stream(self.stream)
+        """Order the current stream after every exchange enqueued so far.  (Only when there is one: inside a CUDA-graph
+        capture a wait on the idle exchange stream would be a dependency from outside the capture.)"""
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self._pending = False
 
     def close(self):
         lib = L.lib()
