@@ -653,7 +653,8 @@ def run_ours(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 GEMMs / f32 elsewhere', 'data': 'synthetic',
         'config': bench_config(args),
         'impl_detail': {'conv_impl': args.conv_impl, 'step_execution': mode, 'native_so_sha256': so_sha256(),
-                        'syncbn_collective': peer_status, 'gradient_buckets': bucket_stats, **({'DIAGNOSIS_ONLY': diag} if diag else {})},
+                        'syncbn_collective': peer_status, 'gradient_buckets': bucket_stats,
+                        'gradient_allreduce': ('copy engines over IPC windows (K8b)' if trainer is not None and getattr(trainer, 'buckets', None) and any(b.ce is not None for b in trainer.buckets.values()) else 'nccl') if world > 1 else None, **({'DIAGNOSIS_ONLY': diag} if diag else {})},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
