@@ -156,3 +156,36 @@ def test_trainer_iteration_two_ranks_equals_one_rank_on_all_clips():
     want = torch.cat([p.detach().flatten() for p in list(model.parameters()) + list(d.parameters())])
     assert torch.equal(res[0], res[1])
     assert (res[0] - want).abs().max() <= 1e-5 * want.abs().max()
+
+
+def _collective_choice_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      AG2V_GRAD_ALLREDUCE='ce')
+    os.environ.pop('AG2V_PEER_SYNCBN', None)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import warnings
+        from ag2video_b200 import peer
+        with warnings.catch_warnings(record=True) as seen:
+            warnings.simplefilter('always')
+            ex = peer.get(None)
+        buckets = GradBuckets([torch.nn.Parameter(torch.zeros(4))])
+        out[rank] = (ex is None, peer.status(), len(seen), buckets.ce is None)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_windows_are_not_used_outside_nccl_groups_and_say_so():
+    """The NVLink peer windows (SyncBN sums, copy-engine gradient exchange) exist for NCCL groups with one GPU per rank.
+    On a gloo group of CPU ranks both stay off, the process group's own all-reduce is used, and the choice is
+    reported (status + one warning on rank 0) instead of being silent."""
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_collective_choice_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    for rank in range(world):
+        is_none, status, warned, no_ce = res[rank]
+        assert is_none and no_ce
+        assert status['collective'] == 'group' and 'gloo' in status['why']
+        assert warned == (1 if rank == 0 else 0)
