@@ -1,4 +1,6 @@
 # A/B on one box at N GPUs: dynamic vs static conv tile schedule, per-weight vs batched spectral-norm sigma gradient.
+# (When profiles/r02_scaling/n2_r2ab_* were taken the per-weight nodes were the default and AG2V_SN_BATCHED_GRAD=1 selected
+# the batched node; the defaults were then set from these runs.)
 N=${1:-2}
 mkdir -p gpurun_out/r2ab
 run() { name=$1; shift
@@ -9,10 +11,10 @@ d=json.loads(open("gpurun_out/r2ab/$name.json").read().strip().splitlines()[-1])
 print("$name", round(d["value"],1), round(d["ms_per_step"],3))
 PY
 }
-run dyn_perw A=1
-run static_perw AG2V_TC_STATIC=1
-run dyn_batched AG2V_SN_BATCHED_GRAD=1
-run static_batched AG2V_TC_STATIC=1 AG2V_SN_BATCHED_GRAD=1
-run dyn_perw_2 A=1
-run static_perw_2 AG2V_TC_STATIC=1
+run dyn_perw AG2V_SN_PER_WEIGHT_GRAD=1
+run static_perw AG2V_TC_STATIC=1 AG2V_SN_PER_WEIGHT_GRAD=1
+run dyn_batched A=1
+run static_batched AG2V_TC_STATIC=1
+run dyn_perw_2 AG2V_SN_PER_WEIGHT_GRAD=1
+run static_perw_2 AG2V_TC_STATIC=1 AG2V_SN_PER_WEIGHT_GRAD=1
 run none AG2V_DIAG=nosyncbn,nograd
